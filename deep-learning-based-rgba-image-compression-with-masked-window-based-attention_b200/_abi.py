@@ -1,0 +1,98 @@
+"""ctypes binding of the C ABI in include/mwa_b200.h (libmwa_b200.so, built in-tree by build.py).
+
+There is no fallback: if the library is missing or a call returns a non-zero status, a Python
+exception is raised.  Tensors cross the boundary as raw device pointers + sizes; the stream is
+torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libmwa_b200.so")
+
+MWA_OK = 0
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/mwa_b200.h one to one
+_SIGNATURES = {
+    "mwa_b200_abi_version": (c_int, []),
+    "mwa_b200_status_string": (c_char_p, [c_int]),
+    "mwa_b200_last_cuda_error": (c_char_p, []),
+    "gdn_param_bytes": (c_int64, [c_int]),
+    "gdn_prepare": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
+    "gdn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "gdn_backward_workspace_bytes": (c_int64, [c_int64, c_int, c_int64]),
+    "gdn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),
+    "mwa_param_bytes": (c_int64, [c_int, c_int, c_int]),
+    "mwa_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                            c_void_p, c_int64, c_void_p]),
+    "mwa_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_int, c_void_p, c_void_p]),
+    "window_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
+    "round_ste_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "quantize_offset_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                        c_int, c_int64, c_void_p]),
+    "lrp_add_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "quantize_levels_forward": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class MwaB200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and type its entry points.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MwaB200Error(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+            "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library drifted apart
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.mwa_b200_abi_version()
+    if got != ABI_VERSION:
+        raise MwaB200Error(f"ABI version mismatch: library {got}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == MWA_OK:
+        return
+    lib = load()
+    msg = lib.mwa_b200_status_string(status).decode()
+    extra = lib.mwa_b200_last_cuda_error().decode() if status == -5 else ""
+    raise MwaB200Error(f"{what} failed: {msg} (status {status}) {extra}".rstrip())
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda_f32(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise MwaB200Error(f"{name} must be a CUDA tensor (got {t.device}); this package is sm_100a-only "
+                           "and has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise MwaB200Error(f"{name} must be float32 (got {t.dtype})")

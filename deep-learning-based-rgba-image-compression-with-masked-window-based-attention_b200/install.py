@@ -1,0 +1,66 @@
+"""Make the reference's own `models/`, `trainRGB.py`, `trainmask.py` run on the B200 modules, unchanged.
+
+The reference imports its hot-path layers by module name:
+    layers/Masked_Attention.py:6   from .masked_win_attention import *
+    layers/Attention.py:6          from .win_attention import *
+    layers/TransformRGB.py:4       from .GDN import *          (also layers/SupplyMask.py:4)
+`install(reference_root)` puts the reference tree on sys.path and pre-seeds `sys.modules` with this
+package's drop-ins under those three names, so every later `import layers.X` / `from .X import *`
+inside the reference resolves to the CUDA-backed modules.  `patch_model_rounding(model_module)`
+swaps the `ste_round` helper the model files define for themselves (models/AutoEncoderRGB_Journal.py:31).
+
+    import mwa_b200; mwa_b200.install("/path/to/reference")
+    from models.AutoEncoderRGB_Journal import AutoEncoder      # the reference's file, our kernels
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+_DROPINS = ("GDN", "masked_win_attention", "win_attention")
+
+
+def install(reference_root: str, extra_paths=()) -> None:
+    reference_root = os.path.abspath(reference_root)
+    if not os.path.isdir(os.path.join(reference_root, "layers")):
+        raise FileNotFoundError(f"{reference_root} does not look like the reference tree (no layers/)")
+    for p in (*extra_paths, reference_root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if "layers" in sys.modules and not _is_reference_layers(sys.modules["layers"], reference_root):
+        raise RuntimeError("a different top-level package named 'layers' is already imported")
+    # A namespace for the reference's `layers` package whose __path__ still points at the reference tree
+    # (so Masked_Attention.py, TransformRGB.py, SupplyMask.py ... load from there) ...
+    if "layers" not in sys.modules:
+        pkg = types.ModuleType("layers")
+        pkg.__path__ = [os.path.join(reference_root, "layers")]
+        pkg.__package__ = "layers"
+        sys.modules["layers"] = pkg
+    # ... but whose three hot-path submodules are ours.
+    ours = importlib.import_module(__package__ + ".layers")
+    for name in _DROPINS:
+        mod = importlib.import_module(f"{__package__}.layers.{name}")
+        sys.modules[f"layers.{name}"] = mod
+        setattr(sys.modules["layers"], name, mod)
+    sys.modules["layers"].__mwa_b200__ = ours
+
+
+def _is_reference_layers(mod, root) -> bool:
+    paths = [os.path.abspath(p) for p in getattr(mod, "__path__", [])]
+    return os.path.join(root, "layers") in paths
+
+
+def patch_model_rounding(model_module) -> None:
+    """Replace the model file's module-level `ste_round` with the CUDA one (same forward value, same gradient)."""
+    from .quant import ste_round
+    if not hasattr(model_module, "ste_round"):
+        raise AttributeError(f"{model_module.__name__} defines no ste_round")
+    model_module.ste_round = ste_round
+
+
+def uninstall() -> None:
+    for name in ("layers",) + tuple(f"layers.{n}" for n in _DROPINS):
+        sys.modules.pop(name, None)

@@ -1,0 +1,139 @@
+"""B200 drop-in for the reference's `layers/GDN.py` (same names, constructor, parameters, forward).
+
+    GDN(ch, inverse=False, beta_min=1e-6, gamma_init=0.1, reparam_offset=2**-18).forward(inputs)
+        y_i = x_i / sqrt(beta_i + sum_j gamma[i, j] * x_j^2)        (inverse: multiplied)
+
+Reference: layers/GDN.py:26-94 (module), :9-23 (LowerBound).  Forward and backward run the
+hand-written sm_100a kernels behind include/mwa_b200.h (`gdn_prepare`, `gdn_forward`,
+`gdn_backward`); CPU tensors are rejected -- there is no fallback.
+State-dict keys: `beta` (C,), `gamma` (C, C) -- identical to the reference.
+"""
+import torch
+import torch.utils.data
+from torch import nn, optim
+from torch.nn import functional as F
+from torch.autograd import Function
+
+from .. import _abi
+from ._params import ParamBlock
+
+
+class LowerBound(Function):
+    """max(inputs, bound) with the reference's pass-through gradient (layers/GDN.py:9-23).
+
+    Elementwise on tiny (C,) / (C, C) parameters; kept in PyTorch so `LowerBound.apply` stays usable
+    by callers.  The GDN kernels apply the same rule internally (gdn_prepare / gdn_backward).
+    """
+
+    @staticmethod
+    def forward(ctx, inputs, bound):
+        b = torch.ones_like(inputs) * bound
+        ctx.save_for_backward(inputs, b)
+        return torch.max(inputs, b)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        inputs, b = ctx.saved_tensors
+        keep = (inputs >= b) | (grad_output < 0)
+        return keep.type(grad_output.dtype) * grad_output, None
+
+
+class _GDNFunction(Function):
+    @staticmethod
+    def forward(ctx, x, beta, gamma, mod):
+        lib = _abi.load()
+        _abi.require_cuda_f32(x, "GDN input")
+        _abi.require_cuda_f32(beta, "GDN.beta")
+        _abi.require_cuda_f32(gamma, "GDN.gamma")
+        B, C = x.shape[0], x.shape[1]
+        if gamma.shape != (C, C) or beta.shape != (C,):
+            raise RuntimeError(f"GDN built for {beta.shape[0]} channels got input with {C}")
+        channels_last = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
+        if not channels_last:
+            x = x.contiguous()
+        hw = x.shape[2] * x.shape[3]
+        with torch.cuda.device(x.device):
+            blk = mod._param_block(beta, gamma)
+            y = torch.empty_like(x)          # preserves the memory format
+            _abi.check(lib.gdn_forward(x.data_ptr(), y.data_ptr(), blk.data_ptr(), B, C, hw, int(mod.inverse),
+                                       int(channels_last), mod.algo, _abi.stream_handle()), "gdn_forward")
+        ctx.mod = mod
+        ctx.channels_last = channels_last
+        ctx.save_for_backward(x, beta, gamma, blk)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _abi.load()
+        x, beta, gamma, blk = ctx.saved_tensors
+        mod = ctx.mod
+        B, C = x.shape[0], x.shape[1]
+        hw = x.shape[2] * x.shape[3]
+        if ctx.channels_last:
+            grad_y = grad_y.contiguous(memory_format=torch.channels_last)
+        else:
+            grad_y = grad_y.contiguous()
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            gb = torch.empty_like(beta)
+            gg = torch.empty_like(gamma)
+            ws_bytes = lib.gdn_backward_workspace_bytes(B, C, hw)
+            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
+            _abi.check(lib.gdn_backward(x.data_ptr(), grad_y.data_ptr(), beta.data_ptr(), gamma.data_ptr(),
+                                        blk.data_ptr(), mod.beta_bound, mod.gamma_bound, gx.data_ptr(),
+                                        gb.data_ptr(), gg.data_ptr(), ws.data_ptr(), ws.numel(), B, C, hw,
+                                        int(mod.inverse), int(ctx.channels_last), _abi.stream_handle()),
+                       "gdn_backward")
+        return gx, gb, gg, None
+
+
+class GDN(nn.Module):
+    """Generalized divisive normalization layer (B200 kernels).
+    y[i] = x[i] / sqrt(beta[i] + sum_j(gamma[i, j] * x[j]^2))
+    """
+
+    def __init__(self,
+                 ch,
+                 inverse=False,
+                 beta_min=1e-6,
+                 gamma_init=0.1,
+                 reparam_offset=2**-18,
+                 ):
+        super(GDN, self).__init__()
+        self.inverse = inverse
+        self.beta_min = beta_min
+        self.gamma_init = gamma_init
+        self.reparam_offset = reparam_offset
+        self.algo = _abi.ALGO_AUTO
+        self._blk = ParamBlock()
+        self.build(ch)
+
+    def build(self, ch):
+        self.pedestal = self.reparam_offset ** 2
+        self.beta_bound = (self.beta_min + self.reparam_offset ** 2) ** 0.5
+        self.gamma_bound = self.reparam_offset
+        self.beta = nn.Parameter(torch.sqrt(torch.ones(ch) + self.pedestal))
+        self.gamma = nn.Parameter(torch.sqrt(self.gamma_init * torch.eye(ch) + self.pedestal))
+
+    def _param_block(self, beta, gamma):
+        lib = _abi.load()
+        C = beta.shape[0]
+        nbytes = int(lib.gdn_param_bytes(C))
+
+        def fill(blk):
+            _abi.check(lib.gdn_prepare(beta.data_ptr(), gamma.data_ptr(), C, self.beta_bound, self.gamma_bound,
+                                       self.pedestal, blk.data_ptr(), blk.numel(), _abi.stream_handle()),
+                       "gdn_prepare")
+
+        return self._blk.get((beta, gamma), nbytes, fill)
+
+    def forward(self, inputs):
+        unfold = False
+        if inputs.dim() == 5:
+            unfold = True
+            bs, ch, d, w, h = inputs.size()
+            inputs = inputs.view(bs, ch, d * w, h)
+        outputs = _GDNFunction.apply(inputs, self.beta, self.gamma, self)
+        if unfold:
+            outputs = outputs.view(bs, ch, d, w, h)
+        return outputs

@@ -1,0 +1,236 @@
+"""Shared machinery of the two window-attention drop-ins (masked / unmasked).
+
+Forward = the fused sm_100a kernel (`mwa_forward`, `window_attention_forward`).
+Backward (training, BASELINE config 5) is INTERIM: it re-computes the block with differentiable
+torch CUDA ops on the saved inputs and back-propagates through that graph.  It is numerically the
+same function (fp32) and keeps training runnable until the hand-written backward kernels land
+("what comes next").  It is never used for forward values.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from .. import _abi
+from ._params import ParamBlock
+
+
+def _window_partition(x, window_size):
+    B, H, W, C = x.shape
+    x = x.view(B, H // window_size, window_size, W // window_size, window_size, C)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, window_size, window_size, C)
+
+
+def _window_reverse(windows, window_size, H, W):
+    B = int(windows.shape[0] / (H * W / window_size / window_size))
+    x = windows.view(B, H // window_size, W // window_size, window_size, window_size, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
+
+
+def _band(n, size, ws, s, device):
+    c = torch.arange(n, device=device)
+    return (c >= size - ws).long() + (c >= size - s).long()
+
+
+def _differentiable_block(x, alpha, qkv_w, qkv_b, proj_w, proj_b, table, index, heads, ws, shift, scale):
+    """torch re-statement used ONLY to obtain gradients (see module docstring)."""
+    B, C, H, W = x.shape
+    N = ws * ws
+    xs = x.permute(0, 2, 3, 1)
+    if shift > 0:
+        xs = torch.roll(xs, shifts=(-shift, -shift), dims=(1, 2))
+    xw = _window_partition(xs, ws).reshape(-1, N, C)
+    if alpha is None:
+        keep = torch.ones(xw.shape[0], dtype=torch.bool, device=x.device)
+    else:
+        a = alpha.permute(0, 2, 3, 1)
+        if shift > 0:
+            a = torch.roll(a, shifts=(-shift, -shift), dims=(1, 2))
+        keep = _window_partition(a, ws).sum(dim=(1, 2, 3)) != 0
+    d = C // heads
+    qkv = torch.nn.functional.linear(xw, qkv_w, qkv_b).reshape(-1, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    att = (qkv[0] * scale) @ qkv[1].transpose(-2, -1)
+    att = att + table[index.view(-1)].view(N, N, -1).permute(2, 0, 1).unsqueeze(0)
+    if shift > 0:
+        rid = 3 * _band(H, H, ws, shift, x.device)[:, None] + _band(W, W, ws, shift, x.device)[None, :]
+        rid = _window_partition(rid.view(1, H, W, 1).float(), ws).view(-1, N)
+        m = (rid[:, :, None] != rid[:, None, :]).float() * -100.0
+        att = att + m.repeat(B, 1, 1)[:, None]
+    y = (torch.softmax(att, dim=-1) @ qkv[2]).transpose(1, 2).reshape(-1, N, C)
+    y = torch.nn.functional.linear(y, proj_w, proj_b)
+    y = y * keep[:, None, None].to(y.dtype)
+    ys = _window_reverse(y.view(-1, ws, ws, C), ws, H, W)
+    if shift > 0:
+        ys = torch.roll(ys, shifts=(shift, shift), dims=(1, 2))
+    return x + ys.permute(0, 3, 1, 2)
+
+
+class WindowAttentionFunction(Function):
+    """out = x + window_attention(x) on kept windows; alpha=None keeps every window."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, qkv_w, qkv_b, proj_w, proj_b, table, attn_mod, ws, shift, algo):
+        lib = _abi.load()
+        _abi.require_cuda_f32(x, "attention input")
+        if alpha is not None:
+            _abi.require_cuda_f32(alpha, "img_alpha")
+        B, C, H, W = x.shape
+        if H % ws or W % ws:
+            # the reference fails in window_partition's .view (layers/masked_win_attention.py:15)
+            raise RuntimeError(f"shape '[{B}, {H // ws}, {ws}, {W // ws}, {ws}, {C}]' is invalid for input of size "
+                               f"{x.numel()}: H={H}, W={W} must be multiples of window_size={ws}")
+        channels_last = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
+        if not channels_last:
+            x = x.contiguous()
+        if alpha is not None:
+            if alpha.shape != (B, 1, H, W):
+                raise RuntimeError(f"img_alpha must have shape {(B, 1, H, W)}, got {tuple(alpha.shape)}")
+            alpha = alpha.contiguous()       # (B,1,H,W): NCHW and NHWC coincide
+        with torch.cuda.device(x.device):
+            blk = attn_mod._param_block(qkv_w, qkv_b, proj_w, proj_b, table)
+            out = torch.empty_like(x)
+            _abi.check(lib.mwa_forward(x.data_ptr(), _abi.ptr(alpha), out.data_ptr(), blk.data_ptr(), B, C, H, W,
+                                       attn_mod.num_heads, ws, shift, int(channels_last), algo, None,
+                                       _abi.stream_handle()), "mwa_forward")
+        ctx.cfg = (attn_mod, ws, shift)
+        ctx.has_bias = qkv_b is not None
+        ctx.save_for_backward(x, alpha, qkv_w, qkv_b, proj_w, proj_b, table)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, alpha, qkv_w, qkv_b, proj_w, proj_b, table = ctx.saved_tensors
+        attn_mod, ws, shift = ctx.cfg
+        need = ctx.needs_input_grad
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(n) if t is not None else None
+                      for t, n in zip((x, qkv_w, qkv_b, proj_w, proj_b, table),
+                                      (need[0], need[2], need[3], need[4], need[5], need[6]))]
+            xx, w1, b1, w2, b2, tb = leaves
+            y = _differentiable_block(xx, alpha, w1, b1, w2, b2, tb, attn_mod.relative_position_index,
+                                      attn_mod.num_heads, ws, shift, attn_mod.scale)
+            wanted = [t for t in leaves if t is not None and t.requires_grad]
+            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True) if wanted else []
+        it = iter(grads)
+        res = [next(it) if (t is not None and t.requires_grad) else None for t in leaves]
+        gx, gw1, gb1, gw2, gb2, gtb = res
+        return gx, None, gw1, gb1, gw2, gb2, gtb, None, None, None, None
+
+
+class TokenAttentionFunction(Function):
+    """WindowAttention.forward on (K, N, C) tokens with an optional additive (nW, N, N) mask (no residual)."""
+
+    @staticmethod
+    def forward(ctx, xw, mask, qkv_w, qkv_b, proj_w, proj_b, table, attn_mod):
+        lib = _abi.load()
+        _abi.require_cuda_f32(xw, "window tokens")
+        K, N, C = xw.shape
+        ws = attn_mod.window_size[0]
+        if attn_mod.window_size[0] != attn_mod.window_size[1] or N != ws * ws:
+            raise RuntimeError(f"expected {ws * ws} tokens per window, got {N}")
+        xw = xw.contiguous()
+        nw = 0
+        if mask is not None:
+            _abi.require_cuda_f32(mask, "mask")
+            mask = mask.contiguous()
+            nw = mask.shape[0]
+            if nw == 0:
+                print("nW error!")           # layers/masked_win_attention.py:116-118
+                mask, nw = None, 0
+            elif K % nw != 0 or mask.shape[1:] != (N, N):
+                raise RuntimeError(f"mask of shape {tuple(mask.shape)} does not tile {K} windows")
+        with torch.cuda.device(xw.device):
+            blk = attn_mod._param_block(qkv_w, qkv_b, proj_w, proj_b, table)
+            out = torch.empty_like(xw)
+            _abi.check(lib.window_attention_forward(xw.data_ptr(), _abi.ptr(mask), out.data_ptr(), blk.data_ptr(), K, C,
+                                                    attn_mod.num_heads, ws, nw, _abi.stream_handle()),
+                       "window_attention_forward")
+        ctx.attn_mod = attn_mod
+        ctx.save_for_backward(xw, mask, qkv_w, qkv_b, proj_w, proj_b, table)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xw, mask, qkv_w, qkv_b, proj_w, proj_b, table = ctx.saved_tensors
+        m = ctx.attn_mod
+        need = ctx.needs_input_grad
+        K, N, C = xw.shape
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(n) if t is not None else None
+                      for t, n in zip((xw, qkv_w, qkv_b, proj_w, proj_b, table),
+                                      (need[0], need[2], need[3], need[4], need[5], need[6]))]
+            xx, w1, b1, w2, b2, tb = leaves
+            d = C // m.num_heads
+            qkv = torch.nn.functional.linear(xx, w1, b1).reshape(K, N, 3, m.num_heads, d).permute(2, 0, 3, 1, 4)
+            att = (qkv[0] * m.scale) @ qkv[1].transpose(-2, -1)
+            att = att + tb[m.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1).unsqueeze(0)
+            if mask is not None:
+                nw = mask.shape[0]
+                att = (att.view(K // nw, nw, m.num_heads, N, N) + mask[None, :, None]).view(-1, m.num_heads, N, N)
+            y = (torch.softmax(att, dim=-1) @ qkv[2]).transpose(1, 2).reshape(K, N, C)
+            y = torch.nn.functional.linear(y, w2, b2)
+            wanted = [t for t in leaves if t is not None and t.requires_grad]
+            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True) if wanted else []
+        it = iter(grads)
+        res = [next(it) if (t is not None and t.requires_grad) else None for t in leaves]
+        return res[0], None, res[1], res[2], res[3], res[4], res[5], None
+
+
+class WindowAttentionBase(nn.Module):
+    """Window based multi-head self attention (W-MSA) with relative position bias -- parameter container and
+    token-level forward.  Same constructor / attributes / state-dict keys as the reference class
+    (layers/masked_win_attention.py:49-131 == layers/win_attention.py:37-115)."""
+
+    def __init__(self, dim=192, window_size=(8, 8), num_heads=8, qkv_bias=True, qk_scale=None, attn_drop=0.,
+                 proj_drop=0.):
+        super().__init__()
+        if attn_drop != 0. or proj_drop != 0.:
+            raise NotImplementedError("the fused sm_100a kernel implements attn_drop = proj_drop = 0 "
+                                      "(the only values the reference models use)")
+        if dim % num_heads != 0:
+            raise ValueError(f"dim={dim} must be divisible by num_heads={num_heads}")
+        self.dim = dim
+        self.window_size = tuple(window_size)
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * window_size[0] - 1) * (2 * window_size[1] - 1), num_heads))
+
+        t = torch.arange(window_size[0] * window_size[1])
+        ty, tx = t // window_size[1], t % window_size[1]
+        rel = (ty[:, None] - ty[None, :] + window_size[0] - 1) * (2 * window_size[1] - 1) \
+            + (tx[:, None] - tx[None, :] + window_size[1] - 1)
+        self.register_buffer("relative_position_index", rel)
+
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+        self._blk = ParamBlock()
+
+    def _param_block(self, qkv_w, qkv_b, proj_w, proj_b, table):
+        lib = _abi.load()
+        if self.window_size[0] != self.window_size[1]:
+            raise NotImplementedError("square windows only (the reference only builds square windows)")
+        C, h, ws = self.dim, self.num_heads, self.window_size[0]
+        for name, t in (("qkv.weight", qkv_w), ("proj.weight", proj_w), ("proj.bias", proj_b),
+                        ("relative_position_bias_table", table)):
+            _abi.require_cuda_f32(t, name)
+        nbytes = int(lib.mwa_param_bytes(C, h, ws))
+
+        def fill(blk):
+            _abi.check(lib.mwa_prepare(qkv_w.data_ptr(), _abi.ptr(qkv_b), proj_w.data_ptr(), proj_b.data_ptr(),
+                                       table.data_ptr(), C, h, ws, float(self.scale), blk.data_ptr(), blk.numel(),
+                                       _abi.stream_handle()), "mwa_prepare")
+
+        return self._blk.get((qkv_w, qkv_b, proj_w, proj_b, table), nbytes, fill)
+
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None."""
+        return TokenAttentionFunction.apply(x, mask, self.qkv.weight, self.qkv.bias, self.proj.weight,
+                                            self.proj.bias, self.relative_position_bias_table, self)

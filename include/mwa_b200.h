@@ -1,0 +1,127 @@
+/*
+ * mwa_b200.h -- C ABI of the B200-native hot path: masked window attention, GDN / IGDN, latent rounding.
+ *
+ * The reference (Yoshiki172/Deep-Learning-based-RGBA-Image-Compression-with-Masked-Window-based-Attention)
+ * is pure Python and has no FFI; its boundary for this path is the nn.Module API of three files
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  The Python drop-in modules in
+ * `<package>/layers/` bind these symbols with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer valid on the current device;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, never synchronise,
+ *     never allocate; the caller owns all memory including workspaces;
+ *   - tensors are fp32, dense, either NCHW (`channels_last == 0`) or NHWC (`channels_last == 1`);
+ *   - return value: MWA_OK or a negative MWA_ERR_* code; mwa_b200_status_string() describes it.
+ */
+#ifndef MWA_B200_H_
+#define MWA_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MWA_API __attribute__((visibility("default")))
+#else
+#define MWA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWA_B200_ABI_VERSION 1
+
+enum {
+    MWA_OK = 0,
+    MWA_ERR_INVALID = -1,      /* bad argument (null pointer, non-positive size, shift >= window ...) */
+    MWA_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels cover (documented per function) */
+    MWA_ERR_ALIGNMENT = -3,    /* pointer not 16-byte aligned */
+    MWA_ERR_WORKSPACE = -4,    /* workspace too small */
+    MWA_ERR_CUDA = -5          /* a CUDA runtime call failed (launch error) */
+};
+
+/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel */
+enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2 };
+
+MWA_API int mwa_b200_abi_version(void);
+MWA_API const char* mwa_b200_status_string(int status);
+/* last CUDA error string recorded by a failing call on this thread ("" if none) */
+MWA_API const char* mwa_b200_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GDN / IGDN      replaces  layers/GDN.py:64-94  (GDN.forward)  and  :9-23 (LowerBound, fwd part)
+ *
+ * gdn_prepare   : beta = max(beta_p, beta_bound)^2 - pedestal ; gamma = max(gamma_p, gamma_bound)^2 - pedestal
+ *                 (layers/GDN.py:74-80) expanded into the kernel-ready parameter block `params`
+ *                 (fp32 beta / gamma / gamma^T and the bf16 hi/lo UMMA operand images of gamma).
+ * gdn_forward   : y[i] = x[i] * (beta[i] + sum_j gamma[i][j] * x[j]^2) ^ (-1/2)   (inverse: ^ (+1/2))
+ *                 per pixel, x/y of logical shape (n_img, C, hw)  (layers/GDN.py:83-90).
+ * gdn_backward  : gradients wrt x, beta_p, gamma_p incl. the LowerBound pass-through rule
+ *                 (layers/GDN.py:17-23).  dbeta_p / dgamma_p are OVERWRITTEN (not accumulated).
+ * Supported: 1 <= C <= 512 (SIMT); C == 192 (tcgen05).
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int64_t gdn_param_bytes(int C);
+MWA_API int gdn_prepare(const float* beta_p, const float* gamma_p, int C, float beta_bound, float gamma_bound,
+                float pedestal, void* params, int64_t params_bytes, void* stream);
+MWA_API int gdn_forward(const float* x, float* y, const void* params, int64_t n_img, int C, int64_t hw, int inverse,
+                int channels_last, int algo, void* stream);
+MWA_API int64_t gdn_backward_workspace_bytes(int64_t n_img, int C, int64_t hw);
+MWA_API int gdn_backward(const float* x, const float* grad_y, const float* beta_p, const float* gamma_p,
+                 const void* params, float beta_bound, float gamma_bound, float* grad_x, float* grad_beta_p,
+                 float* grad_gamma_p, void* workspace, int64_t workspace_bytes, int64_t n_img, int C, int64_t hw,
+                 int inverse, int channels_last, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked window attention   replaces  layers/masked_win_attention.py:169-251 (WinBasedAttention.forward,
+ *   with its helpers window_partition :6-18, window_reverse :20-33, remove_zero_windows :35-47 and
+ *   WindowAttention.forward :96-131)  and  layers/win_attention.py:153-207 (alpha == NULL).
+ *
+ * mwa_prepare : packs qkv.weight (3C,C), qkv.bias (3C) or NULL, proj.weight (C,C), proj.bias (C),
+ *               relative_position_bias_table ((2ws-1)^2, heads) into `params`: fp32 transposes, the
+ *               expanded (heads, N, N) bias (layers/masked_win_attention.py:109-112) and fp16 UMMA images.
+ * mwa_forward : out = x + scatter(window_attention(kept windows of roll(x, -shift)))  rolled back;
+ *               a window is kept iff the sum of its (shifted) alpha is != 0; alpha == NULL keeps all.
+ *               x/out logical shape (B, C, H, W), alpha (B, 1, H, W); H % ws == 0 and W % ws == 0
+ *               (else MWA_ERR_INVALID, the reference raises in .view); 0 <= shift < ws.
+ *               `kept_count` (optional device int32, may be NULL) receives the number of kept windows.
+ * Supported: ws*ws <= 64 tokens, C % heads == 0, shared memory footprint <= 227 KB (SIMT: C <= 192 at ws 8);
+ *            tcgen05: (C, heads, ws) in {(192, 8, 8), (192, 6, 8), (80, 8, 4)}.
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int64_t mwa_param_bytes(int C, int heads, int ws);
+MWA_API int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
+                const float* bias_table, int C, int heads, int ws, float scale, void* params,
+                int64_t params_bytes, void* stream);
+MWA_API int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* stream);
+
+/* window_attention_forward : replaces layers/masked_win_attention.py:96-131 / layers/win_attention.py:84-115
+ *   (WindowAttention.forward on already-partitioned tokens): xw/out are (K, N, C) with N = ws*ws, `mask` is
+ *   NULL or an additive (mask_windows, N, N) tensor applied to window k as mask[k % mask_windows]; no residual. */
+MWA_API int window_attention_forward(const float* xw, const float* mask, float* out, const void* params, int64_t K,
+                                     int C, int heads, int ws, int mask_windows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent rounding   replaces  models/AutoEncoderRGB_Journal.py:31-32 (ste_round; forward value) and its
+ *   uses :227-229, :257, :262-264, :212-214  (= models/AutoEncoderMask_Journal.py:142-143, :255-257, :284).
+ * All are elementwise over `rows` rows of `row_len` contiguous floats; row r of tensor t starts at
+ * t + r * t_row_stride (lets a channel chunk of a (B,C,H,W) tensor be passed without a copy).
+ *
+ * round_ste_forward       : out = rint(x)                      (round-half-to-even)
+ * quantize_offset_forward : out = rint(x - mu) + mu            mu: same shape (mu_channels == 0) or one
+ *                           value per channel (mu_channels == C, row_len == C*hw, channel = (i / hw) % C)
+ * lrp_add_forward         : out = y_hat + 0.5 * tanh(lrp)
+ * quantize_levels_forward : out = rint(m * levels) / levels
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int round_ste_forward(const float* x, float* out, int64_t rows, int64_t row_len, int64_t x_row_stride,
+                      int64_t out_row_stride, void* stream);
+MWA_API int quantize_offset_forward(const float* x, const float* mu, float* out, int64_t rows, int64_t row_len,
+                            int64_t x_row_stride, int64_t mu_row_stride, int64_t out_row_stride,
+                            int mu_channels, int64_t hw, void* stream);
+MWA_API int lrp_add_forward(const float* y_hat, const float* lrp, float* out, int64_t rows, int64_t row_len,
+                    int64_t y_row_stride, int64_t lrp_row_stride, int64_t out_row_stride, void* stream);
+MWA_API int quantize_levels_forward(const float* m, float* out, int64_t n, float levels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MWA_B200_H_ */

@@ -1,0 +1,114 @@
+"""Seeded input recipes shared by make_golden.py (build container, live reference) and the tests
+(anywhere).  TEST INFRASTRUCTURE ONLY.  Inputs are regenerated from torch's CPU generator (bit-stable
+for a given torch build; an input checksum stored with every golden output detects drift), so the
+committed fixtures only carry the reference's OUTPUTS.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import torch
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def checksum(*tensors) -> int:
+    c = 0
+    for t in tensors:
+        if t is not None:
+            c = zlib.crc32(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes(), c)
+    return c
+
+
+def blob_alpha(B, H, W, ws, shift, drop_frac, seed, soft=True):
+    """alpha (B,1,H,W) >= 0 whose SHIFTED-frame windows are all-zero with probability ~drop_frac."""
+    g = _gen(seed)
+    keep = (torch.rand(B, 1, H // ws, W // ws, generator=g) >= drop_frac).float()
+    a = keep.repeat_interleave(ws, 2).repeat_interleave(ws, 3)
+    if soft:
+        a = a * torch.round(torch.rand(B, 1, H, W, generator=g) * 255) / 255
+    return torch.roll(a, shifts=(shift, shift), dims=(2, 3))
+
+
+ATTENTION_CASES = {
+    # name: dict(C, heads, ws, shift, B, H, W, drop, masked, seed)
+    "attn_c32_h4_ws4_s2": dict(C=32, heads=4, ws=4, shift=2, B=2, H=8, W=12, drop=0.3, masked=True, seed=11),
+    "attn_c80_h8_ws4_s2": dict(C=80, heads=8, ws=4, shift=2, B=2, H=16, W=24, drop=0.4, masked=True, seed=12),
+    "attn_c192_h8_ws8_s4": dict(C=192, heads=8, ws=8, shift=4, B=1, H=24, W=32, drop=0.4, masked=True, seed=13),
+    "attn_c192_h6_ws8_s0": dict(C=192, heads=6, ws=8, shift=0, B=2, H=16, W=16, drop=0.5, masked=True, seed=14),
+    "attn_c192_h8_ws8_s4_unmasked": dict(C=192, heads=8, ws=8, shift=4, B=1, H=16, W=24, drop=0.0, masked=False,
+                                         seed=15),
+    "attn_c80_h8_ws4_s0_unmasked": dict(C=80, heads=8, ws=4, shift=0, B=1, H=8, W=8, drop=0.0, masked=False,
+                                        seed=16),
+    "attn_c192_all_transparent": dict(C=192, heads=8, ws=8, shift=4, B=1, H=16, W=16, drop=1.0, masked=True,
+                                      seed=17),
+    "attn_c48_h3_ws2_s1_nobias": dict(C=48, heads=3, ws=2, shift=1, B=1, H=6, W=4, drop=0.2, masked=True, seed=18,
+                                      qkv_bias=False),
+}
+
+
+def attention_inputs(cfg):
+    """returns dict(x, alpha|None, qkv_w, qkv_b|None, proj_w, proj_b, table)"""
+    g = _gen(cfg["seed"])
+    C, h, ws = cfg["C"], cfg["heads"], cfg["ws"]
+    x = torch.randn(cfg["B"], C, cfg["H"], cfg["W"], generator=g) * 1.5
+    s = C ** -0.5
+    p = dict(
+        x=x,
+        qkv_w=torch.randn(3 * C, C, generator=g) * s * 1.5,
+        qkv_b=(torch.randn(3 * C, generator=g) * 0.2) if cfg.get("qkv_bias", True) else None,
+        proj_w=torch.randn(C, C, generator=g) * s,
+        proj_b=torch.randn(C, generator=g) * 0.1,
+        table=torch.randn((2 * ws - 1) ** 2, h, generator=g) * 0.5,
+    )
+    if cfg["masked"]:
+        a = blob_alpha(cfg["B"], cfg["H"], cfg["W"], ws, cfg["shift"], cfg["drop"], cfg["seed"] + 1000)
+        if cfg["drop"] >= 1.0:
+            a = torch.zeros_like(a)
+        elif cfg["drop"] > 0:
+            # one window that survives on a single tiny texel (the predicate is sum != 0, not a threshold)
+            ys, xs = 0, 0
+            a_s = torch.roll(a, (-cfg["shift"], -cfg["shift"]), (2, 3))
+            a_s[0, 0, ys:ys + ws, xs:xs + ws] = 0
+            a_s[0, 0, ys + 1, xs + 1] = 1e-30
+            a = torch.roll(a_s, (cfg["shift"], cfg["shift"]), (2, 3))
+        p["alpha"] = a
+    else:
+        p["alpha"] = None
+    return p
+
+
+GDN_CASES = {
+    "gdn_c192": dict(C=192, B=2, H=8, W=12, inverse=False, seed=21),
+    "igdn_c192": dict(C=192, B=2, H=8, W=12, inverse=True, seed=22),
+    "gdn_c16_bounds": dict(C=16, B=1, H=5, W=7, inverse=False, seed=23, hit_bounds=True),
+    "igdn_c40_5d": dict(C=40, B=1, H=6, W=4, D=3, inverse=True, seed=24),
+}
+
+
+def gdn_inputs(cfg):
+    g = _gen(cfg["seed"])
+    C = cfg["C"]
+    shape = (cfg["B"], C, cfg["D"], cfg["H"], cfg["W"]) if "D" in cfg else (cfg["B"], C, cfg["H"], cfg["W"])
+    x = torch.randn(*shape, generator=g) * 2.0
+    pedestal = (2 ** -18) ** 2
+    beta = torch.sqrt(0.5 + torch.rand(C, generator=g) * 2 + pedestal)
+    gamma = torch.sqrt(0.1 * torch.eye(C) + torch.rand(C, C, generator=g) * 0.02 + pedestal)
+    if cfg.get("hit_bounds"):
+        beta[::3] = 1e-5            # below beta_bound  -> clamped
+        gamma[::2, 1::2] = 0.0      # below gamma_bound -> clamped
+        gamma[1, 2] = -0.3
+    return dict(x=x, beta=beta, gamma=gamma)
+
+
+def rounding_inputs():
+    g = _gen(31)
+    half = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 3.5, 1e-8, -1e-8, 0.0, -0.0, 8388607.5, 1e10, -7.49999, 7.5])
+    x = torch.cat([half, torch.randn(4081, generator=g) * 6])
+    mu = torch.randn(x.numel(), generator=g) * 2
+    lrp = torch.randn(x.numel(), generator=g) * 1.5
+    m = torch.rand(x.numel(), generator=g)
+    return dict(x=x, mu=mu, lrp=lrp, m=m)

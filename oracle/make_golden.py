@@ -1,0 +1,102 @@
+"""Regenerate tests/golden/*.npz from the LIVE reference (build container only).
+
+    python -m oracle.make_golden
+
+Runs the unmodified reference modules (through oracle/live_reference.py) on the seeded recipes of
+oracle/golden_cases.py, in fp32 on CPU, and stores their forward outputs and autograd gradients.
+TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import golden_cases as G
+from . import live_reference
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_attention(ref):
+    out = {}
+    for name, cfg in G.ATTENTION_CASES.items():
+        p = G.attention_inputs(cfg)
+        cls = ref.masked.WinBasedAttention if cfg["masked"] else ref.unmasked.WinBasedAttention
+        m = cls(dim=cfg["C"], num_heads=cfg["heads"], window_size=cfg["ws"], shift_size=cfg["shift"],
+                qkv_bias=cfg.get("qkv_bias", True))
+        with torch.no_grad():
+            m.attn.qkv.weight.copy_(p["qkv_w"])
+            if p["qkv_b"] is not None:
+                m.attn.qkv.bias.copy_(p["qkv_b"])
+            m.attn.proj.weight.copy_(p["proj_w"])
+            m.attn.proj.bias.copy_(p["proj_b"])
+            m.attn.relative_position_bias_table.copy_(p["table"])
+        x = p["x"].clone().requires_grad_(True)
+        y = m(x, p["alpha"]) if cfg["masked"] else m(x)
+        gsel = torch.Generator().manual_seed(cfg["seed"] + 5)
+        gy = torch.randn(y.shape, generator=gsel)
+        y.backward(gy)
+        out[name + "/y"] = _np(y)
+        out[name + "/dx"] = _np(x.grad)
+        if cfg["C"] <= 80:                      # keep the fixtures small: weight gradients for the small cases only
+            out[name + "/dqkv_w"] = _np(m.attn.qkv.weight.grad)
+            out[name + "/dproj_w"] = _np(m.attn.proj.weight.grad)
+        out[name + "/dtable"] = _np(m.attn.relative_position_bias_table.grad)
+        out[name + "/crc"] = np.array(G.checksum(*[p[k] for k in ("x", "alpha", "qkv_w", "qkv_b", "proj_w", "proj_b",
+                                                                 "table")]), dtype=np.int64)
+    return out
+
+
+def make_gdn(ref):
+    out = {}
+    for name, cfg in G.GDN_CASES.items():
+        p = G.gdn_inputs(cfg)
+        m = ref.gdn.GDN(cfg["C"], inverse=cfg["inverse"])
+        with torch.no_grad():
+            m.beta.copy_(p["beta"])
+            m.gamma.copy_(p["gamma"])
+        x = p["x"].clone().requires_grad_(True)
+        y = m(x)
+        gsel = torch.Generator().manual_seed(cfg["seed"] + 5)
+        gy = torch.randn(y.shape, generator=gsel)
+        y.backward(gy)
+        out[name + "/y"] = _np(y)
+        out[name + "/dx"] = _np(x.grad)
+        out[name + "/dbeta"] = _np(m.beta.grad)
+        out[name + "/dgamma"] = _np(m.gamma.grad)
+        out[name + "/crc"] = np.array(G.checksum(p["x"], p["beta"], p["gamma"]), dtype=np.int64)
+    return out
+
+
+def make_rounding(ref):
+    p = G.rounding_inputs()
+    rgb = ref.model("rgb")
+    out = {
+        "ste_round": _np(rgb.ste_round(p["x"])),
+        "quantize_offset": _np(rgb.ste_round(p["x"] - p["mu"]) + p["mu"]),
+        "lrp_add": _np(p["x"] + 0.5 * torch.tanh(p["lrp"])),
+        "levels255": _np(torch.round(p["m"] * 255) / 255),
+        "crc": np.array(G.checksum(p["x"], p["mu"], p["lrp"], p["m"]), dtype=np.int64),
+    }
+    return out
+
+
+def main():
+    ref = live_reference.load()
+    torch.set_num_threads(1)           # fixed reduction order
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for fname, data in (("attention.npz", make_attention(ref)), ("gdn.npz", make_gdn(ref)),
+                        ("rounding.npz", make_rounding(ref))):
+        path = os.path.join(OUT_DIR, fname)
+        np.savez_compressed(path, **data)
+        print(f"wrote {path}: {len(data)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+// Hardware probe for the tcgen05 building blocks used by the library (run on the B200 box under `timeout`):
+// D[128 x N] = A[128 x K] * B[N x K]^T with fp16/bf16 operands written to shared memory by the threads in the
+// K-major SWIZZLE_128B canonical layout, accumulated in TMEM and read back with tcgen05.ld.
+// Prints max |err| against a host fp32 reference for a list of (N, K, dtype) cases.  Exit code 0 = all pass.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_bf16.h>
+#include "../deep-learning-based-rgba-image-compression-with-masked-window-based-attention_b200/csrc/common.cuh"
+
+using namespace b200;
+
+#define CK(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                       \
+        }                                                                                  \
+    } while (0)
+
+// A: [128][K] 16-bit row-major, B: [N][K] 16-bit row-major, D: [128][N] fp32
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, float* __restrict__ D, int N, int K,
+             uint32_t fmt) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int kblocks = (K + 63) / 64;
+    uint8_t* sA = smem;                                  // kblocks x [128 rows x 128 B]
+    uint8_t* sB = smem + kblocks * 128 * 128;            // kblocks x [N rows x 128 B]  (N % 8 == 0)
+
+    // zero-fill (partial K blocks must read as zeros)
+    for (int i = tid; i < (kblocks * (128 + N) * 128) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < 128 * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<uint16_t*>(sA + (k / 64) * (128 * 128) + sw128_offset(r, k % 64)) = A[i];
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<uint16_t*>(sB + (k / 64) * (N * 128) + sw128_offset(r, k % 64)) = B[i];
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_s;
+
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = umma_idesc(fmt, fmt, 128, N);
+        const int ksteps = K / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int kb = ks / 4, kin = ks % 4;
+            uint64_t ad = umma_desc_k_sw128(smem_u32(sA + kb * 128 * 128) + kin * 32);
+            uint64_t bd = umma_desc_k_sw128(smem_u32(sB + kb * N * 128) + kin * 32);
+            umma_f16_ss(tmem_d, ad, bd, idesc, ks > 0);
+        }
+        umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    tc_fence_after_sync();
+
+    const int row = tid;  // lane == row
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld_x8(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+        tmem_wait_ld();
+        for (int j = 0; j < 8; ++j) D[row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_d);
+}
+
+static uint16_t f2h(float f, uint32_t fmt) {
+    if (fmt == kFmtF16) {
+        __half h = __float2half_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+static float h2f(uint16_t u, uint32_t fmt) {
+    if (fmt == kFmtF16) {
+        __half h = *reinterpret_cast<__half*>(&u);
+        return __half2float(h);
+    }
+    __nv_bfloat16 h = *reinterpret_cast<__nv_bfloat16*>(&u);
+    return __bfloat162float(h);
+}
+
+static int run_case(int N, int K, uint32_t fmt) {
+    std::vector<uint16_t> hA(128 * K), hB(N * K);
+    std::vector<float> fA(128 * K), fB(N * K), ref(128 * N), hD(128 * N);
+    srand(1234 + N * 7 + K);
+    for (size_t i = 0; i < hA.size(); ++i) {
+        hA[i] = f2h((rand() % 2001 - 1000) / 500.f, fmt);
+        fA[i] = h2f(hA[i], fmt);
+    }
+    for (size_t i = 0; i < hB.size(); ++i) {
+        hB[i] = f2h((rand() % 2001 - 1000) / 500.f, fmt);
+        fB[i] = h2f(hB[i], fmt);
+    }
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double acc = 0;
+            for (int k = 0; k < K; ++k) acc += double(fA[m * K + k]) * fB[n * K + k];
+            ref[m * N + n] = float(acc);
+        }
+    uint16_t *dA, *dB;
+    float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2));
+    CK(cudaMalloc(&dB, hB.size() * 2));
+    CK(cudaMalloc(&dD, hD.size() * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, hD.size() * 4));
+    const int kblocks = (K + 63) / 64;
+    const int smem = kblocks * (128 + N) * 128;
+    CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, fmt);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (size_t i = 0; i < hD.size(); ++i) {
+        double e = fabs(double(hD[i]) - ref[i]);
+        if (!(e <= maxerr)) maxerr = e;   // catches NaN
+    }
+    const bool ok = maxerr < 1e-2;
+    printf("probe N=%3d K=%3d fmt=%s  max|err|=%.3e  %s\n", N, K, fmt == kFmtF16 ? "f16 " : "bf16", maxerr,
+           ok ? "OK" : "FAIL");
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dD);
+    return ok ? 0 : 1;
+}
+
+int main() {
+    int bad = 0;
+    const int Ns[] = {16, 32, 64, 80, 128, 192, 256};
+    const int Ks[] = {16, 32, 64, 80, 128, 192};
+    for (int N : Ns)
+        for (int K : Ks) bad += run_case(N, K, kFmtF16);
+    bad += run_case(192, 192, kFmtBF16);
+    bad += run_case(128, 64, kFmtBF16);
+    printf(bad ? "PROBE FAILED (%d cases)\n" : "PROBE PASSED\n", bad);
+    return bad ? 1 : 0;
+}
