@@ -14,8 +14,13 @@ enum Op { kRound = 0, kQuantSame = 1, kQuantChan = 2, kLrp = 3 };
 
 template <int OP>
 __device__ __forceinline__ float apply(float a, float b) {
-    if (OP == kRound) return rintf(a);
-    if (OP == kQuantSame || OP == kQuantChan) return __fadd_rn(rintf(__fsub_rn(a, b)), b);
+    // ste_round(v) = (round(v) - v) + v evaluated literally (models/AutoEncoderRGB_Journal.py:31-32): the value is
+    // rint(v) except that a zero result is always +0.0 (e.g. v = -0.3: (-0.0 + 0.3) - 0.3 = +0.0), like the reference.
+    if (OP == kRound) return __fadd_rn(__fsub_rn(rintf(a), a), a);
+    if (OP == kQuantSame || OP == kQuantChan) {
+        const float d = __fsub_rn(a, b);
+        return __fadd_rn(__fadd_rn(__fsub_rn(rintf(d), d), d), b);
+    }
     return __fadd_rn(a, __fmul_rn(0.5f, tanhf(b)));
 }
 
@@ -72,10 +77,11 @@ template <int OP>
 int launch_rowwise(const float* a, const float* b, float* out, int64_t rows, int64_t row_len, int64_t a_stride,
                    int64_t b_stride, int64_t o_stride, int mu_channels, int64_t hw, cudaStream_t st,
                    const char* where) {
-    if (!a || !out || rows < 0 || row_len < 0) return MWA_ERR_INVALID;
+    if (rows < 0 || row_len < 0) return MWA_ERR_INVALID;
+    if (rows == 0 || row_len == 0) return MWA_OK;            // empty tensors carry null data pointers
+    if (!a || !out) return MWA_ERR_INVALID;
     if ((OP != kRound) && !b) return MWA_ERR_INVALID;
     if (OP == kQuantChan && (mu_channels <= 0 || hw <= 0)) return MWA_ERR_INVALID;
-    if (rows == 0 || row_len == 0) return MWA_OK;
     bool vec = aligned16(a) && aligned16(out) && row_len % 4 == 0 && a_stride % 4 == 0 && o_stride % 4 == 0;
     if (OP == kQuantSame || OP == kLrp) vec = vec && aligned16(b) && b_stride % 4 == 0;
     if (vec) {
@@ -118,8 +124,9 @@ int lrp_add_forward(const float* y_hat, const float* lrp, float* out, int64_t ro
 }
 
 int quantize_levels_forward(const float* m, float* out, int64_t n, float levels, void* stream) {
-    if (!m || !out || n < 0 || !(levels > 0.f)) return MWA_ERR_INVALID;
+    if (n < 0 || !(levels > 0.f)) return MWA_ERR_INVALID;
     if (n == 0) return MWA_OK;
+    if (!m || !out) return MWA_ERR_INVALID;
     levels_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(m, out, n, levels);
     return check_launch("quantize_levels_forward");
 }

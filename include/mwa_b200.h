@@ -106,8 +106,8 @@ MWA_API int window_attention_forward(const float* xw, const float* mask, float* 
  * All are elementwise over `rows` rows of `row_len` contiguous floats; row r of tensor t starts at
  * t + r * t_row_stride (lets a channel chunk of a (B,C,H,W) tensor be passed without a copy).
  *
- * round_ste_forward       : out = rint(x)                      (round-half-to-even)
- * quantize_offset_forward : out = rint(x - mu) + mu            mu: same shape (mu_channels == 0) or one
+ * round_ste_forward       : out = (rint(x) - x) + x  == rint(x), zero results are +0.0 (round-half-to-even)
+ * quantize_offset_forward : out = ste_round(x - mu) + mu           mu: same shape (mu_channels == 0) or one
  *                           value per channel (mu_channels == C, row_len == C*hw, channel = (i / hw) % C)
  * lrp_add_forward         : out = y_hat + 0.5 * tanh(lrp)
  * quantize_levels_forward : out = rint(m * levels) / levels
