@@ -33,8 +33,9 @@ _SIGNATURES = {
     "mwa_param_bytes": (c_int64, [c_int, c_int, c_int]),
     "mwa_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                             c_void_p, c_int64, c_void_p]),
+    "mwa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "mwa_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                            c_int, c_int, c_void_p, c_void_p]),
+                            c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "window_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                          c_void_p]),
     "round_ste_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),

@@ -9,7 +9,9 @@
 namespace b200 {
 
 int mwa_forward_tc(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
-                   int heads, int ws, int shift, int channels_last, int32_t* kept_count, cudaStream_t st);  // mwa_tc.cu
+                   int heads, int ws, int shift, int channels_last, int32_t* kept_count, void* workspace,
+                   int64_t workspace_bytes, cudaStream_t st);                                                // mwa_tc.cu
+int64_t mwa_tc_workspace_bytes(int64_t nwin);
 bool mwa_tc_supported(int C, int heads, int ws, int H, int W, int shift, int channels_last);
 void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
                            int heads, int ws, float scale, uint8_t* blk, cudaStream_t st);                    // mwa_tc.cu
@@ -278,8 +280,14 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     return check_launch("mwa_prepare(images)");
 }
 
+int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
+    if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;
+    return mwa_tc_workspace_bytes(int64_t(B) * (H / ws) * (W / ws));
+}
+
 int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
-                int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* stream) {
+                int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* workspace,
+                int64_t workspace_bytes, void* stream) {
     if (!x || !out || !params) return MWA_ERR_INVALID;
     if (B < 0 || C <= 0 || H <= 0 || W <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return MWA_ERR_INVALID;
     if (shift < 0 || shift >= ws) return MWA_ERR_INVALID;
@@ -291,7 +299,8 @@ int mwa_forward(const float* x, const float* alpha, float* out, const void* para
     if (algo == MWA_ALGO_TCGEN05 || (algo == MWA_ALGO_AUTO && tc_ok)) {
         if (!tc_ok) return MWA_ERR_UNSUPPORTED;
         if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
-        return mwa_forward_tc(x, alpha, out, params, B, C, H, W, heads, ws, shift, channels_last, kept_count, st);
+        return mwa_forward_tc(x, alpha, out, params, B, C, H, W, heads, ws, shift, channels_last, kept_count, workspace,
+                              workspace_bytes, st);
     }
     const int N = ws * ws;
     if (N > 64) return MWA_ERR_UNSUPPORTED;

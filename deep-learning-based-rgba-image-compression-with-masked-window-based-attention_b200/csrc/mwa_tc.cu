@@ -1,9 +1,722 @@
-// placeholder until the tcgen05 attention kernel lands
+// Fused masked window attention forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// Reference semantics: layers/masked_win_attention.py:169-251 (block) and :96-131 (window attention).
+//
+// Three launches per forward, no host synchronisation:
+//   1. mwa_scan_kernel      keep flag per window (sum of the cyclically shifted alpha != 0, :35-47); dropped
+//                           windows are copied x -> out right here (the block is the identity there).
+//   2. mwa_compact_kernel   ordered compaction of the kept windows into a work list + count.
+//   3. mwa_tc_kernel        persistent, one CTA per SM; a tile = 128 tokens = 2 kept 8x8 windows (8 kept 4x4
+//                           windows); everything between the x load and the out store stays on chip.
+//
+// Tile pipeline (16 warps; thread 0 issues every MMA and feeds the weight ring):
+//   load     x (fp32, NCHW or NHWC, cyclic shift + window partition by index arithmetic) -> fp16 A operand in smem
+//   per head group g (64 padded q/k/v columns = 2 heads of d<=32 or 4 heads of d<=16):
+//     QKV    D[128 x 192] = X[128 x C] * Wqkv_g^T   (weights streamed from L2 through a 2-slot bulk-copy ring;
+//            q rows pre-scaled by d^-1/2 and zero-padded per head at prepare time)
+//     drain  + bias -> fp16 -> Q_g / K_g (K-major) and V_g^T (keys contiguous) operands in smem
+//     per head: S = Q_h K_h^T over all 128 tokens of the tile (block diagonal: a token only uses the 64 / 16
+//            columns of its own window), + relative-position bias + SW-MSA region mask (from coordinates),
+//            row softmax split over 4 threads per row (max exchanged through smem, sums deferred),
+//            P (fp16, exact zeros off the diagonal blocks) -> smem, O_h = P V_h accumulated in TMEM
+//     drain  O / rowsum -> fp16 A operand;  proj: Dproj[128 x C] += O_g * Wproj_g^T  (accumulated over groups)
+//   epilogue out = x + Dproj + bproj, scattered back to the un-shifted pixel positions.
+// Operand precision: fp16 x fp16 -> fp32 accumulate (kind::f16); softmax, bias, residual in fp32.
 #include "common.cuh"
 #include "params.cuh"
 #include "status.cuh"
+
 namespace b200 {
-bool mwa_tc_supported(int, int, int, int, int, int, int) { return false; }
-int mwa_forward_tc(const float*, const float*, float*, const void*, int, int, int, int, int, int, int, int, int32_t*, cudaStream_t) { return MWA_ERR_UNSUPPORTED; }
-void mwa_tc_prepare_images(const float*, const float*, const float*, const float*, int, int, int, float, uint8_t*, cudaStream_t) {}
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRingSlots = 2;
+constexpr uint32_t kSlabBytes = 192 * 128;          // one K block (64 k) of a 192-row weight slab
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kNegMask = -100.0f;                 // layers/masked_win_attention.py:214
+
+struct Geom {
+    int B, H, W, shift, nwx, nwy, channels_last;
+};
+
+// ------------------------------------------------------------------------------------------------ configuration
+template <int C_, int HEADS_, int WS_>
+struct Cfg {
+    static constexpr int C = C_, HEADS = HEADS_, WS = WS_;
+    static constexpr int D = C / HEADS;
+    static constexpr int DPAD = (D + 15) / 16 * 16;
+    static constexpr int HPG = 64 / DPAD;                 // heads per group
+    static constexpr int NG = HEADS / HPG;                // head groups
+    static constexpr int NTOK = WS * WS;                  // tokens per window
+    static constexpr int WPT = kTileM / NTOK;             // windows per tile
+    static constexpr int KB = (C + 63) / 64;              // K blocks of the x operand
+    static constexpr int KSTEPS = C / 16;
+    static constexpr int CPT = NTOK / 4;                  // softmax columns per thread (4 threads per row)
+    static constexpr int NCHUNK = C / 8;                  // 16-byte fp16 chunks per token row
+    static constexpr int NCOLG = C / 16;                  // 16-column groups of the projection output
+    static constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
+    static constexpr uint32_t kProjSlabBytes = C * 128;
+    static constexpr uint32_t kGroupBytes = KB * kSlabBytes + kProjSlabBytes;
+    static constexpr int kSlabsPerGroup = KB + 1;
+    static constexpr int kSlabsPerTile = NG * kSlabsPerGroup;
+    static_assert(C % 16 == 0 && HEADS % HPG == 0 && DPAD * HPG == 64, "unsupported head geometry");
+    static_assert(kTileM % NTOK == 0 && (CPT == 16 || CPT == 4), "unsupported window size");
+    // shared memory map (offsets from a 1024-aligned base)
+    static constexpr uint32_t oX = 0;                                   // KB x [128 x 64] fp16
+    static constexpr uint32_t oQ = oX + KB * 16384;
+    static constexpr uint32_t oK = oQ + 16384;
+    static constexpr uint32_t oVt = oK + 16384;                         // 2 key blocks x [64 rows x 64 keys]
+    static constexpr uint32_t oP = oVt + 16384;                         // 2 key blocks x [128 x 64]
+    static constexpr uint32_t oO = oP + 32768;
+    static constexpr uint32_t oRing = oO + 16384;
+    static constexpr uint32_t oTbl = oRing + kRingSlots * kSlabBytes;   // fp32 [HEADS][TBL]
+    static constexpr uint32_t oBqkv = oTbl + ((HEADS * TBL * 4 + 15) / 16) * 16;   // fp32 [NG][192]
+    static constexpr uint32_t oBproj = oBqkv + NG * 192 * 4;
+    static constexpr uint32_t oRedMax = oBproj + C * 4;                 // fp32 [4][128]
+    static constexpr uint32_t oRedSum = oRedMax + 4 * 128 * 4;          // fp32 [HPG][4][128]
+    static constexpr uint32_t oBars = oRedSum + HPG * 4 * 128 * 4;
+    static constexpr uint32_t oTmem = oBars + 8 * 8;
+    static constexpr uint32_t oTotal = oTmem + 16;
+    static_assert(oTotal + 1024 <= 227 * 1024, "shared memory budget");
+    // TMEM columns
+    static constexpr uint32_t tA = 0;        // D_qkv [0,192)  /  S_h [0,128)
+    static constexpr uint32_t tO = 256;      // O accumulators of the group: HPG x DPAD = 64 columns
+    static constexpr uint32_t tP = 320;      // projection accumulator, C columns
+};
+
+// layout of the tcgen05 section of the parameter block (offsets from MwaParamLayout::img_wqkv)
+template <class CF>
+struct TcParams {
+    static constexpr int64_t img = 0;                                          // NG x kGroupBytes
+    static constexpr int64_t bq = img + int64_t(CF::NG) * CF::kGroupBytes;     // fp32 [NG][192] padded order
+    static constexpr int64_t total = bq + CF::NG * 192 * 4;
+};
+
+// ------------------------------------------------------------------------------------------------ prepare
+template <class CF>
+__global__ void mwa_tc_prepare_kernel(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
+                                      const float* __restrict__ proj_w, float scale, uint8_t* __restrict__ out) {
+    constexpr int C = CF::C, D = CF::D, DPAD = CF::DPAD, HPG = CF::HPG;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // qkv slabs
+    for (int e = tid; e < CF::NG * 192 * C; e += nth) {
+        const int g = e / (192 * C), n = (e / C) % 192, k = e % C;
+        const int part = n / 64, hh = (n % 64) / DPAD, c = (n % 64) % DPAD;
+        float v = 0.f;
+        if (c < D) {
+            v = qkv_w[int64_t(part * C + (g * HPG + hh) * D + c) * C + k];
+            if (part == 0) v *= scale;
+        }
+        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(k / 64) * kSlabBytes + sw128_offset(n, k % 64);
+        *reinterpret_cast<__half*>(out + TcParams<CF>::img + off) = __float2half_rn(v);
+    }
+    // projection slabs: rows = output channel, K = this group's 64 padded O columns
+    for (int e = tid; e < CF::NG * C * 64; e += nth) {
+        const int g = e / (C * 64), n = (e / 64) % C, kk = e % 64;
+        const int hh = kk / DPAD, c = kk % DPAD;
+        const float v = (c < D) ? proj_w[int64_t(n) * C + (g * HPG + hh) * D + c] : 0.f;
+        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(CF::KB) * kSlabBytes + sw128_offset(n, kk);
+        *reinterpret_cast<__half*>(out + TcParams<CF>::img + off) = __float2half_rn(v);
+    }
+    for (int e = tid; e < CF::NG * 192; e += nth) {
+        const int g = e / 192, n = e % 192;
+        const int part = n / 64, hh = (n % 64) / DPAD, c = (n % 64) % DPAD;
+        float v = 0.f;
+        if (c < D && qkv_b != nullptr) {
+            v = qkv_b[part * C + (g * HPG + hh) * D + c];
+            if (part == 0) v *= scale;
+        }
+        reinterpret_cast<float*>(out + TcParams<CF>::bq)[e] = v;
+    }
 }
+
+__global__ void zero16_kernel(uint4* p, int64_t n16) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n16; i += int64_t(gridDim.x) * blockDim.x)
+        p[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ scan + compaction
+struct ScanWs {           // workspace layout
+    int64_t count, flags, list, total;
+    __host__ __device__ explicit ScanWs(int64_t nwin) {
+        count = 0;
+        flags = 16;
+        list = align_up(flags + nwin, 16);
+        total = align_up(list + 4 * (nwin + 16), 256);
+    }
+};
+
+__device__ __forceinline__ void window_coords(const Geom& g, int win, int& b, int& wy, int& wx) {
+    b = win / (g.nwy * g.nwx);
+    const int r = win - b * g.nwy * g.nwx;
+    wy = r / g.nwx;
+    wx = r - wy * g.nwx;
+}
+// token t of window (wy, wx): original (un-shifted) pixel
+template <int WS>
+__device__ __forceinline__ void token_pixel(const Geom& g, int wy, int wx, int t, int& y, int& x) {
+    y = wy * WS + t / WS + g.shift;
+    if (y >= g.H) y -= g.H;
+    x = wx * WS + t % WS + g.shift;
+    if (x >= g.W) x -= g.W;
+}
+
+// one warp per window: keep = (sum alpha != 0); dropped windows are copied through
+template <int WS>
+__global__ void __launch_bounds__(256)
+mwa_scan_kernel(const float* __restrict__ x, const float* __restrict__ alpha, float* __restrict__ out, Geom g, int C,
+                int nwin, uint8_t* __restrict__ flags) {
+    constexpr int NTOK = WS * WS;
+    const int win = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (win >= nwin) return;
+    int b, wy, wx;
+    window_coords(g, win, b, wy, wx);
+    float a = 0.f;
+    for (int t = lane; t < NTOK; t += 32) {
+        int y, xx;
+        token_pixel<WS>(g, wy, wx, t, y, xx);
+        a += __ldg(alpha + (int64_t(b) * g.H + y) * g.W + xx);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    const bool keep = a != 0.f;
+    if (lane == 0) flags[win] = keep;
+    if (keep) return;
+    const int64_t hw = int64_t(g.H) * g.W;
+    if (!g.channels_last) {
+        for (int e = lane; e < NTOK * C; e += 32) {
+            const int c = e / NTOK, t = e % NTOK;
+            int y, xx;
+            token_pixel<WS>(g, wy, wx, t, y, xx);
+            const int64_t off = (int64_t(b) * C + c) * hw + int64_t(y) * g.W + xx;
+            out[off] = __ldg(x + off);
+        }
+    } else {
+        for (int e = lane; e < NTOK * C; e += 32) {
+            const int t = e / C, c = e % C;
+            int y, xx;
+            token_pixel<WS>(g, wy, wx, t, y, xx);
+            const int64_t off = ((int64_t(b) * g.H + y) * g.W + xx) * C + c;
+            out[off] = __ldg(x + off);
+        }
+    }
+}
+
+// single block: ordered list of kept windows (flags == nullptr: every window kept)
+__global__ void __launch_bounds__(1024)
+mwa_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __restrict__ list,
+                   int32_t* __restrict__ count) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (nwin + 1023) / 1024;
+    const int beg = tid * per, end = min(beg + per, nwin);
+    int n = 0;
+    for (int i = beg; i < end; ++i) n += flags ? flags[i] : 1;
+    part[tid] = n;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
+        const int v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int pos = part[tid] - n;
+    for (int i = beg; i < end; ++i)
+        if (!flags || flags[i]) list[pos++] = i;
+    if (tid == 1023) *count = part[1023];
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ float ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+template <class CF>
+__global__ void __launch_bounds__(kThreads, 1)
+mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
+              const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
+              Geom geo) {
+    constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sb = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF::oBars);
+    uint64_t* bar_full = bars;               // [2] weight slab landed
+    uint64_t* bar_empty = bars + 2;          // [2] MMAs reading the slab done
+    uint64_t* bar_mma = bars + 4;            // [2], used alternately: "all MMAs issued so far are complete"
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + CF::oTmem);
+    float* s_tbl = reinterpret_cast<float*>(smem + CF::oTbl);
+    float* s_bqkv = reinterpret_cast<float*>(smem + CF::oBqkv);
+    float* s_bproj = reinterpret_cast<float*>(smem + CF::oBproj);
+    float* s_max = reinterpret_cast<float*>(smem + CF::oRedMax);
+    float* s_sum = reinterpret_cast<float*>(smem + CF::oRedSum);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = q * 32 + lane;                        // token row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const MwaParamLayout L(C, CF::HEADS, WS);
+
+    // ---- one-time setup
+    if (tid == 0) {
+        mbar_init(bar_full + 0, 1);
+        mbar_init(bar_full + 1, 1);
+        mbar_init(bar_empty + 0, 1);
+        mbar_init(bar_empty + 1, 1);
+        mbar_init(bar_mma + 0, 1);
+        mbar_init(bar_mma + 1, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_ptr);
+    {   // padded-order biases; zero the operand buffers whose padding / off-diagonal blocks must read as exact
+        // zeros for the whole kernel (Q/K/V pad columns come from zero weight rows)
+        const float* bq = reinterpret_cast<const float*>(tcp + TcParams<CF>::bq);
+        for (int i = tid; i < NG * 192; i += kThreads) s_bqkv[i] = bq[i];
+        const float* bp = reinterpret_cast<const float*>(blk + L.bproj);
+        for (int i = tid; i < C; i += kThreads) s_bproj[i] = bp[i];
+        for (int i = tid; i < (CF::oRing - CF::oX) / 16; i += kThreads)
+            reinterpret_cast<uint4*>(smem + CF::oX)[i] = make_uint4(0, 0, 0, 0);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = *tmem_ptr;
+
+    const int count = *count_p;
+    const int num_tiles = (count + CF::WPT - 1) / CF::WPT;
+    const int64_t hw = int64_t(geo.H) * geo.W;
+
+    // thread 0 state: weight ring + MMA completion phase
+    uint32_t slab_issued = 0, slab_used = 0, mma_waits = 0, mma_commits = 0;
+    const uint8_t* wimg = tcp + TcParams<CF>::img;
+    auto slab_src = [&](uint32_t i, uint32_t& bytes) -> const uint8_t* {
+        const uint32_t it = i % CF::kSlabsPerTile, g = it / CF::kSlabsPerGroup, s = it % CF::kSlabsPerGroup;
+        bytes = (s < CF::KB) ? kSlabBytes : CF::kProjSlabBytes;
+        return wimg + int64_t(g) * CF::kGroupBytes + int64_t(s) * kSlabBytes;
+    };
+    auto feed_ring = [&](uint32_t upto, uint32_t total) {        // thread 0 only
+        while (slab_issued <= upto && slab_issued < total) {
+            const uint32_t slot = slab_issued % kRingSlots, use = slab_issued / kRingSlots;
+            if (use > 0) mbar_wait(bar_empty + slot, (use - 1) & 1);
+            uint32_t bytes;
+            const uint8_t* src = slab_src(slab_issued, bytes);
+            mbar_arrive_expect_tx(bar_full + slot, bytes);
+            bulk_g2s(smem + CF::oRing + slot * kSlabBytes, src, bytes, bar_full + slot);
+            ++slab_issued;
+        }
+    };
+    // thread 0: commit k goes to barrier k & 1; every thread: wait k on the same barrier with parity (k >> 1) & 1.
+    // At most two commits are ever issued between two CTA-wide barriers, so a slow waiter can never be lapped.
+    auto commit_mma = [&]() {
+        umma_commit(bar_mma + (mma_commits & 1));
+        ++mma_commits;
+    };
+    auto wait_mma = [&]() {
+        mbar_wait(bar_mma + (mma_waits & 1), (mma_waits >> 1) & 1);
+        ++mma_waits;
+        __syncwarp();
+        tc_fence_after_sync();
+    };
+
+    // number of tiles this CTA will process -> total slabs it will consume
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
+    const uint32_t my_slabs = uint32_t(my_tiles) * CF::kSlabsPerTile;
+
+    // compact relative-position table s_tbl[h][idx], idx = (yi-yj+WS-1)*(2WS-1) + (xi-xj+WS-1), recovered from the
+    // expanded bias[h][i][j] of the parameter block (any token pair with that offset carries the same value)
+    {
+        const float* bexp = reinterpret_cast<const float*>(blk + L.bias);
+        for (int e = tid; e < CF::HEADS * CF::TBL; e += kThreads) {
+            const int h = e / CF::TBL, idx = e % CF::TBL;
+            const int dy = idx / (2 * WS - 1) - (WS - 1), dx = idx % (2 * WS - 1) - (WS - 1);   // yi - yj, xi - xj
+            const int yi = dy >= 0 ? dy : 0, yj = dy >= 0 ? 0 : -dy;
+            const int xi = dx >= 0 ? dx : 0, xj = dx >= 0 ? 0 : -dx;
+            s_tbl[e] = bexp[(int64_t(h) * NTOK + (yi * WS + xi)) * NTOK + (yj * WS + xj)];
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) feed_ring(1, my_slabs);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---------------- tile geometry for this thread's token row
+        const int wslot = r / NTOK, t = r % NTOK;
+        const int lidx = tile * CF::WPT + wslot;
+        const bool row_valid = lidx < count;
+        const int win = list[row_valid ? lidx : (count - 1)];
+        int b, wy, wx, py, px;
+        window_coords(geo, win, b, wy, wx);
+        token_pixel<WS>(geo, wy, wx, t, py, px);
+        const int64_t pix = int64_t(py) * geo.W + px;
+        const int64_t base = geo.channels_last ? (int64_t(b) * hw + pix) * C : int64_t(b) * C * hw + pix;
+        const int64_t cstride = geo.channels_last ? 1 : hw;
+
+        // ---------------- load x -> fp16 A operand (row r, 16-byte chunks ci = cg, cg+4, ...)
+        {
+            const float* xb = x + base;
+#pragma unroll
+            for (int ci = cg; ci < CF::NCHUNK; ci += 4) {
+                float v[8];
+                const float* pc = xb + int64_t(ci * 8) * cstride;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[j] = __ldg(pc);
+                    pc += cstride;
+                }
+                const uint32_t addr = sb + CF::oX + (ci >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 +
+                                      (((ci & 7) ^ (r & 7)) << 4);
+                st_shared_v4(addr, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                             pack_f16x2(v[6], v[7]));
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+
+        // SW-MSA region mask bits of this row (:194-216): bit yj of ymask = band(yj) differs from the row's band
+        uint32_t ymask = 0, xmask = 0;
+        if (geo.shift > 0) {
+            const int ys0 = wy * WS, xs0 = wx * WS;
+            const int ty = t / WS, tx = t % WS;
+            const int by = (ys0 + ty >= geo.H - WS) + (ys0 + ty >= geo.H - geo.shift);
+            const int bx = (xs0 + tx >= geo.W - WS) + (xs0 + tx >= geo.W - geo.shift);
+#pragma unroll
+            for (int j = 0; j < WS; ++j) {
+                const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
+                const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
+                ymask |= uint32_t(byj != by) << j;
+                xmask |= uint32_t(bxj != bx) << j;
+            }
+        }
+
+        for (int g = 0; g < NG; ++g) {
+            // ---------------- QKV GEMM for this head group
+            if (tid == 0) {
+                tc_fence_after_sync();
+                constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, 192);
+#pragma unroll 1
+                for (int kb = 0; kb < CF::KB; ++kb) {
+                    feed_ring(slab_used + 1, my_slabs);
+                    const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
+                    mbar_wait(bar_full + slot, use & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a0 = sb + CF::oX + kb * 16384, b0 = sb + CF::oRing + slot * kSlabBytes;
+                    const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
+                    for (int ks = 0; ks < nks; ++ks)
+                        umma_f16_ss(tm + CF::tA, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc,
+                                    (kb | ks) != 0);
+                    umma_commit(bar_empty + slot);
+                    ++slab_used;
+                }
+                commit_mma();
+            }
+            wait_mma();
+
+            // ---------------- drain: q (cg 0) / k (cg 1) / v (cg 2), + bias, -> fp16 operands
+            if (cg < 3) {
+                const float* bias = s_bqkv + g * 192 + cg * 64;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t acc[16];
+                    tmem_ld_x16(tm + CF::tA + lane_addr + cg * 64 + cc * 16, acc);
+                    tmem_wait_ld();
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + bias[cc * 16 + j];
+                    if (cg < 2) {
+                        const uint32_t rowaddr = sb + (cg == 0 ? CF::oQ : CF::oK) + (r >> 3) * 1024 + (r & 7) * 128;
+                        st_shared_v4(rowaddr + (((2 * cc) ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]),
+                                     pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+                        st_shared_v4(rowaddr + (((2 * cc + 1) ^ (r & 7)) << 4), pack_f16x2(v[8], v[9]),
+                                     pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                    } else {
+                        // V^T: row = channel (cc*16 + j), K index = key = token row r (key block r / 64)
+                        const uint32_t kbase = sb + CF::oVt + (r >> 6) * 8192;
+                        const uint32_t kk = r & 63;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t row = cc * 16 + j;
+                            const __half hv = __float2half_rn(v[j]);
+                            st_shared_u16(kbase + sw128_offset(row, kk), *reinterpret_cast<const uint16_t*>(&hv));
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+
+            // ---------------- heads of the group
+            for (int hh = 0; hh < HPG; ++hh) {
+                const int head = g * HPG + hh;
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    constexpr uint32_t idesc_s = umma_idesc(kFmtF16, kFmtF16, kTileM, 128);
+                    const uint32_t a0 = sb + CF::oQ + hh * DPAD * 2, b0 = sb + CF::oK + hh * DPAD * 2;
+#pragma unroll
+                    for (int ks = 0; ks < DPAD / 16; ++ks)
+                        umma_f16_ss(tm + CF::tA, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32),
+                                    idesc_s, ks != 0);
+                    commit_mma();
+                }
+                wait_mma();
+
+                // ---- softmax over the row's own window: 4 threads per row, CPT columns each
+                const int col0 = wslot * NTOK + cg * CF::CPT;          // first column (key index in the tile)
+                float sv[CF::CPT];
+                {
+                    // tcgen05.ld is warp-collective: the column address must be warp-uniform.  With 8x8 windows a warp
+                    // lies inside one window; with 4x4 windows it covers two, so both candidates are loaded.
+                    uint32_t acc[CF::CPT];
+                    if constexpr (CF::CPT == 16) {
+                        tmem_ld_x16(tm + CF::tA + lane_addr + col0, reinterpret_cast<uint32_t(&)[16]>(acc));
+                        tmem_wait_ld();
+                    } else {
+                        uint32_t a0[4], a1[4];
+                        const uint32_t cbase = (r >> 5) * 32 + cg * CF::CPT;
+                        tmem_ld_x4(tm + CF::tA + lane_addr + cbase, a0);
+                        tmem_ld_x4(tm + CF::tA + lane_addr + cbase + 16, a1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = (wslot & 1) ? a1[j] : a0[j];
+                    }
+                    const float* tb = s_tbl + head * CF::TBL;
+                    const int ty = t / WS, tx = t % WS;
+#pragma unroll
+                    for (int j = 0; j < CF::CPT; ++j) {
+                        const int jj = cg * CF::CPT + j;              // key token index in the window
+                        const int yj = jj / WS, xj = jj % WS;
+                        float s = __uint_as_float(acc[j]) + tb[(ty - yj + WS - 1) * (2 * WS - 1) + (tx - xj + WS - 1)];
+                        if (((ymask >> yj) | (xmask >> xj)) & 1u) s += kNegMask;
+                        sv[j] = s;
+                    }
+                }
+                float m = sv[0];
+#pragma unroll
+                for (int j = 1; j < CF::CPT; ++j) m = fmaxf(m, sv[j]);
+                s_max[cg * 128 + r] = m;
+                __syncthreads();
+                m = fmaxf(fmaxf(s_max[r], s_max[128 + r]), fmaxf(s_max[256 + r], s_max[384 + r]));
+                const float ml = m * kLog2e;
+                float sum = 0.f;
+                uint32_t pk[CF::CPT / 2];
+#pragma unroll
+                for (int j = 0; j < CF::CPT; j += 2) {
+                    const float p0 = ex2(fmaf(sv[j], kLog2e, -ml)), p1 = ex2(fmaf(sv[j + 1], kLog2e, -ml));
+                    sum += p0 + p1;
+                    pk[j / 2] = pack_f16x2(p0, p1);
+                }
+                s_sum[(hh * 4 + cg) * 128 + r] = sum;
+                {
+                    const uint32_t rowaddr = sb + CF::oP + (col0 >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+                    const uint32_t kin = col0 & 63;                    // key offset inside the 64-key block
+                    if constexpr (CF::CPT == 16) {
+                        st_shared_v4(rowaddr + ((((kin >> 3)) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        st_shared_v4(rowaddr + ((((kin >> 3) + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+                        st_shared_v2(rowaddr + (((kin >> 3) ^ (r & 7)) << 4) + (kin & 7) * 2, pk[0], pk[1]);
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();
+
+                // ---- O_h = P V_h  (K = 128 keys, block-diagonal P)
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    constexpr uint32_t idesc_o = umma_idesc(kFmtF16, kFmtF16, kTileM, DPAD);
+                    const uint32_t vrow = hh * DPAD;                   // first V^T row of this head
+                    const uint32_t voff = (vrow >> 3) * 1024;          // DPAD % 8 == 0 -> row group aligned
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t a = sb + CF::oP + (ks >> 2) * 16384 + (ks & 3) * 32;
+                        const uint32_t bb = sb + CF::oVt + (ks >> 2) * 8192 + voff + (ks & 3) * 32;
+                        umma_f16_ss(tm + CF::tO + hh * DPAD, umma_desc_k_sw128(a), umma_desc_k_sw128(bb), idesc_o,
+                                    ks != 0);
+                    }
+                    commit_mma();
+                }
+                wait_mma();      // P buffer and the S columns are free again
+            }
+
+            // ---------------- drain O (64 columns: 16 per thread), normalise by the row sum -> fp16 A operand
+            {
+                uint32_t acc[16];
+                tmem_ld_x16(tm + CF::tO + lane_addr + cg * 16, acc);
+                tmem_wait_ld();
+                const int hh = (cg * 16) / DPAD;
+                const float* ss = s_sum + hh * 4 * 128 + r;
+                const float inv = 1.f / (ss[0] + ss[128] + ss[256] + ss[384]);
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    pk[j] = pack_f16x2(__uint_as_float(acc[2 * j]) * inv, __uint_as_float(acc[2 * j + 1]) * inv);
+                const uint32_t rowaddr = sb + CF::oO + (r >> 3) * 1024 + (r & 7) * 128;
+                st_shared_v4(rowaddr + (((2 * cg) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                st_shared_v4(rowaddr + (((2 * cg + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+
+            // ---------------- projection partial sum over this group's columns
+            if (tid == 0) {
+                tc_fence_after_sync();
+                constexpr uint32_t idesc_p = umma_idesc(kFmtF16, kFmtF16, kTileM, C);
+                feed_ring(slab_used + 1, my_slabs);
+                const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
+                mbar_wait(bar_full + slot, use & 1);
+                tc_fence_after_sync();
+                const uint32_t a0 = sb + CF::oO, b0 = sb + CF::oRing + slot * kSlabBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_f16_ss(tm + CF::tP, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc_p,
+                                (g | ks) != 0);
+                umma_commit(bar_empty + slot);
+                ++slab_used;
+                if (g == NG - 1) commit_mma();
+            }
+        }
+        wait_mma();
+
+        // ---------------- epilogue: out = x + proj + bias at the un-shifted pixel
+        {
+            const float* xb = x + base;
+            float* ob = out + base;
+#pragma unroll 1
+            for (int gi = cg; gi < CF::NCOLG; gi += 4) {
+                uint32_t acc[16];
+                tmem_ld_x16(tm + CF::tP + lane_addr + gi * 16, acc);      // warp-collective: never under a lane predicate
+                tmem_wait_ld();
+                if (row_valid) {
+                    const float* pc = xb + int64_t(gi * 16) * cstride;
+                    float* po = ob + int64_t(gi * 16) * cstride;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        *po = __ldg(pc) + (__uint_as_float(acc[j]) + s_bproj[gi * 16 + j]);
+                        pc += cstride;
+                        po += cstride;
+                    }
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <class CF>
+int launch_tc(const float* x, const float* alpha, float* out, const void* params, int B, int H, int W, int shift,
+              int channels_last, int32_t* kept_count, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    const Geom geo{B, H, W, shift, W / CF::WS, H / CF::WS, channels_last};
+    const int64_t nwin64 = int64_t(B) * geo.nwx * geo.nwy;
+    if (nwin64 > 0x3fffffffll) return MWA_ERR_UNSUPPORTED;
+    const int nwin = static_cast<int>(nwin64);
+    const ScanWs ws(nwin);
+    if (!workspace || workspace_bytes < ws.total) return MWA_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return MWA_ERR_ALIGNMENT;
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    int32_t* count = reinterpret_cast<int32_t*>(wsp + ws.count);
+    uint8_t* flags = wsp + ws.flags;
+    int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
+    const uint8_t* blk = static_cast<const uint8_t*>(params);
+    const MwaParamLayout L(CF::C, CF::HEADS, CF::WS);
+    if (alpha != nullptr) {
+        mwa_scan_kernel<CF::WS><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        int rc = check_launch("mwa_forward(scan)");
+        if (rc != MWA_OK) return rc;
+    }
+    mwa_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, count);
+    int rc = check_launch("mwa_forward(compact)");
+    if (rc != MWA_OK) return rc;
+    const int smem = CF::oTotal + 1024;
+    MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_tc_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                 "mwa_forward(tc attr)");
+    const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
+    const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+    mwa_tc_kernel<CF><<<grid, kThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo);
+    rc = check_launch("mwa_forward(tcgen05)");
+    if (rc != MWA_OK) return rc;
+    if (kept_count)
+        MWA_TRY_CUDA(cudaMemcpyAsync(kept_count, count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st),
+                     "mwa_forward(kept_count)");
+    return MWA_OK;
+}
+
+template <class CF>
+void prepare_tc(const float* qkv_w, const float* qkv_b, const float* proj_w, float scale, uint8_t* dst,
+                cudaStream_t st) {
+    zero16_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), TcParams<CF>::total / 16);
+    mwa_tc_prepare_kernel<CF><<<148, 256, 0, st>>>(qkv_w, qkv_b, proj_w, scale, dst);
+}
+
+using Cfg192h8 = Cfg<192, 8, 8>;
+using Cfg192h6 = Cfg<192, 6, 8>;
+using Cfg80h8 = Cfg<80, 8, 4>;
+
+}  // namespace
+
+int64_t mwa_tc_param_bytes(int C, int heads, int ws) {
+    if (C == 192 && heads == 8 && ws == 8) return TcParams<Cfg192h8>::total;
+    if (C == 192 && heads == 6 && ws == 8) return TcParams<Cfg192h6>::total;
+    if (C == 80 && heads == 8 && ws == 4) return TcParams<Cfg80h8>::total;
+    return 0;
+}
+
+bool mwa_tc_supported(int C, int heads, int ws, int H, int W, int shift, int channels_last) {
+    (void)H; (void)W; (void)shift; (void)channels_last;
+    return mwa_tc_param_bytes(C, heads, ws) > 0;
+}
+
+int64_t mwa_tc_workspace_bytes(int64_t nwin) { return ScanWs(nwin).total; }
+
+void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
+                           int heads, int ws, float scale, uint8_t* blk, cudaStream_t st) {
+    (void)proj_b;
+    const MwaParamLayout L(C, heads, ws);
+    uint8_t* dst = blk + L.img_wqkv;
+    if (C == 192 && heads == 8 && ws == 8) prepare_tc<Cfg192h8>(qkv_w, qkv_b, proj_w, scale, dst, st);
+    else if (C == 192 && heads == 6 && ws == 8) prepare_tc<Cfg192h6>(qkv_w, qkv_b, proj_w, scale, dst, st);
+    else if (C == 80 && heads == 8 && ws == 4) prepare_tc<Cfg80h8>(qkv_w, qkv_b, proj_w, scale, dst, st);
+}
+
+int mwa_forward_tc(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                   int heads, int ws, int shift, int channels_last, int32_t* kept_count, void* workspace,
+                   int64_t workspace_bytes, cudaStream_t st) {
+    if (C == 192 && heads == 8 && ws == 8)
+        return launch_tc<Cfg192h8>(x, alpha, out, params, B, H, W, shift, channels_last, kept_count, workspace,
+                                   workspace_bytes, st);
+    if (C == 192 && heads == 6 && ws == 8)
+        return launch_tc<Cfg192h6>(x, alpha, out, params, B, H, W, shift, channels_last, kept_count, workspace,
+                                   workspace_bytes, st);
+    if (C == 80 && heads == 8 && ws == 4)
+        return launch_tc<Cfg80h8>(x, alpha, out, params, B, H, W, shift, channels_last, kept_count, workspace,
+                                  workspace_bytes, st);
+    return MWA_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200

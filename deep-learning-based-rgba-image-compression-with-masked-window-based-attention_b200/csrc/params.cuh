@@ -35,6 +35,15 @@ struct GdnParamLayout {
 };
 
 // ---------------------------------------------------------------- masked window attention
+// size of the tcgen05 section (fp16 weight operand images per head group + padded-order qkv bias); mirrors Cfg<> /
+// TcParams<> in mwa_tc.cu.  0 when the head geometry has no tcgen05 mapping.
+__host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
+    const int d = C / heads, dpad = (d + 15) / 16 * 16;
+    if (dpad > 64 || 64 % dpad != 0 || heads % (64 / dpad) != 0 || C % 16 != 0) return 0;
+    const int64_t ng = heads / (64 / dpad), kb = (C + 63) / 64;
+    return ng * (kb * 192 * 128 + int64_t(C) * 128) + ng * 192 * 4;
+}
+
 struct MwaParamLayout {
     int C, heads, ws, N, d, dpad, kblocks;
     int64_t header;     // float[4]: scale, -, -, -
@@ -43,11 +52,9 @@ struct MwaParamLayout {
     int64_t wprojT;     // fp32 [C][C]    proj.weight transposed
     int64_t bproj;      // fp32 [C]
     int64_t bias;       // fp32 [heads][N][N]   expanded relative position bias
-    // fp16 UMMA B-operand images (K-major SW128), used by the tcgen05 kernel
-    int64_t img_wqkv;   // 3 sections (q,k,v); each kblocks x [rows_qkv x 64 k]; q,k rows are head-padded (heads*dpad),
-                        // q rows pre-multiplied by scale; v rows = C
-    int64_t img_wproj;  // kblocks x [C rows x 64 k]
-    int64_t bq_pad;     // fp32 [3][heads*dpad]  bias in the padded q/k row order (q part pre-scaled), v part [C]
+    int64_t img_wqkv;   // tcgen05 section (layout: TcParams<> in mwa_tc.cu): per head group the fp16 K-major SW128
+                        // B-operand slabs of Wq|Wk|Wv (rows head-padded to 16/32, q rows pre-scaled) and of Wproj,
+                        // followed by the qkv bias in the same padded order
     int64_t total;
     __host__ __device__ MwaParamLayout(int C_, int heads_, int ws_)
         : C(C_), heads(heads_), ws(ws_), N(ws_ * ws_), d(C_ / heads_), dpad(int(align_up(C_ / heads_, 16))),
@@ -59,13 +66,9 @@ struct MwaParamLayout {
         wprojT = o;    o = align_up(o + 4ll * C * C, 1024);
         bproj = o;     o = align_up(o + 4ll * C, 1024);
         bias = o;      o = align_up(o + 4ll * heads * N * N, 1024);
-        img_wqkv = o;  o = align_up(o + 3 * qkv_section_bytes(), 1024);
-        img_wproj = o; o = align_up(o + int64_t(kblocks) * align_up(C, 8) * 128, 1024);
-        bq_pad = o;    o = align_up(o + 4ll * 3 * hp(), 1024);
+        img_wqkv = o;  o = align_up(o + mwa_tc_section_bytes(C, heads), 1024);
         total = o;
     }
-    __host__ __device__ int hp() const { return heads * dpad; }          // padded q/k width (>= C)
-    __host__ __device__ int64_t qkv_section_bytes() const { return int64_t(kblocks) * hp() * 128; }
 };
 
 }  // namespace b200

@@ -90,9 +90,10 @@ class WindowAttentionFunction(Function):
         with torch.cuda.device(x.device):
             blk = attn_mod._param_block(qkv_w, qkv_b, proj_w, proj_b, table)
             out = torch.empty_like(x)
+            wsp = torch.empty(int(lib.mwa_workspace_bytes(B, H, W, ws)), dtype=torch.uint8, device=x.device)
             _abi.check(lib.mwa_forward(x.data_ptr(), _abi.ptr(alpha), out.data_ptr(), blk.data_ptr(), B, C, H, W,
                                        attn_mod.num_heads, ws, shift, int(channels_last), algo, None,
-                                       _abi.stream_handle()), "mwa_forward")
+                                       wsp.data_ptr(), wsp.numel(), _abi.stream_handle()), "mwa_forward")
         ctx.cfg = (attn_mod, ws, shift)
         ctx.has_bias = qkv_b is not None
         ctx.save_for_backward(x, alpha, qkv_w, qkv_b, proj_w, proj_b, table)

@@ -84,6 +84,8 @@ MWA_API int gdn_backward(const float* x, const float* grad_y, const float* beta_
  *               x/out logical shape (B, C, H, W), alpha (B, 1, H, W); H % ws == 0 and W % ws == 0
  *               (else MWA_ERR_INVALID, the reference raises in .view); 0 <= shift < ws.
  *               `kept_count` (optional device int32, may be NULL) receives the number of kept windows.
+ *               `workspace` (>= mwa_workspace_bytes(B, H, W, ws) bytes, 16-byte aligned, device) holds the keep flags
+ *               and the compacted list of kept windows of the tcgen05 path; contents are scratch.
  * Supported: ws*ws <= 64 tokens, C % heads == 0, shared memory footprint <= 227 KB (SIMT: C <= 192 at ws 8);
  *            tcgen05: (C, heads, ws) in {(192, 8, 8), (192, 6, 8), (80, 8, 4)}.
  * ------------------------------------------------------------------------------------------------ */
@@ -91,8 +93,10 @@ MWA_API int64_t mwa_param_bytes(int C, int heads, int ws);
 MWA_API int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
                 const float* bias_table, int C, int heads, int ws, float scale, void* params,
                 int64_t params_bytes, void* stream);
+MWA_API int64_t mwa_workspace_bytes(int B, int H, int W, int ws);
 MWA_API int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
-                int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* stream);
+                int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* workspace,
+                int64_t workspace_bytes, void* stream);
 
 /* window_attention_forward : replaces layers/masked_win_attention.py:96-131 / layers/win_attention.py:84-115
  *   (WindowAttention.forward on already-partitioned tokens): xw/out are (K, N, C) with N = ws*ws, `mask` is

@@ -47,9 +47,10 @@ def test_status_strings_and_sizes(lib):
 def test_argument_validation_without_gpu(lib):
     """these return before touching the device"""
     one = ctypes.c_void_p(16)
-    assert lib.mwa_forward(None, None, None, None, 1, 192, 8, 8, 8, 8, 0, 0, 0, None, None) == -1
-    assert lib.mwa_forward(one, None, one, one, 1, 192, 8, 8, 8, 8, 8, 0, 0, None, None) == -1     # shift >= ws
-    assert lib.mwa_forward(one, None, one, one, 1, 192, 12, 8, 8, 8, 0, 0, 0, None, None) == -1    # H % ws
+    assert lib.mwa_forward(None, None, None, None, 1, 192, 8, 8, 8, 8, 0, 0, 0, None, None, 0, None) == -1
+    assert lib.mwa_forward(one, None, one, one, 1, 192, 8, 8, 8, 8, 8, 0, 0, None, None, 0, None) == -1     # shift >= ws
+    assert lib.mwa_forward(one, None, one, one, 1, 192, 12, 8, 8, 8, 0, 0, 0, None, None, 0, None) == -1    # H % ws
+    assert lib.mwa_workspace_bytes(16, 128, 192, 8) >= 5 * 6144
     assert lib.gdn_forward(None, None, None, 1, 192, 64, 0, 0, 0, None) == -1
     assert lib.gdn_forward(one, one, one, 0, 192, 64, 0, 0, 0, None) == 0                          # empty batch
     assert lib.round_ste_forward(one, one, 0, 0, 0, 0, None) == 0                                  # empty input

@@ -122,8 +122,11 @@ def test_attention_is_graph_capturable_and_counts_kept(pkg, cuda_dev, lib):
     blk = m.attn._param_block(m.attn.qkv.weight, m.attn.qkv.bias, m.attn.proj.weight, m.attn.proj.bias,
                               m.attn.relative_position_bias_table)
     o2 = torch.empty_like(x)
+    wsp = torch.empty(int(lib.mwa_workspace_bytes(x.shape[0], x.shape[2], x.shape[3], cfg["ws"])), dtype=torch.uint8,
+                      device=cuda_dev)
     st = lib.mwa_forward(x.data_ptr(), a.data_ptr(), o2.data_ptr(), blk.data_ptr(), *x.shape, cfg["heads"], cfg["ws"],
-                         cfg["shift"], 0, 0, kept.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                         cfg["shift"], 0, 0, kept.data_ptr(), wsp.data_ptr(), wsp.numel(),
+                         torch.cuda.current_stream().cuda_stream)
     assert st == 0
     assert int(kept.item()) == int(R.window_keep(p["alpha"], cfg["ws"], cfg["shift"]).sum())
 
