@@ -33,6 +33,7 @@ _SIGNATURES = {
     "mwa_param_bytes": (c_int64, [c_int, c_int, c_int]),
     "mwa_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                             c_void_p, c_int64, c_void_p]),
+    "mwa_debug_set_timing_buffer": (None, [c_void_p]),
     "mwa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "mwa_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),

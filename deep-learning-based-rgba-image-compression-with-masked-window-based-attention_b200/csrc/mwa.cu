@@ -12,6 +12,7 @@ int mwa_forward_tc(const float* x, const float* alpha, float* out, const void* p
                    int heads, int ws, int shift, int channels_last, int32_t* kept_count, void* workspace,
                    int64_t workspace_bytes, cudaStream_t st);                                                // mwa_tc.cu
 int64_t mwa_tc_workspace_bytes(int64_t nwin);
+void mwa_tc_set_timing_buffer(void* p);
 bool mwa_tc_supported(int C, int heads, int ws, int H, int W, int shift, int channels_last);
 void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
                            int heads, int ws, float scale, uint8_t* blk, cudaStream_t st);                    // mwa_tc.cu
@@ -279,6 +280,8 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     mwa_tc_prepare_images(qkv_w, qkv_b, proj_w, proj_b, C, heads, ws, scale, blk, st);
     return check_launch("mwa_prepare(images)");
 }
+
+void mwa_debug_set_timing_buffer(void* device_u64x16) { mwa_tc_set_timing_buffer(device_u64x16); }
 
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
     if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;

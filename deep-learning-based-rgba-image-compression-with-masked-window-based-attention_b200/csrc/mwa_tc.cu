@@ -31,7 +31,7 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRingSlots = 2;
+constexpr int kRingSlots = 3;
 constexpr uint32_t kSlabBytes = 192 * 128;          // one K block (64 k) of a 192-row weight slab
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNegMask = -100.0f;                 // layers/masked_win_attention.py:214
@@ -68,17 +68,21 @@ struct Cfg {
     static constexpr uint32_t oK = oQ + 16384;
     static constexpr uint32_t oVt = oK + 16384;                         // 2 key blocks x [64 rows x 64 keys]
     static constexpr uint32_t oP = oVt + 16384;                         // 2 key blocks x [128 x 64]
-    static constexpr uint32_t oO = oP + 32768;
-    static constexpr uint32_t oRing = oO + 16384;
+    static constexpr uint32_t oO = oQ;                                  // O_g reuses the Q_g buffer
+    static constexpr uint32_t oRing = oP + 32768;
     static constexpr uint32_t oTbl = oRing + kRingSlots * kSlabBytes;   // fp32 [HEADS][TBL]
     static constexpr uint32_t oBqkv = oTbl + ((HEADS * TBL * 4 + 15) / 16) * 16;   // fp32 [NG][192]
     static constexpr uint32_t oBproj = oBqkv + NG * 192 * 4;
-    static constexpr uint32_t oRedMax = oBproj + C * 4;                 // fp32 [4][128]
-    static constexpr uint32_t oRedSum = oRedMax + 4 * 128 * 4;          // fp32 [HPG][4][128]
+    static constexpr uint32_t oRedMax = oBproj + C * 4;                 // fp32 [2][4][128]
+    static constexpr uint32_t oRedSum = oRedMax + 2 * 4 * 128 * 4;          // fp32 [HPG][4][128]
     static constexpr uint32_t oBars = oRedSum + HPG * 4 * 128 * 4;
-    static constexpr uint32_t oTmem = oBars + 8 * 8;
+    static constexpr uint32_t oTmem = oBars + 16 * 8;
     static constexpr uint32_t oTotal = oTmem + 16;
-    static_assert(oTotal + 1024 <= 227 * 1024, "shared memory budget");
+    static_assert(oTotal <= 227 * 1024, "shared memory budget");
+    // fp32 [C][128] output staging of the NCHW epilogue, over operand buffers that are dead (and fully rewritten
+    // by the next tile) at that point
+    static constexpr uint32_t oStage = (C * 512 <= 3 * 16384) ? oQ : oX;
+    static_assert(oStage + C * 512 <= oP, "output staging must fit the dead operand buffers");
     // TMEM columns
     static constexpr uint32_t tA = 0;        // D_qkv [0,192)  /  S_h [0,128)
     static constexpr uint32_t tO = 256;      // O accumulators of the group: HPG x DPAD = 64 columns
@@ -237,6 +241,9 @@ __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ float ex2(float v) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -249,19 +256,30 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
                  : "memory");
 }
 
-template <class CF>
+// VEC: widest vector (floats) that tiles a window row in memory: 4 when shift % 4 == 0 and W % 4 == 0, else 2 / 1
+template <class CF, int VEC>
 __global__ void __launch_bounds__(kThreads, 1)
 mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
               const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
-              Geom geo) {
+              Geom geo, unsigned long long* __restrict__ timing) {
     constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // optional phase timing (development aid): CTA 0 / thread 0 accumulates clock64() deltas per phase
+    const bool do_time = timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_prev = do_time ? clock64() : 0;
+    auto tick = [&](int phase) {
+        if (do_time) {
+            const long long now = clock64();
+            timing[phase] += static_cast<unsigned long long>(now - t_prev);
+            t_prev = now;
+        }
+    };
+    constexpr int XI = (CF::NCHUNK + 3) / 4;            // 16-byte chunks of the x row handled per thread
+    extern __shared__ __align__(1024) uint8_t smem[];   // base is 1024-aligned (checked once below)
     const uint32_t sb = smem_u32(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF::oBars);
-    uint64_t* bar_full = bars;               // [2] weight slab landed
-    uint64_t* bar_empty = bars + 2;          // [2] MMAs reading the slab done
-    uint64_t* bar_mma = bars + 4;            // [2], used alternately: "all MMAs issued so far are complete"
+    uint64_t* bar_full = bars;                           // [kRingSlots] weight slab landed
+    uint64_t* bar_empty = bars + kRingSlots;             // [kRingSlots] MMAs reading the slab done
+    uint64_t* bar_mma = bars + 2 * kRingSlots;           // [2], used alternately: "MMAs issued so far are complete"
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + CF::oTmem);
     float* s_tbl = reinterpret_cast<float*>(smem + CF::oTbl);
     float* s_bqkv = reinterpret_cast<float*>(smem + CF::oBqkv);
@@ -277,10 +295,11 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
 
     // ---- one-time setup
     if (tid == 0) {
-        mbar_init(bar_full + 0, 1);
-        mbar_init(bar_full + 1, 1);
-        mbar_init(bar_empty + 0, 1);
-        mbar_init(bar_empty + 1, 1);
+        if (sb & 1023u) __trap();
+        for (int i = 0; i < kRingSlots; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, 1);
+        }
         mbar_init(bar_mma + 0, 1);
         mbar_init(bar_mma + 1, 1);
         fence_mbar_init();
@@ -294,6 +313,16 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         for (int i = tid; i < C; i += kThreads) s_bproj[i] = bp[i];
         for (int i = tid; i < (CF::oRing - CF::oX) / 16; i += kThreads)
             reinterpret_cast<uint4*>(smem + CF::oX)[i] = make_uint4(0, 0, 0, 0);
+        // compact relative-position table s_tbl[h][idx], idx = (yi-yj+WS-1)*(2WS-1) + (xi-xj+WS-1), recovered from
+        // the expanded bias[h][i][j] of the parameter block (any token pair with that offset carries the value)
+        const float* bexp = reinterpret_cast<const float*>(blk + L.bias);
+        for (int e = tid; e < CF::HEADS * CF::TBL; e += kThreads) {
+            const int h = e / CF::TBL, idx = e % CF::TBL;
+            const int dy = idx / (2 * WS - 1) - (WS - 1), dx = idx % (2 * WS - 1) - (WS - 1);   // yi - yj, xi - xj
+            const int yi = dy >= 0 ? dy : 0, yj = dy >= 0 ? 0 : -dy;
+            const int xi = dx >= 0 ? dx : 0, xj = dx >= 0 ? 0 : -dx;
+            s_tbl[e] = bexp[(int64_t(h) * NTOK + (yi * WS + xi)) * NTOK + (yj * WS + xj)];
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -303,25 +332,42 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     const int count = *count_p;
     const int num_tiles = (count + CF::WPT - 1) / CF::WPT;
     const int64_t hw = int64_t(geo.H) * geo.W;
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
+    const uint32_t my_slabs = uint32_t(my_tiles) * CF::kSlabsPerTile;
 
-    // thread 0 state: weight ring + MMA completion phase
+    // ---- thread 0: weight ring (bulk copies L2 -> smem) and MMA completion tracking
     uint32_t slab_issued = 0, slab_used = 0, mma_waits = 0, mma_commits = 0;
     const uint8_t* wimg = tcp + TcParams<CF>::img;
-    auto slab_src = [&](uint32_t i, uint32_t& bytes) -> const uint8_t* {
-        const uint32_t it = i % CF::kSlabsPerTile, g = it / CF::kSlabsPerGroup, s = it % CF::kSlabsPerGroup;
-        bytes = (s < CF::KB) ? kSlabBytes : CF::kProjSlabBytes;
-        return wimg + int64_t(g) * CF::kGroupBytes + int64_t(s) * kSlabBytes;
+    auto issue_slab = [&]() {
+        const uint32_t slot = slab_issued % kRingSlots;
+        const uint32_t it = slab_issued % CF::kSlabsPerTile, g = it / CF::kSlabsPerGroup, sidx = it % CF::kSlabsPerGroup;
+        const uint32_t bytes = (sidx < uint32_t(CF::KB)) ? kSlabBytes : CF::kProjSlabBytes;
+        mbar_arrive_expect_tx(bar_full + slot, bytes);
+        bulk_g2s(smem + CF::oRing + slot * kSlabBytes, wimg + int64_t(g) * CF::kGroupBytes + int64_t(sidx) * kSlabBytes,
+                 bytes, bar_full + slot);
+        ++slab_issued;
     };
-    auto feed_ring = [&](uint32_t upto, uint32_t total) {        // thread 0 only
-        while (slab_issued <= upto && slab_issued < total) {
+    // keep the ring as full as the completed MMAs allow; never blocks
+    auto feed_try = [&]() {
+        while (slab_issued < my_slabs && slab_issued < slab_used + kRingSlots) {
+            const uint32_t slot = slab_issued % kRingSlots, use = slab_issued / kRingSlots;
+            if (use > 0 && !mbar_test_wait(bar_empty + slot, (use - 1) & 1)) break;
+            issue_slab();
+        }
+    };
+    // slab `slab_used` is needed now: make sure it has been requested, then wait for it
+    auto acquire_slab = [&]() -> uint32_t {
+        while (slab_issued <= slab_used) {
             const uint32_t slot = slab_issued % kRingSlots, use = slab_issued / kRingSlots;
             if (use > 0) mbar_wait(bar_empty + slot, (use - 1) & 1);
-            uint32_t bytes;
-            const uint8_t* src = slab_src(slab_issued, bytes);
-            mbar_arrive_expect_tx(bar_full + slot, bytes);
-            bulk_g2s(smem + CF::oRing + slot * kSlabBytes, src, bytes, bar_full + slot);
-            ++slab_issued;
+            issue_slab();
         }
+        feed_try();
+        const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
+        mbar_wait(bar_full + slot, use & 1);
+        tc_fence_after_sync();
+        return slot;
     };
     // thread 0: commit k goes to barrier k & 1; every thread: wait k on the same barrier with parity (k >> 1) & 1.
     // At most two commits are ever issued between two CTA-wide barriers, so a slow waiter can never be lapped.
@@ -334,69 +380,151 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         ++mma_waits;
         __syncwarp();
         tc_fence_after_sync();
+        if (tid == 0) feed_try();
+        __syncwarp();
     };
 
-    // number of tiles this CTA will process -> total slabs it will consume
-    int my_tiles = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
-    const uint32_t my_slabs = uint32_t(my_tiles) * CF::kSlabsPerTile;
-
-    // compact relative-position table s_tbl[h][idx], idx = (yi-yj+WS-1)*(2WS-1) + (xi-xj+WS-1), recovered from the
-    // expanded bias[h][i][j] of the parameter block (any token pair with that offset carries the same value)
-    {
-        const float* bexp = reinterpret_cast<const float*>(blk + L.bias);
-        for (int e = tid; e < CF::HEADS * CF::TBL; e += kThreads) {
-            const int h = e / CF::TBL, idx = e % CF::TBL;
-            const int dy = idx / (2 * WS - 1) - (WS - 1), dx = idx % (2 * WS - 1) - (WS - 1);   // yi - yj, xi - xj
-            const int yi = dy >= 0 ? dy : 0, yj = dy >= 0 ? 0 : -dy;
-            const int xi = dx >= 0 ? dx : 0, xj = dx >= 0 ? 0 : -dx;
-            s_tbl[e] = bexp[(int64_t(h) * NTOK + (yi * WS + xi)) * NTOK + (yj * WS + xj)];
-        }
-    }
-    __syncthreads();
-
-    if (tid == 0) feed_ring(1, my_slabs);
-
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // ---------------- tile geometry for this thread's token row
-        const int wslot = r / NTOK, t = r % NTOK;
+    // geometry of this thread's token row in a tile
+    const int wslot = r / NTOK, tok = r % NTOK;
+    auto row_base = [&](int tile, bool& valid) -> int64_t {
         const int lidx = tile * CF::WPT + wslot;
-        const bool row_valid = lidx < count;
-        const int win = list[row_valid ? lidx : (count - 1)];
+        valid = lidx < count;
+        const int win = list[valid ? lidx : (count - 1)];
         int b, wy, wx, py, px;
         window_coords(geo, win, b, wy, wx);
-        token_pixel<WS>(geo, wy, wx, t, py, px);
+        token_pixel<WS>(geo, wy, wx, tok, py, px);
         const int64_t pix = int64_t(py) * geo.W + px;
-        const int64_t base = geo.channels_last ? (int64_t(b) * hw + pix) * C : int64_t(b) * C * hw + pix;
-        const int64_t cstride = geo.channels_last ? 1 : hw;
+        return geo.channels_last ? (int64_t(b) * hw + pix) * C : int64_t(b) * C * hw + pix;
+    };
 
-        // ---------------- load x -> fp16 A operand (row r, 16-byte chunks ci = cg, cg+4, ...)
+    if (tid == 0) feed_try();
+    tick(0);                                             // 0: prologue
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        bool row_valid;
+        const int64_t base = row_base(tile, row_valid);
+        int wy, wx;
         {
-            const float* xb = x + base;
+            int b;
+            window_coords(geo, list[row_valid ? tile * CF::WPT + wslot : count - 1], b, wy, wx);
+        }
+
+        // ---------------- load x -> fp16 A operand.
+        // NCHW: lane l owns the 4 consecutive tokens 4l..4l+3 of the tile (one window row or half of it, contiguous
+        // pixels), warp w owns the 8-channel chunks w, w+16: every load instruction moves 512 contiguous-by-row
+        // bytes of one channel.  NHWC: thread (row r, cg) reads its own 32-byte chunks.
+        int64_t gbase[4 / VEC];                 // NCHW: element offset of each VEC-pixel piece of this lane (channel 0)
+        bool lane_valid = false;
+        if (!geo.channels_last) {
+            const int r0 = 4 * lane, ws_l = r0 / NTOK, tok0 = r0 % NTOK;
+            const int lidx = tile * CF::WPT + ws_l;
+            lane_valid = lidx < count;
+            int b, lwy, lwx;
+            window_coords(geo, list[lane_valid ? lidx : count - 1], b, lwy, lwx);
+            int py = lwy * WS + tok0 / WS + geo.shift;
+            if (py >= geo.H) py -= geo.H;
 #pragma unroll
-            for (int ci = cg; ci < CF::NCHUNK; ci += 4) {
-                float v[8];
-                const float* pc = xb + int64_t(ci * 8) * cstride;
+            for (int pc = 0; pc < 4 / VEC; ++pc) {
+                int px = lwx * WS + tok0 % WS + geo.shift + pc * VEC;
+                if (px >= geo.W) px -= geo.W;
+                gbase[pc] = int64_t(b) * C * hw + int64_t(py) * geo.W + px;
+            }
+            constexpr int NCI = (CF::NCHUNK + kWarps - 1) / kWarps;
+            float v[NCI][8][4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[j] = __ldg(pc);
-                    pc += cstride;
+            for (int i = 0; i < NCI; ++i) {
+                const int ci = warp + kWarps * i;
+                if (ci < CF::NCHUNK) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float* pcn = x + int64_t(ci * 8 + j) * hw;
+#pragma unroll
+                        for (int pc = 0; pc < 4 / VEC; ++pc) {
+                            if constexpr (VEC == 4) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(pcn + gbase[pc]));
+                                v[i][j][0] = t4.x; v[i][j][1] = t4.y; v[i][j][2] = t4.z; v[i][j][3] = t4.w;
+                            } else if constexpr (VEC == 2) {
+                                const float2 t2 = __ldg(reinterpret_cast<const float2*>(pcn + gbase[pc]));
+                                v[i][j][2 * pc] = t2.x; v[i][j][2 * pc + 1] = t2.y;
+                            } else {
+                                v[i][j][pc] = __ldg(pcn + gbase[pc]);
+                            }
+                        }
+                    }
                 }
-                const uint32_t addr = sb + CF::oX + (ci >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 +
-                                      (((ci & 7) ^ (r & 7)) << 4);
-                st_shared_v4(addr, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
-                             pack_f16x2(v[6], v[7]));
+            }
+            // Lane l stores its rows in the rotated order 4l + ((k + l/2) & 3): the 8 lanes of every 128-bit store
+            // phase then hit 8 different (row & 7) values, i.e. 8 different 16-byte bank groups of the swizzled
+            // layout (storing row 4l + k from every lane would be a 16-way bank conflict).
+            const int rot = (lane >> 1) & 3;
+#pragma unroll
+            for (int i = 0; i < NCI; ++i) {
+                const int ci = warp + kWarps * i;
+                if (ci < CF::NCHUNK) {
+                    uint32_t pk[4][4];                       // [token k][channel pair]
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp) pk[k][jp] = pack_f16x2(v[i][2 * jp][k], v[i][2 * jp + 1][k]);
+                    // rotate the token index by `rot` with two conditional stages (no dynamic register indexing)
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        uint32_t a0 = pk[0][jp], a1 = pk[1][jp], a2 = pk[2][jp], a3 = pk[3][jp];
+                        if (rot & 1) { const uint32_t t0 = a0; a0 = a1; a1 = a2; a2 = a3; a3 = t0; }
+                        if (rot & 2) { const uint32_t t0 = a0, t1 = a1; a0 = a2; a1 = a3; a2 = t0; a3 = t1; }
+                        pk[0][jp] = a0; pk[1][jp] = a1; pk[2][jp] = a2; pk[3][jp] = a3;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int row = 4 * lane + ((k + rot) & 3);
+                        const uint32_t addr = sb + CF::oX + (ci >> 3) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 +
+                                              (((ci & 7) ^ (row & 7)) << 4);
+                        st_shared_v4(addr, pk[k][0], pk[k][1], pk[k][2], pk[k][3]);
+                    }
+                }
+            }
+        } else {
+            const float* xb = x + base;
+            float4 v[XI][2];
+#pragma unroll
+            for (int i = 0; i < XI; ++i) {
+                const int ci = cg + 4 * i;
+                if (ci < CF::NCHUNK) {
+                    v[i][0] = __ldg(reinterpret_cast<const float4*>(xb + ci * 8));
+                    v[i][1] = __ldg(reinterpret_cast<const float4*>(xb + ci * 8 + 4));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < XI; ++i) {
+                const int ci = cg + 4 * i;
+                if (ci < CF::NCHUNK) {
+                    const uint32_t addr = sb + CF::oX + (ci >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 +
+                                          (((ci & 7) ^ (r & 7)) << 4);
+                    st_shared_v4(addr, pack_f16x2(v[i][0].x, v[i][0].y), pack_f16x2(v[i][0].z, v[i][0].w),
+                                 pack_f16x2(v[i][1].x, v[i][1].y), pack_f16x2(v[i][1].z, v[i][1].w));
+                }
+            }
+        }
+        // the x rows of this CTA's next tile -> L2 (its loads and the residual re-read of the epilogue then hit L2)
+        if (tile + int(gridDim.x) < num_tiles) {
+            bool nv;
+            const float* nb = x + row_base(tile + gridDim.x, nv);
+            if (geo.channels_last) {
+                for (int i = cg; i < (C * 4 + 127) / 128; i += 4) prefetch_l2(nb + i * 32);
+            } else if ((tok % WS) == 0) {            // one sector (or half) per window row and channel
+                for (int c = cg; c < C; c += 4) prefetch_l2(nb + int64_t(c) * hw);
             }
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
+        tick(1);                                         // 1: x load + convert
 
         // SW-MSA region mask bits of this row (:194-216): bit yj of ymask = band(yj) differs from the row's band
         uint32_t ymask = 0, xmask = 0;
         if (geo.shift > 0) {
             const int ys0 = wy * WS, xs0 = wx * WS;
-            const int ty = t / WS, tx = t % WS;
+            const int ty = tok / WS, tx = tok % WS;
             const int by = (ys0 + ty >= geo.H - WS) + (ys0 + ty >= geo.H - geo.shift);
             const int bx = (xs0 + tx >= geo.W - WS) + (xs0 + tx >= geo.W - geo.shift);
 #pragma unroll
@@ -408,6 +536,89 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
         }
 
+        // softmax of one head for this thread's CPT columns; returns packed fp16 probabilities and stores the
+        // partial row sum.  S_h lives at TMEM columns tA + sreg * 128.
+        auto softmax_head = [&](int head, int hh, int sreg, uint32_t (&pk)[CF::CPT / 2]) {
+            const int col0 = wslot * NTOK + cg * CF::CPT;          // first column (key index in the tile)
+            float sv[CF::CPT];
+            {
+                // tcgen05.ld is warp-collective: the column address must be warp-uniform.  With 8x8 windows a warp
+                // lies inside one window; with 4x4 windows it covers two, so both candidates are loaded.
+                uint32_t acc[CF::CPT];
+                const uint32_t sbase = tm + CF::tA + sreg * 128 + lane_addr;
+                if constexpr (CF::CPT == 16) {
+                    tmem_ld_x16(sbase + col0, reinterpret_cast<uint32_t(&)[16]>(acc));
+                    tmem_wait_ld();
+                } else {
+                    uint32_t a0[4], a1[4];
+                    const uint32_t cbase = (r >> 5) * 32 + cg * CF::CPT;
+                    tmem_ld_x4(sbase + cbase, a0);
+                    tmem_ld_x4(sbase + cbase + 16, a1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = (wslot & 1) ? a1[j] : a0[j];
+                }
+                const float* tb = s_tbl + head * CF::TBL;
+                const int ty = tok / WS, tx = tok % WS;
+#pragma unroll
+                for (int j = 0; j < CF::CPT; ++j) {
+                    const int jj = cg * CF::CPT + j;              // key token index in the window
+                    const int yj = jj / WS, xj = jj % WS;
+                    float sc = __uint_as_float(acc[j]) + tb[(ty - yj + WS - 1) * (2 * WS - 1) + (tx - xj + WS - 1)];
+                    if (((ymask >> yj) | (xmask >> xj)) & 1u) sc += kNegMask;
+                    sv[j] = sc;
+                }
+            }
+            float m = sv[0];
+#pragma unroll
+            for (int j = 1; j < CF::CPT; ++j) m = fmaxf(m, sv[j]);
+            float* smx = s_max + (hh & 1) * 512;
+            smx[cg * 128 + r] = m;
+            __syncthreads();
+            m = fmaxf(fmaxf(smx[r], smx[128 + r]), fmaxf(smx[256 + r], smx[384 + r]));
+            const float ml = m * kLog2e;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < CF::CPT; j += 2) {
+                const float p0 = ex2(fmaf(sv[j], kLog2e, -ml)), p1 = ex2(fmaf(sv[j + 1], kLog2e, -ml));
+                sum += p0 + p1;
+                pk[j / 2] = pack_f16x2(p0, p1);
+            }
+            s_sum[(hh * 4 + cg) * 128 + r] = sum;
+        };
+        auto store_p = [&](const uint32_t (&pk)[CF::CPT / 2]) {
+            const int col0 = wslot * NTOK + cg * CF::CPT;
+            const uint32_t rowaddr = sb + CF::oP + (col0 >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+            const uint32_t kin = col0 & 63;                        // key offset inside the 64-key block
+            if constexpr (CF::CPT == 16) {
+                st_shared_v4(rowaddr + ((((kin >> 3)) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                st_shared_v4(rowaddr + ((((kin >> 3) + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+            } else {
+                st_shared_v2(rowaddr + (((kin >> 3) ^ (r & 7)) << 4) + (kin & 7) * 2, pk[0], pk[1]);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+        };
+        auto issue_s = [&](int hh, int sreg) {                     // thread 0
+            constexpr uint32_t idesc_s = umma_idesc(kFmtF16, kFmtF16, kTileM, 128);
+            const uint32_t a0 = sb + CF::oQ + hh * DPAD * 2, b0 = sb + CF::oK + hh * DPAD * 2;
+#pragma unroll
+            for (int ks = 0; ks < DPAD / 16; ++ks)
+                umma_f16_ss(tm + CF::tA + sreg * 128, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32),
+                            idesc_s, ks != 0);
+        };
+        auto issue_pv = [&](int hh) {                              // thread 0: O_h = P V_h, K = 128 keys
+            constexpr uint32_t idesc_o = umma_idesc(kFmtF16, kFmtF16, kTileM, DPAD);
+            const uint32_t voff = ((hh * DPAD) >> 3) * 1024;       // first V^T row of this head (row-group aligned)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t a = sb + CF::oP + (ks >> 2) * 16384 + (ks & 3) * 32;
+                const uint32_t bb = sb + CF::oVt + (ks >> 2) * 8192 + voff + (ks & 3) * 32;
+                umma_f16_ss(tm + CF::tO + hh * DPAD, umma_desc_k_sw128(a), umma_desc_k_sw128(bb), idesc_o, ks != 0);
+            }
+        };
+
         for (int g = 0; g < NG; ++g) {
             // ---------------- QKV GEMM for this head group
             if (tid == 0) {
@@ -415,10 +626,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, 192);
 #pragma unroll 1
                 for (int kb = 0; kb < CF::KB; ++kb) {
-                    feed_ring(slab_used + 1, my_slabs);
-                    const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
-                    mbar_wait(bar_full + slot, use & 1);
-                    tc_fence_after_sync();
+                    const uint32_t slot = acquire_slab();
                     const uint32_t a0 = sb + CF::oX + kb * 16384, b0 = sb + CF::oRing + slot * kSlabBytes;
                     const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
                     for (int ks = 0; ks < nks; ++ks)
@@ -429,7 +637,9 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 }
                 commit_mma();
             }
+            tick(2);                                     // 2: QKV issue (incl. waiting for weight slabs)
             wait_mma();
+            tick(3);                                     // 3: QKV MMA completion wait
 
             // ---------------- drain: q (cg 0) / k (cg 1) / v (cg 2), + bias, -> fp16 operands
             if (cg < 3) {
@@ -464,101 +674,44 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
+            tick(4);                                     // 4: q/k/v drain
 
-            // ---------------- heads of the group
-            for (int hh = 0; hh < HPG; ++hh) {
-                const int head = g * HPG + hh;
+            // ---------------- heads of the group, two at a time: both score tiles are issued up front and the PV
+            //                  MMA of the first head runs under the softmax arithmetic of the second
+            for (int hp = 0; hp < HPG; hp += 2) {
                 if (tid == 0) {
                     tc_fence_after_sync();
-                    constexpr uint32_t idesc_s = umma_idesc(kFmtF16, kFmtF16, kTileM, 128);
-                    const uint32_t a0 = sb + CF::oQ + hh * DPAD * 2, b0 = sb + CF::oK + hh * DPAD * 2;
-#pragma unroll
-                    for (int ks = 0; ks < DPAD / 16; ++ks)
-                        umma_f16_ss(tm + CF::tA, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32),
-                                    idesc_s, ks != 0);
+                    issue_s(hp, 0);
+                    issue_s(hp + 1, 1);
                     commit_mma();
                 }
                 wait_mma();
-
-                // ---- softmax over the row's own window: 4 threads per row, CPT columns each
-                const int col0 = wslot * NTOK + cg * CF::CPT;          // first column (key index in the tile)
-                float sv[CF::CPT];
-                {
-                    // tcgen05.ld is warp-collective: the column address must be warp-uniform.  With 8x8 windows a warp
-                    // lies inside one window; with 4x4 windows it covers two, so both candidates are loaded.
-                    uint32_t acc[CF::CPT];
-                    if constexpr (CF::CPT == 16) {
-                        tmem_ld_x16(tm + CF::tA + lane_addr + col0, reinterpret_cast<uint32_t(&)[16]>(acc));
-                        tmem_wait_ld();
-                    } else {
-                        uint32_t a0[4], a1[4];
-                        const uint32_t cbase = (r >> 5) * 32 + cg * CF::CPT;
-                        tmem_ld_x4(tm + CF::tA + lane_addr + cbase, a0);
-                        tmem_ld_x4(tm + CF::tA + lane_addr + cbase + 16, a1);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[j] = (wslot & 1) ? a1[j] : a0[j];
-                    }
-                    const float* tb = s_tbl + head * CF::TBL;
-                    const int ty = t / WS, tx = t % WS;
-#pragma unroll
-                    for (int j = 0; j < CF::CPT; ++j) {
-                        const int jj = cg * CF::CPT + j;              // key token index in the window
-                        const int yj = jj / WS, xj = jj % WS;
-                        float s = __uint_as_float(acc[j]) + tb[(ty - yj + WS - 1) * (2 * WS - 1) + (tx - xj + WS - 1)];
-                        if (((ymask >> yj) | (xmask >> xj)) & 1u) s += kNegMask;
-                        sv[j] = s;
-                    }
-                }
-                float m = sv[0];
-#pragma unroll
-                for (int j = 1; j < CF::CPT; ++j) m = fmaxf(m, sv[j]);
-                s_max[cg * 128 + r] = m;
-                __syncthreads();
-                m = fmaxf(fmaxf(s_max[r], s_max[128 + r]), fmaxf(s_max[256 + r], s_max[384 + r]));
-                const float ml = m * kLog2e;
-                float sum = 0.f;
+                tick(5);                                 // 5: score MMAs
                 uint32_t pk[CF::CPT / 2];
-#pragma unroll
-                for (int j = 0; j < CF::CPT; j += 2) {
-                    const float p0 = ex2(fmaf(sv[j], kLog2e, -ml)), p1 = ex2(fmaf(sv[j + 1], kLog2e, -ml));
-                    sum += p0 + p1;
-                    pk[j / 2] = pack_f16x2(p0, p1);
-                }
-                s_sum[(hh * 4 + cg) * 128 + r] = sum;
-                {
-                    const uint32_t rowaddr = sb + CF::oP + (col0 >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-                    const uint32_t kin = col0 & 63;                    // key offset inside the 64-key block
-                    if constexpr (CF::CPT == 16) {
-                        st_shared_v4(rowaddr + ((((kin >> 3)) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-                        st_shared_v4(rowaddr + ((((kin >> 3) + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
-                    } else {
-                        st_shared_v2(rowaddr + (((kin >> 3) ^ (r & 7)) << 4) + (kin & 7) * 2, pk[0], pk[1]);
-                    }
-                }
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                __syncthreads();
-
-                // ---- O_h = P V_h  (K = 128 keys, block-diagonal P)
+                softmax_head(g * HPG + hp, hp, 0, pk);
+                store_p(pk);
+                tick(6);                                 // 6: softmax + P store, first head
                 if (tid == 0) {
                     tc_fence_after_sync();
-                    constexpr uint32_t idesc_o = umma_idesc(kFmtF16, kFmtF16, kTileM, DPAD);
-                    const uint32_t vrow = hh * DPAD;                   // first V^T row of this head
-                    const uint32_t voff = (vrow >> 3) * 1024;          // DPAD % 8 == 0 -> row group aligned
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t a = sb + CF::oP + (ks >> 2) * 16384 + (ks & 3) * 32;
-                        const uint32_t bb = sb + CF::oVt + (ks >> 2) * 8192 + voff + (ks & 3) * 32;
-                        umma_f16_ss(tm + CF::tO + hh * DPAD, umma_desc_k_sw128(a), umma_desc_k_sw128(bb), idesc_o,
-                                    ks != 0);
-                    }
+                    issue_pv(hp);
                     commit_mma();
                 }
-                wait_mma();      // P buffer and the S columns are free again
+                softmax_head(g * HPG + hp + 1, hp + 1, 1, pk);
+                tick(7);                                 // 7: softmax second head (PV of the first runs underneath)
+                wait_mma();                      // PV of the first head done: the P buffer is free again
+                store_p(pk);
+                tick(8);                                 // 8: wait PV + P store
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    issue_pv(hp + 1);
+                    commit_mma();
+                }
+                wait_mma();
+                tick(9);                                 // 9: PV second head
             }
 
             // ---------------- drain O (64 columns: 16 per thread), normalise by the row sum -> fp16 A operand
+            //                  (reuses the Q buffer: every score MMA of the group has completed)
             {
                 uint32_t acc[16];
                 tmem_ld_x16(tm + CF::tO + lane_addr + cg * 16, acc);
@@ -577,15 +730,13 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
+            tick(10);                                    // 10: O drain
 
             // ---------------- projection partial sum over this group's columns
             if (tid == 0) {
                 tc_fence_after_sync();
                 constexpr uint32_t idesc_p = umma_idesc(kFmtF16, kFmtF16, kTileM, C);
-                feed_ring(slab_used + 1, my_slabs);
-                const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
-                mbar_wait(bar_full + slot, use & 1);
-                tc_fence_after_sync();
+                const uint32_t slot = acquire_slab();
                 const uint32_t a0 = sb + CF::oO, b0 = sb + CF::oRing + slot * kSlabBytes;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
@@ -595,32 +746,113 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 ++slab_used;
                 if (g == NG - 1) commit_mma();
             }
+            tick(11);                                    // 11: projection issue (incl. slab wait)
         }
-        wait_mma();
 
-        // ---------------- epilogue: out = x + proj + bias at the un-shifted pixel
-        {
+        // ---------------- epilogue: out = x + proj + bias at the un-shifted pixel.
+        // NCHW: the projection tile is staged in shared memory as [channel][token] (the operand buffers are dead now)
+        // and written with the same lane = 4 tokens / warp = channel mapping as the load (512-byte row groups per
+        // store instruction); the residual x loads are issued before waiting for the last projection MMA.
+        if (!geo.channels_last) {
+            constexpr int NCH = (C + kWarps - 1) / kWarps;         // channels per warp
+            float xres[NCH][4];
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int c = warp + kWarps * i;
+                if (c < C) {
+                    const float* pcn = x + int64_t(c) * hw;
+#pragma unroll
+                    for (int pc = 0; pc < 4 / VEC; ++pc) {
+                        if constexpr (VEC == 4) {
+                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(pcn + gbase[pc]));
+                            xres[i][0] = t4.x; xres[i][1] = t4.y; xres[i][2] = t4.z; xres[i][3] = t4.w;
+                        } else if constexpr (VEC == 2) {
+                            const float2 t2 = __ldg(reinterpret_cast<const float2*>(pcn + gbase[pc]));
+                            xres[i][2 * pc] = t2.x; xres[i][2 * pc + 1] = t2.y;
+                        } else {
+                            xres[i][pc] = __ldg(pcn + gbase[pc]);
+                        }
+                    }
+                }
+            }
+            tick(12);                                    // 12: residual loads issued
+            wait_mma();
+            tick(13);                                    // 13: wait last projection
+            float* stage = reinterpret_cast<float*>(smem + CF::oStage);
+            constexpr int EG = (CF::NCOLG + 3) / 4;
+#pragma unroll
+            for (int i = 0; i < EG; ++i) {
+                const int gi = cg + 4 * i;
+                if (gi < CF::NCOLG) {                   // warp-uniform (cg): tcgen05.ld stays warp-collective
+                    uint32_t acc[16];
+                    tmem_ld_x16(tm + CF::tP + lane_addr + gi * 16, acc);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        stage[(gi * 16 + j) * kTileM + r] = __uint_as_float(acc[j]) + s_bproj[gi * 16 + j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int c = warp + kWarps * i;
+                if (c < C && lane_valid) {
+                    const float4 sv = *reinterpret_cast<const float4*>(stage + c * kTileM + 4 * lane);
+                    float* pon = out + int64_t(c) * hw;
+                    const float o0 = xres[i][0] + sv.x, o1 = xres[i][1] + sv.y, o2 = xres[i][2] + sv.z,
+                                o3 = xres[i][3] + sv.w;
+                    if constexpr (VEC == 4) {
+                        *reinterpret_cast<float4*>(pon + gbase[0]) = make_float4(o0, o1, o2, o3);
+                    } else if constexpr (VEC == 2) {
+                        *reinterpret_cast<float2*>(pon + gbase[0]) = make_float2(o0, o1);
+                        *reinterpret_cast<float2*>(pon + gbase[1]) = make_float2(o2, o3);
+                    } else {
+                        pon[gbase[0]] = o0; pon[gbase[1]] = o1; pon[gbase[2]] = o2; pon[gbase[3]] = o3;
+                    }
+                }
+            }
+        } else {
+            constexpr int EG = (CF::NCOLG + 3) / 4;
             const float* xb = x + base;
             float* ob = out + base;
-#pragma unroll 1
-            for (int gi = cg; gi < CF::NCOLG; gi += 4) {
-                uint32_t acc[16];
-                tmem_ld_x16(tm + CF::tP + lane_addr + gi * 16, acc);      // warp-collective: never under a lane predicate
-                tmem_wait_ld();
-                if (row_valid) {
-                    const float* pc = xb + int64_t(gi * 16) * cstride;
-                    float* po = ob + int64_t(gi * 16) * cstride;
+            float4 xres[EG][4];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        *po = __ldg(pc) + (__uint_as_float(acc[j]) + s_bproj[gi * 16 + j]);
-                        pc += cstride;
-                        po += cstride;
+            for (int i = 0; i < EG; ++i) {
+                const int gi = cg + 4 * i;
+                if (gi < CF::NCOLG) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xres[i][j] = __ldg(reinterpret_cast<const float4*>(xb + gi * 16 + 4 * j));
+                }
+            }
+            tick(12);
+            wait_mma();
+            tick(13);
+#pragma unroll
+            for (int i = 0; i < EG; ++i) {
+                const int gi = cg + 4 * i;
+                if (gi < CF::NCOLG) {
+                    uint32_t acc[16];
+                    tmem_ld_x16(tm + CF::tP + lane_addr + gi * 16, acc);
+                    tmem_wait_ld();
+                    if (row_valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float* bp = s_bproj + gi * 16 + 4 * j;
+                            float4 o;
+                            o.x = xres[i][j].x + (__uint_as_float(acc[4 * j + 0]) + bp[0]);
+                            o.y = xres[i][j].y + (__uint_as_float(acc[4 * j + 1]) + bp[1]);
+                            o.z = xres[i][j].z + (__uint_as_float(acc[4 * j + 2]) + bp[2]);
+                            o.w = xres[i][j].w + (__uint_as_float(acc[4 * j + 3]) + bp[3]);
+                            *reinterpret_cast<float4*>(ob + gi * 16 + 4 * j) = o;
+                        }
                     }
                 }
             }
         }
         tc_fence_before_sync();
         __syncthreads();
+        tick(14);                                        // 14: epilogue stores
+        if (do_time) timing[15] += 1;                    // 15: tiles
     }
 
     tc_fence_before_sync();
@@ -629,6 +861,8 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+unsigned long long* g_timing = nullptr;     // development aid, see mwa_debug_set_timing_buffer
+
 template <class CF>
 int launch_tc(const float* x, const float* alpha, float* out, const void* params, int B, int H, int W, int shift,
               int channels_last, int32_t* kept_count, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
@@ -653,12 +887,21 @@ int launch_tc(const float* x, const float* alpha, float* out, const void* params
     mwa_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, count);
     int rc = check_launch("mwa_forward(compact)");
     if (rc != MWA_OK) return rc;
-    const int smem = CF::oTotal + 1024;
-    MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_tc_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-                 "mwa_forward(tc attr)");
+    const int smem = CF::oTotal;
     const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
     const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-    mwa_tc_kernel<CF><<<grid, kThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo);
+    const int vec = (shift % 4 == 0 && W % 4 == 0) ? 4 : (shift % 2 == 0 && W % 2 == 0) ? 2 : 1;
+#define MWA_LAUNCH_TC(V)                                                                                            \
+    do {                                                                                                            \
+        MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_tc_kernel<CF, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), \
+                     "mwa_forward(tc attr)");                                                                       \
+        mwa_tc_kernel<CF, V><<<grid, kThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,         \
+                                                          g_timing);                                                \
+    } while (0)
+    if (vec == 4) MWA_LAUNCH_TC(4);
+    else if (vec == 2) MWA_LAUNCH_TC(2);
+    else MWA_LAUNCH_TC(1);
+#undef MWA_LAUNCH_TC
     rc = check_launch("mwa_forward(tcgen05)");
     if (rc != MWA_OK) return rc;
     if (kept_count)
@@ -693,6 +936,7 @@ bool mwa_tc_supported(int C, int heads, int ws, int H, int W, int shift, int cha
 }
 
 int64_t mwa_tc_workspace_bytes(int64_t nwin) { return ScanWs(nwin).total; }
+void mwa_tc_set_timing_buffer(void* p) { g_timing = static_cast<unsigned long long*>(p); }
 
 void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
                            int heads, int ws, float scale, uint8_t* blk, cudaStream_t st) {
