@@ -281,7 +281,7 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     return check_launch("mwa_prepare(images)");
 }
 
-void mwa_debug_set_timing_buffer(void* device_u64x16) { mwa_tc_set_timing_buffer(device_u64x16); }
+void mwa_debug_set_timing_buffer(void* device_u64x32) { mwa_tc_set_timing_buffer(device_u64x32); }
 
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
     if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;

@@ -31,8 +31,6 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRingSlots = 3;
-constexpr uint32_t kSlabBytes = 192 * 128;          // one K block (64 k) of a 192-row weight slab
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNegMask = -100.0f;                 // layers/masked_win_attention.py:214
 
@@ -56,10 +54,14 @@ struct Cfg {
     static constexpr int NCHUNK = C / 8;                  // 16-byte fp16 chunks per token row
     static constexpr int NCOLG = C / 16;                  // 16-column groups of the projection output
     static constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
+    static constexpr int NQ = HPG * D;                    // un-padded q (k, v) columns of a head group
+    static constexpr int NQKV = (3 * NQ + 15) / 16 * 16;  // rows of a QKV weight slab = columns of D_qkv
+    static constexpr uint32_t kQkvSlabBytes = NQKV * 128;
     static constexpr uint32_t kProjSlabBytes = C * 128;
-    static constexpr uint32_t kGroupBytes = KB * kSlabBytes + kProjSlabBytes;
-    static constexpr int kSlabsPerGroup = KB + 1;
-    static constexpr int kSlabsPerTile = NG * kSlabsPerGroup;
+    static constexpr uint32_t kGroupBytes = KB * kQkvSlabBytes + kProjSlabBytes;
+    static_assert(NQ % 8 == 0 && kQkvSlabBytes % 1024 == 0 && kProjSlabBytes % 1024 == 0, "slab geometry");
+    // QKV slab ring: a whole group (KB slabs) when it fits the 227 KB budget, else 2 slots
+    static constexpr int kQSlots = (3 * kQkvSlabBytes + kProjSlabBytes <= 80 * 1024) ? 3 : 2;
     static_assert(C % 16 == 0 && HEADS % HPG == 0 && DPAD * HPG == 64, "unsupported head geometry");
     static_assert(kTileM % NTOK == 0 && (CPT == 16 || CPT == 4), "unsupported window size");
     // shared memory map (offsets from a 1024-aligned base)
@@ -69,10 +71,11 @@ struct Cfg {
     static constexpr uint32_t oVt = oK + 16384;                         // 2 key blocks x [64 rows x 64 keys]
     static constexpr uint32_t oP = oVt + 16384;                         // 2 key blocks x [128 x 64]
     static constexpr uint32_t oO = oQ;                                  // O_g reuses the Q_g buffer
-    static constexpr uint32_t oRing = oP + 32768;
-    static constexpr uint32_t oTbl = oRing + kRingSlots * kSlabBytes;   // fp32 [HEADS][TBL]
-    static constexpr uint32_t oBqkv = oTbl + ((HEADS * TBL * 4 + 15) / 16) * 16;   // fp32 [NG][192]
-    static constexpr uint32_t oBproj = oBqkv + NG * 192 * 4;
+    static constexpr uint32_t oRing = oP + 32768;                        // kQSlots QKV slabs, then 1 projection slab
+    static constexpr uint32_t oRingP = oRing + kQSlots * kQkvSlabBytes;
+    static constexpr uint32_t oTbl = oRingP + kProjSlabBytes;           // fp32 [HEADS][TBL]
+    static constexpr uint32_t oBqkv = oTbl + ((HEADS * TBL * 4 + 15) / 16) * 16;   // fp32 [NG][NQKV]
+    static constexpr uint32_t oBproj = oBqkv + NG * NQKV * 4;
     static constexpr uint32_t oRedMax = oBproj + C * 4;                 // fp32 [2][4][128]
     static constexpr uint32_t oRedSum = oRedMax + 2 * 4 * 128 * 4;          // fp32 [HPG][4][128]
     static constexpr uint32_t oBars = oRedSum + HPG * 4 * 128 * 4;
@@ -94,7 +97,7 @@ template <class CF>
 struct TcParams {
     static constexpr int64_t img = 0;                                          // NG x kGroupBytes
     static constexpr int64_t bq = img + int64_t(CF::NG) * CF::kGroupBytes;     // fp32 [NG][192] padded order
-    static constexpr int64_t total = bq + CF::NG * 192 * 4;
+    static constexpr int64_t total = bq + CF::NG * CF::NQKV * 4;
 };
 
 // ------------------------------------------------------------------------------------------------ prepare
@@ -103,31 +106,30 @@ __global__ void mwa_tc_prepare_kernel(const float* __restrict__ qkv_w, const flo
                                       const float* __restrict__ proj_w, float scale, uint8_t* __restrict__ out) {
     constexpr int C = CF::C, D = CF::D, DPAD = CF::DPAD, HPG = CF::HPG;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    // qkv slabs
-    for (int e = tid; e < CF::NG * 192 * C; e += nth) {
-        const int g = e / (192 * C), n = (e / C) % 192, k = e % C;
-        const int part = n / 64, hh = (n % 64) / DPAD, c = (n % 64) % DPAD;
-        float v = 0.f;
-        if (c < D) {
-            v = qkv_w[int64_t(part * C + (g * HPG + hh) * D + c) * C + k];
-            if (part == 0) v *= scale;
-        }
-        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(k / 64) * kSlabBytes + sw128_offset(n, k % 64);
+    // qkv slabs: row n of group g = part (q|k|v) * NQ + head-in-group * D + c   (no padding inside the slab; rows
+    // 3*NQ .. NQKV-1 stay zero); q rows and the q bias are pre-multiplied by the softmax scale
+    constexpr int NQ = CF::NQ, NQKV = CF::NQKV;
+    for (int e = tid; e < CF::NG * 3 * NQ * C; e += nth) {
+        const int g = e / (3 * NQ * C), n = (e / C) % (3 * NQ), k = e % C;
+        const int part = n / NQ, hh = (n % NQ) / D, c = (n % NQ) % D;
+        float v = qkv_w[int64_t(part * C + (g * HPG + hh) * D + c) * C + k];
+        if (part == 0) v *= scale;
+        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(k / 64) * CF::kQkvSlabBytes + sw128_offset(n, k % 64);
         *reinterpret_cast<__half*>(out + TcParams<CF>::img + off) = __float2half_rn(v);
     }
-    // projection slabs: rows = output channel, K = this group's 64 padded O columns
+    // projection slabs: rows = output channel, K = this group's 64 head-padded O columns
     for (int e = tid; e < CF::NG * C * 64; e += nth) {
         const int g = e / (C * 64), n = (e / 64) % C, kk = e % 64;
         const int hh = kk / DPAD, c = kk % DPAD;
         const float v = (c < D) ? proj_w[int64_t(n) * C + (g * HPG + hh) * D + c] : 0.f;
-        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(CF::KB) * kSlabBytes + sw128_offset(n, kk);
+        const int64_t off = int64_t(g) * CF::kGroupBytes + int64_t(CF::KB) * CF::kQkvSlabBytes + sw128_offset(n, kk);
         *reinterpret_cast<__half*>(out + TcParams<CF>::img + off) = __float2half_rn(v);
     }
-    for (int e = tid; e < CF::NG * 192; e += nth) {
-        const int g = e / 192, n = e % 192;
-        const int part = n / 64, hh = (n % 64) / DPAD, c = (n % 64) % DPAD;
+    for (int e = tid; e < CF::NG * NQKV; e += nth) {
+        const int g = e / NQKV, n = e % NQKV;
         float v = 0.f;
-        if (c < D && qkv_b != nullptr) {
+        if (n < 3 * NQ && qkv_b != nullptr) {
+            const int part = n / NQ, hh = (n % NQ) / D, c = (n % NQ) % D;
             v = qkv_b[part * C + (g * HPG + hh) * D + c];
             if (part == 0) v *= scale;
         }
@@ -166,8 +168,9 @@ __device__ __forceinline__ void token_pixel(const Geom& g, int wy, int wx, int t
     if (x >= g.W) x -= g.W;
 }
 
-// one warp per window: keep = (sum alpha != 0); dropped windows are copied through
-template <int WS>
+// one warp per window: keep = (sum alpha != 0); dropped windows are copied through (the block is the identity
+// there).  NCHW copy: lane = 4 consecutive tokens (VEC-wide pieces, as in the main kernel), 8 channels in flight.
+template <int WS, int VEC>
 __global__ void __launch_bounds__(256)
 mwa_scan_kernel(const float* __restrict__ x, const float* __restrict__ alpha, float* __restrict__ out, Geom g, int C,
                 int nwin, uint8_t* __restrict__ flags) {
@@ -189,20 +192,62 @@ mwa_scan_kernel(const float* __restrict__ x, const float* __restrict__ alpha, fl
     if (keep) return;
     const int64_t hw = int64_t(g.H) * g.W;
     if (!g.channels_last) {
-        for (int e = lane; e < NTOK * C; e += 32) {
-            const int c = e / NTOK, t = e % NTOK;
-            int y, xx;
-            token_pixel<WS>(g, wy, wx, t, y, xx);
-            const int64_t off = (int64_t(b) * C + c) * hw + int64_t(y) * g.W + xx;
-            out[off] = __ldg(x + off);
+        constexpr int GROUPS = NTOK / 4;                  // token groups of 4 (16 for 8x8, 4 for 4x4 windows)
+        constexpr int CPI = 32 / GROUPS;                  // channels covered by one warp iteration (2 / 8)
+        const int grp = lane % GROUPS, csub = lane / GROUPS;
+        const int tok0 = grp * 4;
+        int py = wy * WS + tok0 / WS + g.shift;
+        if (py >= g.H) py -= g.H;
+        int64_t off[4 / VEC];
+#pragma unroll
+        for (int pc = 0; pc < 4 / VEC; ++pc) {
+            int px = wx * WS + tok0 % WS + g.shift + pc * VEC;
+            if (px >= g.W) px -= g.W;
+            off[pc] = int64_t(b) * C * hw + int64_t(py) * g.W + px;
+        }
+        constexpr int U = 4;                              // iterations in flight
+        for (int c0 = csub; c0 < C; c0 += CPI * U) {
+            float v[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * CPI;
+                if (c < C) {
+#pragma unroll
+                    for (int pc = 0; pc < 4 / VEC; ++pc) {
+                        const float* src = x + int64_t(c) * hw + off[pc];
+                        if constexpr (VEC == 4) {
+                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(src));
+                            v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
+                        } else if constexpr (VEC == 2) {
+                            const float2 t2 = __ldg(reinterpret_cast<const float2*>(src));
+                            v[u][2 * pc] = t2.x; v[u][2 * pc + 1] = t2.y;
+                        } else {
+                            v[u][pc] = __ldg(src);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * CPI;
+                if (c < C) {
+#pragma unroll
+                    for (int pc = 0; pc < 4 / VEC; ++pc) {
+                        float* dst = out + int64_t(c) * hw + off[pc];
+                        if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                        else if constexpr (VEC == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[u][2 * pc], v[u][2 * pc + 1]);
+                        else *dst = v[u][pc];
+                    }
+                }
+            }
         }
     } else {
-        for (int e = lane; e < NTOK * C; e += 32) {
-            const int t = e / C, c = e % C;
+        for (int t = 0; t < NTOK; ++t) {                  // NHWC: a token is C contiguous floats
             int y, xx;
             token_pixel<WS>(g, wy, wx, t, y, xx);
-            const int64_t off = ((int64_t(b) * g.H + y) * g.W + xx) * C + c;
-            out[off] = __ldg(x + off);
+            const int64_t o = ((int64_t(b) * g.H + y) * g.W + xx) * C;
+            for (int c = lane * 4; c < C; c += 128)
+                *reinterpret_cast<float4*>(out + o + c) = __ldg(reinterpret_cast<const float4*>(x + o + c));
         }
     }
 }
@@ -277,9 +322,9 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     extern __shared__ __align__(1024) uint8_t smem[];   // base is 1024-aligned (checked once below)
     const uint32_t sb = smem_u32(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF::oBars);
-    uint64_t* bar_full = bars;                           // [kRingSlots] weight slab landed
-    uint64_t* bar_empty = bars + kRingSlots;             // [kRingSlots] MMAs reading the slab done
-    uint64_t* bar_mma = bars + 2 * kRingSlots;           // [2], used alternately: "MMAs issued so far are complete"
+    uint64_t* bar_full = bars;                           // [CF::kQSlots + 1] weight slab landed (last: projection slab)
+    uint64_t* bar_empty = bars + (CF::kQSlots + 1);          // [CF::kQSlots + 1] MMAs reading the slab done
+    uint64_t* bar_mma = bars + 2 * (CF::kQSlots + 1);        // [2], used alternately: "MMAs issued so far are complete"
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + CF::oTmem);
     float* s_tbl = reinterpret_cast<float*>(smem + CF::oTbl);
     float* s_bqkv = reinterpret_cast<float*>(smem + CF::oBqkv);
@@ -296,7 +341,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     // ---- one-time setup
     if (tid == 0) {
         if (sb & 1023u) __trap();
-        for (int i = 0; i < kRingSlots; ++i) {
+        for (int i = 0; i < CF::kQSlots + 1; ++i) {
             mbar_init(bar_full + i, 1);
             mbar_init(bar_empty + i, 1);
         }
@@ -308,7 +353,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     {   // padded-order biases; zero the operand buffers whose padding / off-diagonal blocks must read as exact
         // zeros for the whole kernel (Q/K/V pad columns come from zero weight rows)
         const float* bq = reinterpret_cast<const float*>(tcp + TcParams<CF>::bq);
-        for (int i = tid; i < NG * 192; i += kThreads) s_bqkv[i] = bq[i];
+        for (int i = tid; i < NG * CF::NQKV; i += kThreads) s_bqkv[i] = bq[i];
         const float* bp = reinterpret_cast<const float*>(blk + L.bproj);
         for (int i = tid; i < C; i += kThreads) s_bproj[i] = bp[i];
         for (int i = tid; i < (CF::oRing - CF::oX) / 16; i += kThreads)
@@ -334,54 +379,85 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     const int64_t hw = int64_t(geo.H) * geo.W;
     int my_tiles = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
-    const uint32_t my_slabs = uint32_t(my_tiles) * CF::kSlabsPerTile;
-
-    // ---- thread 0: weight ring (bulk copies L2 -> smem) and MMA completion tracking
-    uint32_t slab_issued = 0, slab_used = 0, mma_waits = 0, mma_commits = 0;
+    // ---- thread 0: two weight rings fed with bulk copies (L2 -> smem, TMA engine):
+    //   QKV ring : CF::kQSlots slabs of [NQKV rows x 64 k]; slab i (running index) = K block i % KB of group (i / KB) % NG.
+    //              All slabs of the NEXT group are requested as soon as the MMAs of the current group have
+    //              released the slots, i.e. they travel during the whole attention phase.
+    //   proj slot: one slab [C rows x 64 k] of group i % NG, requested when the previous projection MMA is done.
+    const uint32_t my_qslabs = uint32_t(my_tiles) * NG * CF::KB, my_pslabs = uint32_t(my_tiles) * NG;
+    uint32_t q_issued = 0, q_used = 0, p_issued = 0, p_used = 0, mma_waits = 0, mma_commits = 0;
     const uint8_t* wimg = tcp + TcParams<CF>::img;
-    auto issue_slab = [&]() {
-        const uint32_t slot = slab_issued % kRingSlots;
-        const uint32_t it = slab_issued % CF::kSlabsPerTile, g = it / CF::kSlabsPerGroup, sidx = it % CF::kSlabsPerGroup;
-        const uint32_t bytes = (sidx < uint32_t(CF::KB)) ? kSlabBytes : CF::kProjSlabBytes;
-        mbar_arrive_expect_tx(bar_full + slot, bytes);
-        bulk_g2s(smem + CF::oRing + slot * kSlabBytes, wimg + int64_t(g) * CF::kGroupBytes + int64_t(sidx) * kSlabBytes,
-                 bytes, bar_full + slot);
-        ++slab_issued;
-    };
-    // keep the ring as full as the completed MMAs allow; never blocks
-    auto feed_try = [&]() {
-        while (slab_issued < my_slabs && slab_issued < slab_used + kRingSlots) {
-            const uint32_t slot = slab_issued % kRingSlots, use = slab_issued / kRingSlots;
-            if (use > 0 && !mbar_test_wait(bar_empty + slot, (use - 1) & 1)) break;
-            issue_slab();
+    uint64_t* bar_pfull = bar_full + CF::kQSlots;
+    uint64_t* bar_pempty = bar_empty + CF::kQSlots;
+    // All ring / MMA-issue code below is executed by the WHOLE warp 0 in convergence (uniform state in every lane);
+    // the instructions with side effects are issued by one elected lane.  (A lone thread 0 issuing while its 31
+    // siblings spin in mbarrier.try_wait shares the warp's issue slot with that spin loop and is stalled by its
+    // hardware suspend: measured ~200 cycles per MMA issue and ~500 per barrier probe.)
+    auto issue_q = [&]() {
+        const uint32_t slot = q_issued % CF::kQSlots, g = (q_issued / CF::KB) % NG, kb = q_issued % CF::KB;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full + slot, CF::kQkvSlabBytes);
+            bulk_g2s(smem + CF::oRing + slot * CF::kQkvSlabBytes,
+                     wimg + int64_t(g) * CF::kGroupBytes + int64_t(kb) * CF::kQkvSlabBytes, CF::kQkvSlabBytes,
+                     bar_full + slot);
         }
+        __syncwarp();
+        ++q_issued;
     };
-    // slab `slab_used` is needed now: make sure it has been requested, then wait for it
-    auto acquire_slab = [&]() -> uint32_t {
-        while (slab_issued <= slab_used) {
-            const uint32_t slot = slab_issued % kRingSlots, use = slab_issued / kRingSlots;
+    auto issue_p = [&]() {
+        const uint32_t g = p_issued % NG;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_pfull, CF::kProjSlabBytes);
+            bulk_g2s(smem + CF::oRingP, wimg + int64_t(g) * CF::kGroupBytes + int64_t(CF::KB) * CF::kQkvSlabBytes,
+                     CF::kProjSlabBytes, bar_pfull);
+        }
+        __syncwarp();
+        ++p_issued;
+    };
+    // keep both rings as full as the completed MMAs allow; never blocks
+    auto feed_try = [&]() {
+        while (q_issued < my_qslabs && q_issued < q_used + CF::kQSlots) {
+            const uint32_t slot = q_issued % CF::kQSlots, use = q_issued / CF::kQSlots;
+            if (use > 0 && !mbar_test_wait(bar_empty + slot, (use - 1) & 1)) break;
+            issue_q();
+        }
+        if (p_issued < my_pslabs && p_issued == p_used &&
+            (p_issued == 0 || mbar_test_wait(bar_pempty, (p_issued - 1) & 1)))
+            issue_p();
+    };
+    auto acquire_q = [&]() -> uint32_t {                 // slab `q_used` is needed now
+        while (q_issued <= q_used) {
+            const uint32_t slot = q_issued % CF::kQSlots, use = q_issued / CF::kQSlots;
             if (use > 0) mbar_wait(bar_empty + slot, (use - 1) & 1);
-            issue_slab();
+            issue_q();
         }
         feed_try();
-        const uint32_t slot = slab_used % kRingSlots, use = slab_used / kRingSlots;
+        const uint32_t slot = q_used % CF::kQSlots, use = q_used / CF::kQSlots;
         mbar_wait(bar_full + slot, use & 1);
         tc_fence_after_sync();
         return slot;
     };
+    auto acquire_p = [&]() {
+        if (p_issued <= p_used) {
+            if (p_issued > 0) mbar_wait(bar_pempty, (p_issued - 1) & 1);
+            issue_p();
+        }
+        mbar_wait(bar_pfull, p_used & 1);
+        tc_fence_after_sync();
+    };
     // thread 0: commit k goes to barrier k & 1; every thread: wait k on the same barrier with parity (k >> 1) & 1.
     // At most two commits are ever issued between two CTA-wide barriers, so a slow waiter can never be lapped.
-    auto commit_mma = [&]() {
-        umma_commit(bar_mma + (mma_commits & 1));
+    auto commit_mma = [&]() {                             // warp 0
+        if (elect_one()) umma_commit(bar_mma + (mma_commits & 1));
+        __syncwarp();
         ++mma_commits;
     };
     auto wait_mma = [&]() {
-        mbar_wait(bar_mma + (mma_waits & 1), (mma_waits >> 1) & 1);
+        mbar_wait_sleep(bar_mma + (mma_waits & 1), (mma_waits >> 1) & 1);
         ++mma_waits;
         __syncwarp();
         tc_fence_after_sync();
-        if (tid == 0) feed_try();
-        __syncwarp();
+        if (warp == 0) feed_try();
     };
 
     // geometry of this thread's token row in a tile
@@ -397,7 +473,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         return geo.channels_last ? (int64_t(b) * hw + pix) * C : int64_t(b) * C * hw + pix;
     };
 
-    if (tid == 0) feed_try();
+    if (warp == 0) feed_try();
     tick(0);                                             // 0: prologue
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -600,40 +676,53 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             tc_fence_before_sync();
             __syncthreads();
         };
-        auto issue_s = [&](int hh, int sreg) {                     // thread 0
+        // descriptors advance by (bytes >> 4) in their low (start address) field; no carry: smem < 256 KB
+        auto issue_s = [&](int hh, int sreg) {                     // warp 0
             constexpr uint32_t idesc_s = umma_idesc(kFmtF16, kFmtF16, kTileM, 128);
-            const uint32_t a0 = sb + CF::oQ + hh * DPAD * 2, b0 = sb + CF::oK + hh * DPAD * 2;
+            const uint64_t a0 = umma_desc_k_sw128(sb + CF::oQ + hh * DPAD * 2);
+            const uint64_t b0 = umma_desc_k_sw128(sb + CF::oK + hh * DPAD * 2);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < DPAD / 16; ++ks)
-                umma_f16_ss(tm + CF::tA + sreg * 128, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32),
-                            idesc_s, ks != 0);
+                for (int ks = 0; ks < DPAD / 16; ++ks)
+                    umma_f16_ss(tm + CF::tA + sreg * 128, a0 + ks * 2, b0 + ks * 2, idesc_s, ks != 0);
+            }
+            __syncwarp();
         };
-        auto issue_pv = [&](int hh) {                              // thread 0: O_h = P V_h, K = 128 keys
+        auto issue_pv = [&](int hh) {                              // warp 0: O_h = P V_h, K = 128 keys
             constexpr uint32_t idesc_o = umma_idesc(kFmtF16, kFmtF16, kTileM, DPAD);
             const uint32_t voff = ((hh * DPAD) >> 3) * 1024;       // first V^T row of this head (row-group aligned)
+            const uint64_t a0 = umma_desc_k_sw128(sb + CF::oP);
+            const uint64_t b0 = umma_desc_k_sw128(sb + CF::oVt + voff);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t a = sb + CF::oP + (ks >> 2) * 16384 + (ks & 3) * 32;
-                const uint32_t bb = sb + CF::oVt + (ks >> 2) * 8192 + voff + (ks & 3) * 32;
-                umma_f16_ss(tm + CF::tO + hh * DPAD, umma_desc_k_sw128(a), umma_desc_k_sw128(bb), idesc_o, ks != 0);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16_ss(tm + CF::tO + hh * DPAD, a0 + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2,
+                                b0 + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, idesc_o, ks != 0);
             }
+            __syncwarp();
         };
 
         for (int g = 0; g < NG; ++g) {
             // ---------------- QKV GEMM for this head group
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after_sync();
-                constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, 192);
-#pragma unroll 1
+                constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, CF::NQKV);
+#pragma unroll
                 for (int kb = 0; kb < CF::KB; ++kb) {
-                    const uint32_t slot = acquire_slab();
-                    const uint32_t a0 = sb + CF::oX + kb * 16384, b0 = sb + CF::oRing + slot * kSlabBytes;
+                    long long tq0 = do_time ? clock64() : 0;
+                    const uint32_t slot = acquire_q();
+                    if (do_time) timing[16 + kb] += static_cast<unsigned long long>(clock64() - tq0);
+                    const uint64_t a0 = umma_desc_k_sw128(sb + CF::oX + kb * 16384);
+                    const uint64_t b0 = umma_desc_k_sw128(sb + CF::oRing + slot * CF::kQkvSlabBytes);
                     const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
-                    for (int ks = 0; ks < nks; ++ks)
-                        umma_f16_ss(tm + CF::tA, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc,
-                                    (kb | ks) != 0);
-                    umma_commit(bar_empty + slot);
-                    ++slab_used;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (ks < nks) umma_f16_ss(tm + CF::tA, a0 + ks * 2, b0 + ks * 2, idesc, (kb | ks) != 0);
+                        umma_commit(bar_empty + slot);
+                    }
+                    __syncwarp();
+                    ++q_used;
                 }
                 commit_mma();
             }
@@ -641,33 +730,63 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             wait_mma();
             tick(3);                                     // 3: QKV MMA completion wait
 
-            // ---------------- drain: q (cg 0) / k (cg 1) / v (cg 2), + bias, -> fp16 operands
+            // ---------------- drain: q (cg 0) / k (cg 1) / v (cg 2): NQ un-padded accumulator columns + bias -> fp16,
+            //                  re-spaced to the head-padded operand layout (pad columns written as zeros)
             if (cg < 3) {
-                const float* bias = s_bqkv + g * 192 + cg * 64;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    uint32_t acc[16];
-                    tmem_ld_x16(tm + CF::tA + lane_addr + cg * 64 + cc * 16, acc);
-                    tmem_wait_ld();
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + bias[cc * 16 + j];
+                constexpr int NQ = CF::NQ, D = CF::D;
+                const float* bias = s_bqkv + g * CF::NQKV + cg * NQ;
+                const uint32_t rowaddr = sb + (cg == 0 ? CF::oQ : CF::oK) + (r >> 3) * 1024 + (r & 7) * 128;
+                const uint32_t kbase = sb + CF::oVt + (r >> 6) * 8192;      // V^T: key block of token row r
+                const uint32_t kk = r & 63;
+                auto put8 = [&](int ch, const float (&v)[8]) {   // 8 padded columns 8*ch .. 8*ch+7 of this row
                     if (cg < 2) {
-                        const uint32_t rowaddr = sb + (cg == 0 ? CF::oQ : CF::oK) + (r >> 3) * 1024 + (r & 7) * 128;
-                        st_shared_v4(rowaddr + (((2 * cc) ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]),
-                                     pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-                        st_shared_v4(rowaddr + (((2 * cc + 1) ^ (r & 7)) << 4), pack_f16x2(v[8], v[9]),
-                                     pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                        st_shared_v4(rowaddr + ((ch ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
+                                     pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
                     } else {
-                        // V^T: row = channel (cc*16 + j), K index = key = token row r (key block r / 64)
-                        const uint32_t kbase = sb + CF::oVt + (r >> 6) * 8192;
-                        const uint32_t kk = r & 63;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t row = cc * 16 + j;
+                        for (int j = 0; j < 8; ++j) {
                             const __half hv = __float2half_rn(v[j]);
-                            st_shared_u16(kbase + sw128_offset(row, kk), *reinterpret_cast<const uint16_t*>(&hv));
+                            st_shared_u16(kbase + sw128_offset(8 * ch + j, kk), *reinterpret_cast<const uint16_t*>(&hv));
                         }
+                    }
+                };
+                if constexpr (D % 8 == 0) {
+#pragma unroll
+                    for (int hh = 0; hh < HPG; ++hh)
+#pragma unroll
+                        for (int ci = 0; ci < DPAD / 8; ++ci) {
+                            float v[8];
+                            if (ci * 8 < D) {
+                                uint32_t acc[8];
+                                tmem_ld_x8(tm + CF::tA + lane_addr + cg * NQ + hh * D + ci * 8, acc);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]) + bias[hh * D + ci * 8 + j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                            }
+                            put8(hh * (DPAD / 8) + ci, v);
+                        }
+                } else {
+                    float val[NQ];
+#pragma unroll
+                    for (int cc = 0; cc < NQ / 8; ++cc) {
+                        uint32_t acc[8];
+                        tmem_ld_x8(tm + CF::tA + lane_addr + cg * NQ + cc * 8, acc);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) val[cc * 8 + j] = __uint_as_float(acc[j]) + bias[cc * 8 + j];
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = 8 * ch + j;
+                            v[j] = ((col % DPAD) < D) ? val[(col / DPAD) * D + (col % DPAD)] : 0.f;
+                        }
+                        put8(ch, v);
                     }
                 }
             }
@@ -679,7 +798,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             // ---------------- heads of the group, two at a time: both score tiles are issued up front and the PV
             //                  MMA of the first head runs under the softmax arithmetic of the second
             for (int hp = 0; hp < HPG; hp += 2) {
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after_sync();
                     issue_s(hp, 0);
                     issue_s(hp + 1, 1);
@@ -691,7 +810,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 softmax_head(g * HPG + hp, hp, 0, pk);
                 store_p(pk);
                 tick(6);                                 // 6: softmax + P store, first head
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after_sync();
                     issue_pv(hp);
                     commit_mma();
@@ -701,7 +820,7 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 wait_mma();                      // PV of the first head done: the P buffer is free again
                 store_p(pk);
                 tick(8);                                 // 8: wait PV + P store
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after_sync();
                     issue_pv(hp + 1);
                     commit_mma();
@@ -733,17 +852,18 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             tick(10);                                    // 10: O drain
 
             // ---------------- projection partial sum over this group's columns
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after_sync();
                 constexpr uint32_t idesc_p = umma_idesc(kFmtF16, kFmtF16, kTileM, C);
-                const uint32_t slot = acquire_slab();
-                const uint32_t a0 = sb + CF::oO, b0 = sb + CF::oRing + slot * kSlabBytes;
+                acquire_p();
+                const uint64_t a0 = umma_desc_k_sw128(sb + CF::oO), b0 = umma_desc_k_sw128(sb + CF::oRingP);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_f16_ss(tm + CF::tP, umma_desc_k_sw128(a0 + ks * 32), umma_desc_k_sw128(b0 + ks * 32), idesc_p,
-                                (g | ks) != 0);
-                umma_commit(bar_empty + slot);
-                ++slab_used;
+                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tm + CF::tP, a0 + ks * 2, b0 + ks * 2, idesc_p, (g | ks) != 0);
+                    umma_commit(bar_pempty);
+                }
+                __syncwarp();
+                ++p_used;
                 if (g == NG - 1) commit_mma();
             }
             tick(11);                                    // 11: projection issue (incl. slab wait)
@@ -879,8 +999,11 @@ int launch_tc(const float* x, const float* alpha, float* out, const void* params
     int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
     const uint8_t* blk = static_cast<const uint8_t*>(params);
     const MwaParamLayout L(CF::C, CF::HEADS, CF::WS);
+    const int vec = (shift % 4 == 0 && W % 4 == 0) ? 4 : (shift % 2 == 0 && W % 2 == 0) ? 2 : 1;
     if (alpha != nullptr) {
-        mwa_scan_kernel<CF::WS><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        if (vec == 4) mwa_scan_kernel<CF::WS, 4><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        else if (vec == 2) mwa_scan_kernel<CF::WS, 2><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        else mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
         int rc = check_launch("mwa_forward(scan)");
         if (rc != MWA_OK) return rc;
     }
@@ -890,7 +1013,6 @@ int launch_tc(const float* x, const float* alpha, float* out, const void* params
     const int smem = CF::oTotal;
     const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
     const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-    const int vec = (shift % 4 == 0 && W % 4 == 0) ? 4 : (shift % 2 == 0 && W % 2 == 0) ? 2 : 1;
 #define MWA_LAUNCH_TC(V)                                                                                            \
     do {                                                                                                            \
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_tc_kernel<CF, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), \

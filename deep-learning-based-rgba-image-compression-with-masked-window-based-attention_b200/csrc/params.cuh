@@ -40,8 +40,9 @@ struct GdnParamLayout {
 __host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
     const int d = C / heads, dpad = (d + 15) / 16 * 16;
     if (dpad > 64 || 64 % dpad != 0 || heads % (64 / dpad) != 0 || C % 16 != 0) return 0;
-    const int64_t ng = heads / (64 / dpad), kb = (C + 63) / 64;
-    return ng * (kb * 192 * 128 + int64_t(C) * 128) + ng * 192 * 4;
+    const int64_t hpg = 64 / dpad, ng = heads / hpg, kb = (C + 63) / 64;
+    const int64_t nqkv = (3 * hpg * d + 15) / 16 * 16;
+    return ng * (kb * nqkv * 128 + int64_t(C) * 128) + ng * nqkv * 4;
 }
 
 struct MwaParamLayout {

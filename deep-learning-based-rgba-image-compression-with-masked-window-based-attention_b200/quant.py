@@ -67,6 +67,8 @@ class _QuantizeOffset(Function):
                 if (mrows, mn) != (rows, n):
                     if mrows == 1 and rows > 1:
                         sm = n                       # contiguous mu viewed with x's row split
+                    elif rows == 1 and mrows > 1 and mrows * mn == n:
+                        rows, n, sx = mrows, mn, mn  # contiguous x viewed with mu's row split
                     else:
                         mu = mu.contiguous()
                         sm = n if rows > 1 else mu.numel()
@@ -100,9 +102,16 @@ class _LrpAdd(Function):
         if y_hat.shape != lrp.shape:
             raise _abi.MwaB200Error("lrp_add: shapes differ")
         y_hat, (rows, n, sy) = _as_rows(y_hat)
-        lrp = lrp.contiguous()
+        lrp, (lrows, ln, sl) = _as_rows(lrp)
+        if (lrows, ln) != (rows, n):                 # bring both operands to a common row split
+            if rows == 1 and lrows > 1 and ln * lrows == n:
+                rows, n, sy = lrows, ln, ln
+            elif lrows == 1 and rows > 1:
+                sl = n
+            else:
+                lrp = lrp.contiguous()
+                sl = n if rows > 1 else lrp.numel()
         out = torch.empty(y_hat.shape, dtype=y_hat.dtype, device=y_hat.device)
-        sl = n if rows > 1 else lrp.numel()
         with torch.cuda.device(y_hat.device):
             _abi.check(lib.lrp_add_forward(y_hat.data_ptr(), lrp.data_ptr(), out.data_ptr(), rows, n, sy, sl, n,
                                            _abi.stream_handle()), "lrp_add_forward")

@@ -12,7 +12,7 @@ x = torch.randn(16, C, H, W, device=dev); a = torch.ones(16, 1, H, W, device=dev
 lib = pkg._abi.load()
 with torch.no_grad():
     for _ in range(3): m(x, a)
-    buf = torch.zeros(16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
     lib.mwa_debug_set_timing_buffer(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
@@ -21,6 +21,7 @@ t = buf.cpu().tolist(); tiles = max(t[15], 1)
 names = ["prologue", "x load+convert", "QKV issue (slab waits)", "QKV MMA wait", "qkv drain", "score MMA wait", "softmax0+P store",
          "softmax1", "PV0 wait+P store", "PV1 wait", "O drain", "proj issue (slab wait)", "residual loads issue", "last proj wait", "epilogue stores"]
 tot = sum(t[:15])
+print("  acquire_q wait cycles per tile by K block:", [round(v / tiles) for v in t[16:20]])
 print(f"{what}: kernel+scan {e0.elapsed_time(e1)*1e3:.0f} us, CTA0 tiles {tiles}, cycles/tile {sum(t[1:15])/tiles:.0f}")
 for n, v in zip(names, t):
     print(f"  {n:28s} {v:10d} cyc  {100*v/tot:5.1f}%  per tile {v/tiles:8.0f}")
