@@ -59,6 +59,13 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -66,7 +73,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool kInverse>
+template <bool kInverse, bool kNHWC>
 __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ blk, int64_t hw,
               int64_t tiles_per_img, int64_t num_tiles) {
@@ -122,25 +129,46 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
             const int64_t p0 = (tile - img * tiles_per_img) * kTileM;
             // rows past the end of the image re-read its last pixel (never stored): no predication on the loads
             const int64_t pp = (p0 + p < hw) ? p0 + p : hw - 1;
-            const float* pc = x + (img * kC + cg * 16) * hw + pp;
+            if constexpr (kNHWC) {
+                // a pixel is 192 contiguous floats: this thread's 16 channels of every chunk are 64 contiguous bytes
+                const float* pc = x + (img * hw + pp) * kC + cg * 16;
 #pragma unroll
-            for (int kc = 0; kc < kChunks; ++kc) {
-                const float* pj = pc;
+                for (int kc = 0; kc < kChunks; ++kc)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    xr[kc * 16 + j] = ld_stream(pj);
-                    pj += hw;
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t4 = ld_stream4(pc + kc * kChunkK + 4 * j);
+                        xr[kc * 16 + 4 * j + 0] = t4.x;
+                        xr[kc * 16 + 4 * j + 1] = t4.y;
+                        xr[kc * 16 + 4 * j + 2] = t4.z;
+                        xr[kc * 16 + 4 * j + 3] = t4.w;
+                    }
+            } else {
+                const float* pc = x + (img * kC + cg * 16) * hw + pp;
+#pragma unroll
+                for (int kc = 0; kc < kChunks; ++kc) {
+                    const float* pj = pc;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        xr[kc * 16 + j] = ld_stream(pj);
+                        pj += hw;
+                    }
+                    pc += chunk_stride;
                 }
-                pc += chunk_stride;
             }
         };
-        auto prefetch_tile = [&](int64_t nt) {                 // 768 lines of 128 B, 512 compute threads
+        auto prefetch_tile = [&](int64_t nt) {                 // 768 lines of 128 B, 512 threads
             if (nt >= num_tiles) return;
             const int64_t nimg = nt / tiles_per_img;
             const int64_t np0 = (nt - nimg * tiles_per_img) * kTileM;
-            const float* nb = x + (nimg * kC) * hw + np0;
-            for (int i = tid; i < kC * 4; i += kComputeWarps * 32)
-                if (np0 + (i & 3) * 32 < hw) prefetch_l2(nb + int64_t(i >> 2) * hw + (i & 3) * 32);
+            if constexpr (kNHWC) {
+                const float* nb = x + (nimg * hw + np0) * kC;
+                const int64_t lines = ((hw - np0 < kTileM ? hw - np0 : kTileM) * kC * 4 + 127) / 128;
+                for (int i = tid; i < lines; i += kComputeWarps * 32) prefetch_l2(nb + int64_t(i) * 32);
+            } else {
+                const float* nb = x + (nimg * kC) * hw + np0;
+                for (int i = tid; i < kC * 4; i += kComputeWarps * 32)
+                    if (np0 + (i & 3) * 32 < hw) prefetch_l2(nb + int64_t(i >> 2) * hw + (i & 3) * 32);
+            }
         };
 
         if (int64_t(blockIdx.x) < num_tiles) load_tile(blockIdx.x);
@@ -214,7 +242,7 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
             // (3) epilogue: n = D + beta ; y = x * n^(-/+ 1/2)
             mbar_wait(bar_dfull, it & 1);
             tc_fence_after_sync();
-            float* yc = y + (img * kC + cg * 16) * hw + p0 + p;
+            float* yc = kNHWC ? y + (img * hw + p0 + p) * kC + cg * 16 : y + (img * kC + cg * 16) * hw + p0 + p;
 #pragma unroll
             for (int kc = 0; kc < kChunks; ++kc) {
                 uint32_t acc[16], xv[16];
@@ -226,17 +254,31 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<float4*>(bt + 4 * j) = *reinterpret_cast<const float4*>(s_beta + ch0 + 4 * j);
                 tmem_wait_ld();
-                float* yj = yc;
+                float res[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float n = __uint_as_float(acc[j]) + bt[j];
                     float r;
                     if (kInverse) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
                     else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
-                    if (valid) *yj = __uint_as_float(xv[j]) * r;
-                    yj += hw;
+                    res[j] = __uint_as_float(xv[j]) * r;
                 }
-                yc += chunk_stride;
+                if constexpr (kNHWC) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(yc + kc * kChunkK + 4 * j) =
+                                make_float4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
+                    }
+                } else {
+                    float* yj = yc;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (valid) *yj = res[j];
+                        yj += hw;
+                    }
+                    yc += chunk_stride;
+                }
             }
         }
     }
@@ -249,7 +291,17 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
 }  // namespace
 
 bool gdn_tc_supported(int C, int64_t hw, int channels_last) {
-    return C == kC && !channels_last && hw >= 1;
+    (void)channels_last;
+    return C == kC && hw >= 1;
+}
+
+template <bool kInverse, bool kNHWC>
+static int launch_gdn_tc(const float* x, float* y, const uint8_t* blk, int64_t hw, int64_t tiles_per_img,
+                         int64_t num_tiles, int grid, int smem, cudaStream_t st) {
+    MWA_TRY_CUDA(cudaFuncSetAttribute(gdn_tc_kernel<kInverse, kNHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                 "gdn_forward(tc attr)");
+    gdn_tc_kernel<kInverse, kNHWC><<<grid, kThreads, smem, st>>>(x, y, blk, hw, tiles_per_img, num_tiles);
+    return check_launch("gdn_forward(tcgen05)");
 }
 
 int gdn_forward_tc(const float* x, float* y, const void* params, int64_t n_img, int C, int64_t hw, int inverse,
@@ -260,16 +312,11 @@ int gdn_forward_tc(const float* x, float* y, const void* params, int64_t n_img, 
     const int grid = static_cast<int>(num_tiles < kNumSMs ? num_tiles : kNumSMs);
     const int smem = Smem::total + 1024;
     const uint8_t* blk = static_cast<const uint8_t*>(params);
-    if (inverse) {
-        MWA_TRY_CUDA(cudaFuncSetAttribute(gdn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-                     "gdn_forward(tc attr)");
-        gdn_tc_kernel<true><<<grid, kThreads, smem, st>>>(x, y, blk, hw, tiles_per_img, num_tiles);
-    } else {
-        MWA_TRY_CUDA(cudaFuncSetAttribute(gdn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-                     "gdn_forward(tc attr)");
-        gdn_tc_kernel<false><<<grid, kThreads, smem, st>>>(x, y, blk, hw, tiles_per_img, num_tiles);
-    }
-    return check_launch("gdn_forward(tcgen05)");
+    if (inverse)
+        return channels_last ? launch_gdn_tc<true, true>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st)
+                             : launch_gdn_tc<true, false>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st);
+    return channels_last ? launch_gdn_tc<false, true>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st)
+                         : launch_gdn_tc<false, false>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st);
 }
 
 }  // namespace b200

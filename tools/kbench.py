@@ -62,6 +62,16 @@ def bench_gdn(args, dev, flush):
                 print(f"gdn inverse={int(inverse)} {B}x192x{H}x{W} {name:8s} median {med:8.3f} ms  best {best:8.3f} ms  "
                       f"{gb / med * 1e3:8.1f} GB/s  = {gb / med * 1e3 / PEAKS['hbm_gbs'] * 100:5.1f}% of measured HBM peak",
                       flush=True)
+            # channels_last (NHWC) input through the same module
+            xcl = x.contiguous(memory_format=torch.channels_last)
+            m.algo = pkg.ALGO_TCGEN05
+            with torch.no_grad():
+                ycl = m(xcl)
+                med, best = timeit(lambda: m(xcl), args.iters, flush)
+            gb = x.numel() * 8 / 1e9
+            print(f"gdn inverse={int(inverse)} {B}x192x{H}x{W} tc-NHWC  median {med:8.3f} ms  best {best:8.3f} ms  "
+                  f"{gb / med * 1e3:8.1f} GB/s  = {gb / med * 1e3 / PEAKS['hbm_gbs'] * 100:5.1f}% of measured HBM peak; "
+                  f"max |NHWC - NCHW| {(ycl - res['tcgen05']).abs().max().item():.2e}", flush=True)
             if len(res) == 2:
                 d = (res["simt"] - res["tcgen05"]).abs()
                 rel = d / (res["simt"].abs() + 1e-4 / 1e-3)
