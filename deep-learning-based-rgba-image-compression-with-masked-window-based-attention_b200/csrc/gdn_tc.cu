@@ -69,6 +69,9 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -130,13 +133,17 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
             // rows past the end of the image re-read its last pixel (never stored): no predication on the loads
             const int64_t pp = (p0 + p < hw) ? p0 + p : hw - 1;
             if constexpr (kNHWC) {
-                // a pixel is 192 contiguous floats: this thread's 16 channels of every chunk are 64 contiguous bytes
-                const float* pc = x + (img * hw + pp) * kC + cg * 16;
+                // NHWC: a pixel is 192 contiguous floats.  Coalesced mapping, independent of the TMEM lane mapping:
+                // for chunk kc, piece idx = tid + 512 j (j < 4) is float4 #(idx & 15) of the chunk's 64 channels of
+                // pixel idx >> 4  ->  a warp reads two 256-byte runs per instruction.
+                const float* tb = x + (img * hw) * kC;
 #pragma unroll
                 for (int kc = 0; kc < kChunks; ++kc)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 t4 = ld_stream4(pc + kc * kChunkK + 4 * j);
+                        const int idx = tid + 512 * j;
+                        const int64_t px = p0 + (idx >> 4);
+                        const float4 t4 = ld_stream4(tb + (px < hw ? px : hw - 1) * kC + kc * kChunkK + 4 * (idx & 15));
                         xr[kc * 16 + 4 * j + 0] = t4.x;
                         xr[kc * 16 + 4 * j + 1] = t4.y;
                         xr[kc * 16 + 4 * j + 2] = t4.z;
@@ -197,13 +204,25 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                     const float h0 = __uint_as_float(hi[j] << 16), h1 = __uint_as_float(hi[j] & 0xffff0000u);
                     lo[j] = pack_bf16x2(s0 - h0, s1 - h1);
                 }
+                // (TMEM columns [256,448) of this thread's lane are its private scratch for the fp32 values)
                 tmem_st_x16(tmem_x + lane_addr + kc * kChunkK + cg * 16, raw);
-                const uint32_t row = sbase + Smem::a_ring + slot * kSlotBytes + (p >> 3) * 1024 + (p & 7) * 128;
-                const uint32_t c0 = ((2 * cg) ^ (p & 7)) * 16, c1 = ((2 * cg + 1) ^ (p & 7)) * 16;
-                st_shared_v4(row + c0, hi[0], hi[1], hi[2], hi[3]);
-                st_shared_v4(row + c1, hi[4], hi[5], hi[6], hi[7]);
-                st_shared_v4(row + kAHalfBytes + c0, lo[0], lo[1], lo[2], lo[3]);
-                st_shared_v4(row + kAHalfBytes + c1, lo[4], lo[5], lo[6], lo[7]);
+                if constexpr (kNHWC) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {          // piece j: pixel (tid + 512 j) >> 4, channels 4*(idx & 15)..+3
+                        const int idx = tid + 512 * j, px = idx >> 4, c4 = idx & 15;
+                        const uint32_t a = sbase + Smem::a_ring + slot * kSlotBytes + (px >> 3) * 1024 + (px & 7) * 128 +
+                                           (((c4 >> 1) ^ (px & 7)) << 4) + (c4 & 1) * 8;
+                        st_shared_v2(a, hi[2 * j], hi[2 * j + 1]);
+                        st_shared_v2(a + kAHalfBytes, lo[2 * j], lo[2 * j + 1]);
+                    }
+                } else {
+                    const uint32_t row = sbase + Smem::a_ring + slot * kSlotBytes + (p >> 3) * 1024 + (p & 7) * 128;
+                    const uint32_t c0 = ((2 * cg) ^ (p & 7)) * 16, c1 = ((2 * cg + 1) ^ (p & 7)) * 16;
+                    st_shared_v4(row + c0, hi[0], hi[1], hi[2], hi[3]);
+                    st_shared_v4(row + c1, hi[4], hi[5], hi[6], hi[7]);
+                    st_shared_v4(row + kAHalfBytes + c0, lo[0], lo[1], lo[2], lo[3]);
+                    st_shared_v4(row + kAHalfBytes + c1, lo[4], lo[5], lo[6], lo[7]);
+                }
                 fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core
                 tc_fence_before_sync();              // (also orders this thread's earlier tcgen05.ld of D)
                 __syncwarp();
@@ -242,7 +261,51 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
             // (3) epilogue: n = D + beta ; y = x * n^(-/+ 1/2)
             mbar_wait(bar_dfull, it & 1);
             tc_fence_after_sync();
-            float* yc = kNHWC ? y + (img * hw + p0 + p) * kC + cg * 16 : y + (img * kC + cg * 16) * hw + p0 + p;
+            if constexpr (kNHWC) {
+                // NHWC epilogue: the lane = pixel role turns the accumulator into r = n^(-/+ 1/2) and hands it, through
+                // a swizzled fp32 staging tile in a (now idle) A-ring slot, to the coalesced role that owns x.
+                float* yt = y + (img * hw) * kC;
+#pragma unroll
+                for (int kc = 0; kc < kChunks; ++kc) {
+                    const uint32_t stage = sbase + Smem::a_ring + (kc & 1) * kSlotBytes;   // [128 px][64 ch] fp32
+                    uint32_t acc[16], xv[16];
+                    const int ch0 = kc * kChunkK + cg * 16;
+                    tmem_ld_x16(tmem_d + lane_addr + ch0, acc);
+                    tmem_ld_x16(tmem_x + lane_addr + ch0, xv);
+                    float bt[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(bt + 4 * j) = *reinterpret_cast<const float4*>(s_beta + ch0 + 4 * j);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float rr[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float n = __uint_as_float(acc[4 * j + i]) + bt[4 * j + i];
+                            if (kInverse) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr[i]) : "f"(n));
+                            else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rr[i]) : "f"(n));
+                        }
+                        st_shared_v4(stage + p * 256 + (((cg * 4 + j) ^ (p & 15)) << 4), __float_as_uint(rr[0]),
+                                     __float_as_uint(rr[1]), __float_as_uint(rr[2]), __float_as_uint(rr[3]));
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int idx = tid + 512 * j, px = idx >> 4, c4 = idx & 15;
+                        float4 r4;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                                     : "r"(stage + px * 256 + ((c4 ^ (px & 15)) << 4)));
+                        if (p0 + px < hw)
+                            *reinterpret_cast<float4*>(yt + (p0 + px) * kC + kc * kChunkK + 4 * c4) =
+                                make_float4(__uint_as_float(xv[4 * j]) * r4.x, __uint_as_float(xv[4 * j + 1]) * r4.y,
+                                            __uint_as_float(xv[4 * j + 2]) * r4.z, __uint_as_float(xv[4 * j + 3]) * r4.w);
+                    }
+                }
+                __syncthreads();       // staging lives in the A ring: the next tile's operand stores must wait
+            } else {
+            float* yc = y + (img * kC + cg * 16) * hw + p0 + p;
 #pragma unroll
             for (int kc = 0; kc < kChunks; ++kc) {
                 uint32_t acc[16], xv[16];
@@ -254,31 +317,18 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<float4*>(bt + 4 * j) = *reinterpret_cast<const float4*>(s_beta + ch0 + 4 * j);
                 tmem_wait_ld();
-                float res[16];
+                float* yj = yc;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float n = __uint_as_float(acc[j]) + bt[j];
                     float r;
                     if (kInverse) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
                     else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
-                    res[j] = __uint_as_float(xv[j]) * r;
+                    if (valid) *yj = __uint_as_float(xv[j]) * r;
+                    yj += hw;
                 }
-                if constexpr (kNHWC) {
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<float4*>(yc + kc * kChunkK + 4 * j) =
-                                make_float4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
-                    }
-                } else {
-                    float* yj = yc;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (valid) *yj = res[j];
-                        yj += hw;
-                    }
-                    yc += chunk_stride;
-                }
+                yc += chunk_stride;
+            }
             }
         }
     }
