@@ -431,7 +431,6 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             if (use > 0) mbar_wait(bar_empty + slot, (use - 1) & 1);
             issue_q();
         }
-        feed_try();
         const uint32_t slot = q_used % CF::kQSlots, use = q_used / CF::kQSlots;
         mbar_wait(bar_full + slot, use & 1);
         tc_fence_after_sync();

@@ -21,9 +21,22 @@ using namespace b200;
     } while (0)
 
 // A: [128][K] 16-bit row-major, B: [N][K] 16-bit row-major, D: [128][N] fp32
+// D[tmem] (+)= A * B^T with a lane mask: bit i of mask[k] set = TMEM lane 32k+i is NOT written
+__device__ __forceinline__ void umma_f16_ss_masked(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                   uint32_t m3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
+
+// mode 0: plain.  mode 1: accumulator pre-filled with 7.0, MMA issued with lanes 64..127 disabled.
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, float* __restrict__ D, int N, int K,
-             uint32_t fmt) {
+             uint32_t fmt, int mode) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -53,6 +66,18 @@ probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, flo
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_d = tmem_base_s;
+    if (mode == 1) {
+        for (int c0 = 0; c0 < N; c0 += 8) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+                             tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0),
+                         "r"(__float_as_uint(7.0f))
+                         : "memory");
+        }
+        tmem_wait_st();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
 
     if (warp == 0 && elect_one()) {
         const uint32_t idesc = umma_idesc(fmt, fmt, 128, N);
@@ -61,7 +86,8 @@ probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, flo
             const int kb = ks / 4, kin = ks % 4;
             uint64_t ad = umma_desc_k_sw128(smem_u32(sA + kb * 128 * 128) + kin * 32);
             uint64_t bd = umma_desc_k_sw128(smem_u32(sB + kb * N * 128) + kin * 32);
-            umma_f16_ss(tmem_d, ad, bd, idesc, ks > 0);
+            if (mode == 1) umma_f16_ss_masked(tmem_d, ad, bd, idesc, 1, 0u, 0u, 0xffffffffu, 0xffffffffu);
+            else umma_f16_ss(tmem_d, ad, bd, idesc, ks > 0);
         }
         umma_commit(&bar);
     }
@@ -98,7 +124,7 @@ static float h2f(uint16_t u, uint32_t fmt) {
     return __bfloat162float(h);
 }
 
-static int run_case(int N, int K, uint32_t fmt) {
+static int run_case(int N, int K, uint32_t fmt, int mode = 0) {
     std::vector<uint16_t> hA(128 * K), hB(N * K);
     std::vector<float> fA(128 * K), fB(N * K), ref(128 * N), hD(128 * N);
     srand(1234 + N * 7 + K);
@@ -127,17 +153,19 @@ static int run_case(int N, int K, uint32_t fmt) {
     const int kblocks = (K + 63) / 64;
     const int smem = kblocks * (128 + N) * 128;
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, fmt);
+    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, fmt, mode);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0;
     for (size_t i = 0; i < hD.size(); ++i) {
-        double e = fabs(double(hD[i]) - ref[i]);
+        double want = ref[i];
+        if (mode == 1) want = (i / N < 64) ? ref[i] + 7.0 : 7.0;     // accumulate onto 7.0 / lanes 64..127 untouched
+        double e = fabs(double(hD[i]) - want);
         if (!(e <= maxerr)) maxerr = e;   // catches NaN
     }
     const bool ok = maxerr < 1e-2;
-    printf("probe N=%3d K=%3d fmt=%s  max|err|=%.3e  %s\n", N, K, fmt == kFmtF16 ? "f16 " : "bf16", maxerr,
+    printf("probe N=%3d K=%3d fmt=%s mode=%d  max|err|=%.3e  %s\n", N, K, fmt == kFmtF16 ? "f16 " : "bf16", mode, maxerr,
            ok ? "OK" : "FAIL");
     cudaFree(dA);
     cudaFree(dB);
@@ -153,6 +181,12 @@ int main() {
         for (int K : Ks) bad += run_case(N, K, kFmtF16);
     bad += run_case(192, 192, kFmtBF16);
     bad += run_case(128, 64, kFmtBF16);
+    // lane-masked MMA (disable_output_lane): rows 64..127 must keep their previous contents
+    bad += run_case(64, 64, kFmtF16, 1);
+    bad += run_case(32, 64, kFmtF16, 1);
+    // N = 24 with M = 128 (documented constraint is N % 16 == 0): informational, not counted
+    { int r = run_case(24, 64, kFmtF16, 0); printf("  (N=24 @ M=128 %s)\n", r ? "does NOT work" : "works"); }
+    { int r = run_case(40, 64, kFmtF16, 0); printf("  (N=40 @ M=128 %s)\n", r ? "does NOT work" : "works"); }
     printf(bad ? "PROBE FAILED (%d cases)\n" : "PROBE PASSED\n", bad);
     return bad ? 1 : 0;
 }
