@@ -50,7 +50,6 @@ struct Cfg {
     static constexpr int WPT = kTileM / NTOK;             // windows per tile
     static constexpr int KB = (C + 63) / 64;              // K blocks of the x operand
     static constexpr int KSTEPS = C / 16;
-    static constexpr int CPT = NTOK / 4;                  // softmax columns per thread (4 threads per row)
     static constexpr int NCHUNK = C / 8;                  // 16-byte fp16 chunks per token row
     static constexpr int NCOLG = C / 16;                  // 16-column groups of the projection output
     static constexpr int TBL = (2 * WS - 1) * (2 * WS - 1);
@@ -63,33 +62,33 @@ struct Cfg {
     // QKV slab ring: a whole group (KB slabs) when it fits the 227 KB budget, else 2 slots
     static constexpr int kQSlots = (3 * kQkvSlabBytes + kProjSlabBytes <= 80 * 1024) ? 3 : 2;
     static_assert(C % 16 == 0 && HEADS % HPG == 0 && DPAD * HPG == 64, "unsupported head geometry");
-    static_assert(kTileM % NTOK == 0 && (CPT == 16 || CPT == 4), "unsupported window size");
+    static_assert(kTileM % NTOK == 0 && NTOK % 16 == 0, "unsupported window size");
+    // warp-level attention tasks per head group: (window of the tile) x (head of the group) x (16-row block)
+    static constexpr int RB = NTOK / 16;
+    static constexpr int TASKS = WPT * HPG * RB;
+    static_assert(TASKS % kWarps == 0, "tasks must tile the 16 warps");
     // shared memory map (offsets from a 1024-aligned base)
     static constexpr uint32_t oX = 0;                                   // KB x [128 x 64] fp16
     static constexpr uint32_t oQ = oX + KB * 16384;
     static constexpr uint32_t oK = oQ + 16384;
-    static constexpr uint32_t oVt = oK + 16384;                         // 2 key blocks x [64 rows x 64 keys]
-    static constexpr uint32_t oP = oVt + 16384;                         // 2 key blocks x [128 x 64]
-    static constexpr uint32_t oO = oQ;                                  // O_g reuses the Q_g buffer
-    static constexpr uint32_t oRing = oP + 32768;                        // kQSlots QKV slabs, then 1 projection slab
+    static constexpr uint32_t oV = oK + 16384;                          // [128 keys x 64] like Q / K (not transposed)
+    static constexpr uint32_t oO = oV + 16384;                          // 2 x [128 x 64] head outputs (A operand of proj)
+    static constexpr uint32_t oRing = oO + 32768;                        // kQSlots QKV slabs, then 1 projection slab
     static constexpr uint32_t oRingP = oRing + kQSlots * kQkvSlabBytes;
     static constexpr uint32_t oTbl = oRingP + kProjSlabBytes;           // fp32 [HEADS][TBL]
     static constexpr uint32_t oBqkv = oTbl + ((HEADS * TBL * 4 + 15) / 16) * 16;   // fp32 [NG][NQKV]
     static constexpr uint32_t oBproj = oBqkv + NG * NQKV * 4;
-    static constexpr uint32_t oRedMax = oBproj + C * 4;                 // fp32 [2][4][128]
-    static constexpr uint32_t oRedSum = oRedMax + 2 * 4 * 128 * 4;          // fp32 [HPG][4][128]
-    static constexpr uint32_t oBars = oRedSum + HPG * 4 * 128 * 4;
+    static constexpr uint32_t oBars = (oBproj + C * 4 + 15) / 16 * 16;
     static constexpr uint32_t oTmem = oBars + 16 * 8;
     static constexpr uint32_t oTotal = oTmem + 16;
     static_assert(oTotal <= 227 * 1024, "shared memory budget");
     // fp32 [C][128] output staging of the NCHW epilogue, over operand buffers that are dead (and fully rewritten
     // by the next tile) at that point
     static constexpr uint32_t oStage = (C * 512 <= 3 * 16384) ? oQ : oX;
-    static_assert(oStage + C * 512 <= oP, "output staging must fit the dead operand buffers");
+    static_assert(oStage + C * 512 <= oO, "output staging must fit the dead operand buffers");
     // TMEM columns
-    static constexpr uint32_t tA = 0;        // D_qkv [0,192)  /  S_h [0,128)
-    static constexpr uint32_t tO = 256;      // O accumulators of the group: HPG x DPAD = 64 columns
-    static constexpr uint32_t tP = 320;      // projection accumulator, C columns
+    static constexpr uint32_t tA = 0;        // D_qkv of the current head group, NQKV <= 192 columns
+    static constexpr uint32_t tP = 256;      // projection accumulator, C columns
 };
 
 // layout of the tcgen05 section of the parameter block (offsets from MwaParamLayout::img_wqkv)
@@ -280,12 +279,6 @@ mwa_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __restr
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -294,14 +287,118 @@ __device__ __forceinline__ float ex2(float v) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
-                 : "memory");
-}
 
 // VEC: widest vector (floats) that tiles a window row in memory: 4 when shift % 4 == 0 and W % 4 == 0, else 2 / 1
+// ---- warp-level tensor-core primitives for the per-window attention core (legacy HMMA path: tiles of 16x8x16 keep
+//      the whole softmax of a (window, head, 16-row block) inside one warp's registers -- no TMEM round trip, no
+//      CTA barrier, no single-thread MMA issue for these tiny contractions)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// byte offset of 16-byte chunk `chunk` of row `row` in a [128 rows x 64 fp16] K-major SWIZZLE_128B buffer
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
+    return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+}
+
+// One attention task: rows row0..row0+15 of the tile (all inside one window whose keys are rows key0..key0+NTOK-1)
+// for the head at 16-byte-chunk offset cb of the 64-column group buffers.  S = Q K^T + bias + mask; softmax; O = P V;
+// O / rowsum -> fp16 into the projection operand buffer.  rowmask[i] (i = 0: row lane/4, 1: row lane/4 + 8) holds the
+// SW-MSA band bits of that row: bit yj = its row band differs from key row yj, bit 8 + xj likewise for columns.
+template <class CF>
+__device__ __forceinline__ void attention_task(uint32_t sQ, uint32_t sK, uint32_t sV, uint32_t sO, const float* tb,
+                                               int row0, int key0, int cb, const uint32_t (&rowmask)[2], int lane) {
+    constexpr int WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD;
+    constexpr int KS = DPAD / 16, NT = NTOK / 8, PK = NTOK / 16, ON = DPAD / 8;
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qa[ks], sQ + swz(row0 + (lane & 15), cb + 2 * ks + (lane >> 4)));
+    float sc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t kb[2];
+            ldmatrix_x2(kb, sK + swz(key0 + 8 * n + (lane & 7), cb + 2 * ks + ((lane >> 3) & 1)));
+            mma16816(sc[n], qa[ks], kb);
+        }
+    }
+    // bias + region mask, row maxima (rows lane/4 and lane/4 + 8; a row is spread over the 4 lanes of a quad)
+    const int ta = (row0 + (lane >> 2)) % NTOK, tb2 = ta + 8;
+    const int tya = ta / WS, txa = ta % WS, tyb = tb2 / WS, txb = tb2 % WS;
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = 8 * n + 2 * (lane & 3) + e, yj = j / WS, xj = j % WS;
+            float va = sc[n][e] + tb[(tya - yj + WS - 1) * (2 * WS - 1) + (txa - xj + WS - 1)];
+            float vb = sc[n][2 + e] + tb[(tyb - yj + WS - 1) * (2 * WS - 1) + (txb - xj + WS - 1)];
+            if (((rowmask[0] >> yj) | (rowmask[0] >> (8 + xj))) & 1u) va += kNegMask;
+            if (((rowmask[1] >> yj) | (rowmask[1] >> (8 + xj))) & 1u) vb += kNegMask;
+            sc[n][e] = va;
+            sc[n][2 + e] = vb;
+            ma = fmaxf(ma, va);
+            mb = fmaxf(mb, vb);
+        }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    const float mla = ma * kLog2e, mlb = mb * kLog2e;
+    float suma = 0.f, sumb = 0.f;
+    uint32_t pa[PK][4];                                   // un-normalised probabilities as A fragments of P V
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const float p0 = ex2(fmaf(sc[n][0], kLog2e, -mla)), p1 = ex2(fmaf(sc[n][1], kLog2e, -mla));
+        const float p2 = ex2(fmaf(sc[n][2], kLog2e, -mlb)), p3 = ex2(fmaf(sc[n][3], kLog2e, -mlb));
+        suma += p0 + p1;
+        sumb += p2 + p3;
+        pa[n >> 1][(n & 1) * 2 + 0] = pack_f16x2(p0, p1);
+        pa[n >> 1][(n & 1) * 2 + 1] = pack_f16x2(p2, p3);
+    }
+    suma += __shfl_xor_sync(0xffffffffu, suma, 1);
+    suma += __shfl_xor_sync(0xffffffffu, suma, 2);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 1);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 2);
+    float oc[ON][4];
+#pragma unroll
+    for (int nt = 0; nt < ON; ++nt) oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < PK; ++j)
+#pragma unroll
+        for (int nt = 0; nt < ON; ++nt) {
+            uint32_t vb[2];
+            ldmatrix_x2_trans(vb, sV + swz(key0 + 16 * j + (lane & 7) + 8 * ((lane >> 3) & 1), cb + nt));
+            mma16816(oc[nt], pa[j], vb);
+        }
+    const float inva = 1.f / suma, invb = 1.f / sumb;
+    const uint32_t ra = row0 + (lane >> 2), rb = ra + 8;
+#pragma unroll
+    for (int nt = 0; nt < ON; ++nt) {
+        const uint32_t coff = (lane & 3) * 4;             // byte offset of the column pair inside its 16-byte chunk
+        st_shared_b32(sO + swz(ra, cb + nt) + coff, pack_f16x2(oc[nt][0] * inva, oc[nt][1] * inva));
+        st_shared_b32(sO + swz(rb, cb + nt) + coff, pack_f16x2(oc[nt][2] * invb, oc[nt][3] * invb));
+    }
+}
+
 template <class CF, int VEC>
 __global__ void __launch_bounds__(kThreads, 1)
 mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
@@ -329,8 +426,6 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     float* s_tbl = reinterpret_cast<float*>(smem + CF::oTbl);
     float* s_bqkv = reinterpret_cast<float*>(smem + CF::oBqkv);
     float* s_bproj = reinterpret_cast<float*>(smem + CF::oBproj);
-    float* s_max = reinterpret_cast<float*>(smem + CF::oRedMax);
-    float* s_sum = reinterpret_cast<float*>(smem + CF::oRedSum);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;
@@ -595,159 +690,80 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         __syncthreads();
         tick(1);                                         // 1: x load + convert
 
-        // SW-MSA region mask bits of this row (:194-216): bit yj of ymask = band(yj) differs from the row's band
-        uint32_t ymask = 0, xmask = 0;
-        if (geo.shift > 0) {
-            const int ys0 = wy * WS, xs0 = wx * WS;
-            const int ty = tok / WS, tx = tok % WS;
-            const int by = (ys0 + ty >= geo.H - WS) + (ys0 + ty >= geo.H - geo.shift);
-            const int bx = (xs0 + tx >= geo.W - WS) + (xs0 + tx >= geo.W - geo.shift);
+        // ---------------- per-warp attention tasks of this tile: geometry + SW-MSA region mask bits (:194-216).
+        // task t = warp + 16 i  ->  (16-row block, window slot, head of the group); its two rows per lane are
+        // lane/4 and lane/4 + 8 of the block.
+        constexpr int TPW = CF::TASKS / kWarps;
+        uint32_t task_mask[TPW][2];
 #pragma unroll
-            for (int j = 0; j < WS; ++j) {
-                const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
-                const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
-                ymask |= uint32_t(byj != by) << j;
-                xmask |= uint32_t(bxj != bx) << j;
+        for (int i = 0; i < TPW; ++i) {
+            const int tsk = warp + kWarps * i;
+            const int rbk = tsk % CF::RB, tws = (tsk / CF::RB) % CF::WPT;
+            task_mask[i][0] = task_mask[i][1] = 0;
+            if (geo.shift > 0) {
+                const int lidx = tile * CF::WPT + tws;
+                int tb_, twy, twx;
+                window_coords(geo, list[lidx < count ? lidx : count - 1], tb_, twy, twx);
+                const int ys0 = twy * WS, xs0 = twx * WS;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int tk = rbk * 16 + (lane >> 2) + 8 * h2;          // token of this lane's row in its window
+                    const int by = (ys0 + tk / WS >= geo.H - WS) + (ys0 + tk / WS >= geo.H - geo.shift);
+                    const int bx = (xs0 + tk % WS >= geo.W - WS) + (xs0 + tk % WS >= geo.W - geo.shift);
+                    uint32_t mbits = 0;
+#pragma unroll
+                    for (int j = 0; j < WS; ++j) {
+                        const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
+                        const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
+                        mbits |= uint32_t(byj != by) << j;
+                        mbits |= uint32_t(bxj != bx) << (8 + j);
+                    }
+                    task_mask[i][h2] = mbits;
+                }
             }
         }
 
-        // softmax of one head for this thread's CPT columns; returns packed fp16 probabilities and stores the
-        // partial row sum.  S_h lives at TMEM columns tA + sreg * 128.
-        auto softmax_head = [&](int head, int hh, int sreg, uint32_t (&pk)[CF::CPT / 2]) {
-            const int col0 = wslot * NTOK + cg * CF::CPT;          // first column (key index in the tile)
-            float sv[CF::CPT];
-            {
-                // tcgen05.ld is warp-collective: the column address must be warp-uniform.  With 8x8 windows a warp
-                // lies inside one window; with 4x4 windows it covers two, so both candidates are loaded.
-                uint32_t acc[CF::CPT];
-                const uint32_t sbase = tm + CF::tA + sreg * 128 + lane_addr;
-                if constexpr (CF::CPT == 16) {
-                    tmem_ld_x16(sbase + col0, reinterpret_cast<uint32_t(&)[16]>(acc));
-                    tmem_wait_ld();
-                } else {
-                    uint32_t a0[4], a1[4];
-                    const uint32_t cbase = (r >> 5) * 32 + cg * CF::CPT;
-                    tmem_ld_x4(sbase + cbase, a0);
-                    tmem_ld_x4(sbase + cbase + 16, a1);
-                    tmem_wait_ld();
+        // QKV GEMM of head group g: D_qkv[128 x NQKV] = X * Wqkv_g^T   (warp 0; weights from the slab ring)
+        auto issue_qkv = [&]() {
+            tc_fence_after_sync();
+            constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, CF::NQKV);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = (wslot & 1) ? a1[j] : a0[j];
+            for (int kb = 0; kb < CF::KB; ++kb) {
+                long long tq0 = do_time ? clock64() : 0;
+                const uint32_t slot = acquire_q();
+                if (do_time) timing[16 + kb] += static_cast<unsigned long long>(clock64() - tq0);
+                const uint64_t a0 = umma_desc_k_sw128(sb + CF::oX + kb * 16384);
+                const uint64_t b0 = umma_desc_k_sw128(sb + CF::oRing + slot * CF::kQkvSlabBytes);
+                const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        if (ks < nks) umma_f16_ss(tm + CF::tA, a0 + ks * 2, b0 + ks * 2, idesc, (kb | ks) != 0);
+                    umma_commit(bar_empty + slot);
                 }
-                const float* tb = s_tbl + head * CF::TBL;
-                const int ty = tok / WS, tx = tok % WS;
-#pragma unroll
-                for (int j = 0; j < CF::CPT; ++j) {
-                    const int jj = cg * CF::CPT + j;              // key token index in the window
-                    const int yj = jj / WS, xj = jj % WS;
-                    float sc = __uint_as_float(acc[j]) + tb[(ty - yj + WS - 1) * (2 * WS - 1) + (tx - xj + WS - 1)];
-                    if (((ymask >> yj) | (xmask >> xj)) & 1u) sc += kNegMask;
-                    sv[j] = sc;
-                }
+                __syncwarp();
+                ++q_used;
             }
-            float m = sv[0];
-#pragma unroll
-            for (int j = 1; j < CF::CPT; ++j) m = fmaxf(m, sv[j]);
-            float* smx = s_max + (hh & 1) * 512;
-            smx[cg * 128 + r] = m;
-            __syncthreads();
-            m = fmaxf(fmaxf(smx[r], smx[128 + r]), fmaxf(smx[256 + r], smx[384 + r]));
-            const float ml = m * kLog2e;
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < CF::CPT; j += 2) {
-                const float p0 = ex2(fmaf(sv[j], kLog2e, -ml)), p1 = ex2(fmaf(sv[j + 1], kLog2e, -ml));
-                sum += p0 + p1;
-                pk[j / 2] = pack_f16x2(p0, p1);
-            }
-            s_sum[(hh * 4 + cg) * 128 + r] = sum;
-        };
-        auto store_p = [&](const uint32_t (&pk)[CF::CPT / 2]) {
-            const int col0 = wslot * NTOK + cg * CF::CPT;
-            const uint32_t rowaddr = sb + CF::oP + (col0 >> 6) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-            const uint32_t kin = col0 & 63;                        // key offset inside the 64-key block
-            if constexpr (CF::CPT == 16) {
-                st_shared_v4(rowaddr + ((((kin >> 3)) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-                st_shared_v4(rowaddr + ((((kin >> 3) + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
-            } else {
-                st_shared_v2(rowaddr + (((kin >> 3) ^ (r & 7)) << 4) + (kin & 7) * 2, pk[0], pk[1]);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-        };
-        // descriptors advance by (bytes >> 4) in their low (start address) field; no carry: smem < 256 KB
-        auto issue_s = [&](int hh, int sreg) {                     // warp 0
-            constexpr uint32_t idesc_s = umma_idesc(kFmtF16, kFmtF16, kTileM, 128);
-            const uint64_t a0 = umma_desc_k_sw128(sb + CF::oQ + hh * DPAD * 2);
-            const uint64_t b0 = umma_desc_k_sw128(sb + CF::oK + hh * DPAD * 2);
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < DPAD / 16; ++ks)
-                    umma_f16_ss(tm + CF::tA + sreg * 128, a0 + ks * 2, b0 + ks * 2, idesc_s, ks != 0);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int hh) {                              // warp 0: O_h = P V_h, K = 128 keys
-            constexpr uint32_t idesc_o = umma_idesc(kFmtF16, kFmtF16, kTileM, DPAD);
-            const uint32_t voff = ((hh * DPAD) >> 3) * 1024;       // first V^T row of this head (row-group aligned)
-            const uint64_t a0 = umma_desc_k_sw128(sb + CF::oP);
-            const uint64_t b0 = umma_desc_k_sw128(sb + CF::oVt + voff);
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_f16_ss(tm + CF::tO + hh * DPAD, a0 + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2,
-                                b0 + (ks >> 2) * (8192 >> 4) + (ks & 3) * 2, idesc_o, ks != 0);
-            }
-            __syncwarp();
+            commit_mma();
         };
 
+        if (warp == 0) issue_qkv();
+        tick(2);                                         // 2: QKV issue of group 0 (incl. slab waits)
+
         for (int g = 0; g < NG; ++g) {
-            // ---------------- QKV GEMM for this head group
-            if (warp == 0) {
-                tc_fence_after_sync();
-                constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, kTileM, CF::NQKV);
-#pragma unroll
-                for (int kb = 0; kb < CF::KB; ++kb) {
-                    long long tq0 = do_time ? clock64() : 0;
-                    const uint32_t slot = acquire_q();
-                    if (do_time) timing[16 + kb] += static_cast<unsigned long long>(clock64() - tq0);
-                    const uint64_t a0 = umma_desc_k_sw128(sb + CF::oX + kb * 16384);
-                    const uint64_t b0 = umma_desc_k_sw128(sb + CF::oRing + slot * CF::kQkvSlabBytes);
-                    const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            if (ks < nks) umma_f16_ss(tm + CF::tA, a0 + ks * 2, b0 + ks * 2, idesc, (kb | ks) != 0);
-                        umma_commit(bar_empty + slot);
-                    }
-                    __syncwarp();
-                    ++q_used;
-                }
-                commit_mma();
-            }
-            tick(2);                                     // 2: QKV issue (incl. waiting for weight slabs)
-            wait_mma();
+            wait_mma();                                  // D_qkv of group g complete
             tick(3);                                     // 3: QKV MMA completion wait
 
             // ---------------- drain: q (cg 0) / k (cg 1) / v (cg 2): NQ un-padded accumulator columns + bias -> fp16,
-            //                  re-spaced to the head-padded operand layout (pad columns written as zeros)
+            //                  re-spaced to the head-padded [128 x 64] operand layout (pad columns written as zeros);
+            //                  the three buffers share one layout (K-major SWIZZLE_128B), read back with ldmatrix
             if (cg < 3) {
                 constexpr int NQ = CF::NQ, D = CF::D;
                 const float* bias = s_bqkv + g * CF::NQKV + cg * NQ;
-                const uint32_t rowaddr = sb + (cg == 0 ? CF::oQ : CF::oK) + (r >> 3) * 1024 + (r & 7) * 128;
-                const uint32_t kbase = sb + CF::oVt + (r >> 6) * 8192;      // V^T: key block of token row r
-                const uint32_t kk = r & 63;
+                const uint32_t rowaddr = sb + (cg == 0 ? CF::oQ : cg == 1 ? CF::oK : CF::oV) + (r >> 3) * 1024 + (r & 7) * 128;
                 auto put8 = [&](int ch, const float (&v)[8]) {   // 8 padded columns 8*ch .. 8*ch+7 of this row
-                    if (cg < 2) {
-                        st_shared_v4(rowaddr + ((ch ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
-                                     pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __half hv = __float2half_rn(v[j]);
-                            st_shared_u16(kbase + sw128_offset(8 * ch + j, kk), *reinterpret_cast<const uint16_t*>(&hv));
-                        }
-                    }
+                    st_shared_v4(rowaddr + ((ch ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
+                                 pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
                 };
                 if constexpr (D % 8 == 0) {
 #pragma unroll
@@ -789,73 +805,37 @@ mwa_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     }
                 }
             }
-            fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
             tick(4);                                     // 4: q/k/v drain
 
-            // ---------------- heads of the group, two at a time: both score tiles are issued up front and the PV
-            //                  MMA of the first head runs under the softmax arithmetic of the second
-            for (int hp = 0; hp < HPG; hp += 2) {
-                if (warp == 0) {
-                    tc_fence_after_sync();
-                    issue_s(hp, 0);
-                    issue_s(hp + 1, 1);
-                    commit_mma();
-                }
-                wait_mma();
-                tick(5);                                 // 5: score MMAs
-                uint32_t pk[CF::CPT / 2];
-                softmax_head(g * HPG + hp, hp, 0, pk);
-                store_p(pk);
-                tick(6);                                 // 6: softmax + P store, first head
-                if (warp == 0) {
-                    tc_fence_after_sync();
-                    issue_pv(hp);
-                    commit_mma();
-                }
-                softmax_head(g * HPG + hp + 1, hp + 1, 1, pk);
-                tick(7);                                 // 7: softmax second head (PV of the first runs underneath)
-                wait_mma();                      // PV of the first head done: the P buffer is free again
-                store_p(pk);
-                tick(8);                                 // 8: wait PV + P store
-                if (warp == 0) {
-                    tc_fence_after_sync();
-                    issue_pv(hp + 1);
-                    commit_mma();
-                }
-                wait_mma();
-                tick(9);                                 // 9: PV second head
-            }
+            // ---------------- the next group's QKV GEMM runs on the tensor core while the warps do the attention
+            //                  core of this group (D_qkv has just been drained; X is still resident)
+            if (warp == 0 && g + 1 < NG) issue_qkv();
+            tick(5);                                     // 5: QKV issue of the next group
 
-            // ---------------- drain O (64 columns: 16 per thread), normalise by the row sum -> fp16 A operand
-            //                  (reuses the Q buffer: every score MMA of the group has completed)
+            // ---------------- attention core: one (window, head, 16-row block) task per warp, entirely in registers
             {
-                uint32_t acc[16];
-                tmem_ld_x16(tm + CF::tO + lane_addr + cg * 16, acc);
-                tmem_wait_ld();
-                const int hh = (cg * 16) / DPAD;
-                const float* ss = s_sum + hh * 4 * 128 + r;
-                const float inv = 1.f / (ss[0] + ss[128] + ss[256] + ss[384]);
-                uint32_t pk[8];
+                const uint32_t sO = sb + CF::oO + (g & 1) * 16384;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    pk[j] = pack_f16x2(__uint_as_float(acc[2 * j]) * inv, __uint_as_float(acc[2 * j + 1]) * inv);
-                const uint32_t rowaddr = sb + CF::oO + (r >> 3) * 1024 + (r & 7) * 128;
-                st_shared_v4(rowaddr + (((2 * cg) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-                st_shared_v4(rowaddr + (((2 * cg + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+                for (int i = 0; i < TPW; ++i) {
+                    const int tsk = warp + kWarps * i;
+                    const int rbk = tsk % CF::RB, tws = (tsk / CF::RB) % CF::WPT, hh = tsk / (CF::RB * CF::WPT);
+                    attention_task<CF>(sb + CF::oQ, sb + CF::oK, sb + CF::oV, sO, s_tbl + (g * HPG + hh) * CF::TBL,
+                                       tws * NTOK + rbk * 16, tws * NTOK, hh * (DPAD / 8), task_mask[i], lane);
+                }
             }
-            fence_proxy_async_smem();
+            fence_proxy_async_smem();                    // O_g is read by the projection MMA (async proxy)
             tc_fence_before_sync();
             __syncthreads();
-            tick(10);                                    // 10: O drain
+            tick(6);                                     // 6: attention core
 
             // ---------------- projection partial sum over this group's columns
             if (warp == 0) {
                 tc_fence_after_sync();
                 constexpr uint32_t idesc_p = umma_idesc(kFmtF16, kFmtF16, kTileM, C);
                 acquire_p();
-                const uint64_t a0 = umma_desc_k_sw128(sb + CF::oO), b0 = umma_desc_k_sw128(sb + CF::oRingP);
+                const uint64_t a0 = umma_desc_k_sw128(sb + CF::oO + (g & 1) * 16384), b0 = umma_desc_k_sw128(sb + CF::oRingP);
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tm + CF::tP, a0 + ks * 2, b0 + ks * 2, idesc_p, (g | ks) != 0);

@@ -18,8 +18,8 @@ with torch.no_grad():
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
     lib.mwa_debug_set_timing_buffer(None)
 t = buf.cpu().tolist(); tiles = max(t[15], 1)
-names = ["prologue", "x load+convert", "QKV issue (slab waits)", "QKV MMA wait", "qkv drain", "score MMA wait", "softmax0+P store",
-         "softmax1", "PV0 wait+P store", "PV1 wait", "O drain", "proj issue (slab wait)", "residual loads issue", "last proj wait", "epilogue stores"]
+names = ["prologue", "x load+convert", "QKV issue group 0 (slab waits)", "QKV MMA wait", "qkv drain", "QKV issue next group", "attention core (HMMA)",
+         "-", "-", "-", "-", "proj issue (slab wait)", "residual loads issue", "last proj wait", "epilogue stores"]
 tot = sum(t[:15])
 print("  acquire_q wait cycles per tile by K block:", [round(v / tiles) for v in t[16:20]])
 print(f"{what}: kernel+scan {e0.elapsed_time(e1)*1e3:.0f} us, CTA0 tiles {tiles}, cycles/tile {sum(t[1:15])/tiles:.0f}")
