@@ -17,6 +17,12 @@ bool mwa_tc_supported(int C, int heads, int ws, int H, int W, int shift, int cha
 void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
                            int heads, int ws, float scale, uint8_t* blk, cudaStream_t st);                    // mwa_tc.cu
 
+int mwa_forward_ws(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                   int heads, int ws, int shift, int32_t* kept_count, void* workspace, int64_t workspace_bytes,
+                   cudaStream_t st);                                                                          // mwa_ws.cu
+bool mwa_ws_supported(int C, int heads, int ws, int channels_last);
+void mwa_ws_set_timing_buffer(void* p);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -281,7 +287,10 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     return check_launch("mwa_prepare(images)");
 }
 
-void mwa_debug_set_timing_buffer(void* device_u64x32) { mwa_tc_set_timing_buffer(device_u64x32); }
+void mwa_debug_set_timing_buffer(void* device_u64x32) {
+    mwa_tc_set_timing_buffer(device_u64x32);
+    mwa_ws_set_timing_buffer(device_u64x32);
+}
 
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
     if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;
@@ -299,9 +308,13 @@ int mwa_forward(const float* x, const float* alpha, float* out, const void* para
     if (kept_count) MWA_TRY_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st), "mwa_forward(memset)");
     if (B == 0) return MWA_OK;
     const bool tc_ok = mwa_tc_supported(C, heads, ws, H, W, shift, channels_last);
-    if (algo == MWA_ALGO_TCGEN05 || (algo == MWA_ALGO_AUTO && tc_ok)) {
+    if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || (algo == MWA_ALGO_AUTO && tc_ok)) {
         if (!tc_ok) return MWA_ERR_UNSUPPORTED;
         if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
+        // warp-specialised pipeline where it covers the layout, else the phase-serial v1 kernel
+        if (algo != MWA_ALGO_TCGEN05_V1 && mwa_ws_supported(C, heads, ws, channels_last))
+            return mwa_forward_ws(x, alpha, out, params, B, C, H, W, heads, ws, shift, kept_count, workspace,
+                                  workspace_bytes, st);
         return mwa_forward_tc(x, alpha, out, params, B, C, H, W, heads, ws, shift, channels_last, kept_count, workspace,
                               workspace_bytes, st);
     }

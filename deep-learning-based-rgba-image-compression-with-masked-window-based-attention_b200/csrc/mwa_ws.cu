@@ -1,0 +1,666 @@
+// Fused masked window attention forward, warp-specialised and software-pipelined (tcgen05 + TMEM), sm_100a only.
+// Reference semantics: layers/masked_win_attention.py:169-251 (block) and :96-131 (window attention).
+//
+// Same three launches as mwa_tc.cu (scan -> compact -> persistent main kernel, one CTA per SM, tile = 128 tokens =
+// 2 kept 8x8 windows / 8 kept 4x4 windows), same parameter images.  The main kernel is re-organised around roles
+// that run concurrently behind mbarrier pipelines instead of CTA-wide phases:
+//
+//   warp 0        MMA issuer.  Stream of head groups G = tile * NG + g:  QKV(G): D_qkv[G % 2] = X * Wqkv_g^T,
+//                 PROJ(G - 2): D_proj += O_g * Wproj_g^T.  Runs up to two groups ahead of the attention warps.
+//   warp 1        weight feeder: bulk copies (TMA engine) of the fp16 weight slabs from L2 into a 3-slot ring
+//                 (+ 1 projection slot), in exactly the order the issuer consumes them.
+//   warps 4-11    x producer + epilogue (PE): gather x of tile i+2 into registers (fp32 -> packed fp16) while tile i
+//                 is computed, store it as the swizzled A operand as soon as the QKV MMAs of tile i+1 ... i.e. the
+//                 previous user of the X buffer ... have completed; then the epilogue of tile i
+//                 (TMEM -> + bias + residual -> out), thread = token.
+//   warps 12-19   attention (A): per head group drain D_qkv (+ bias -> fp16 Q / K / V in smem), then the per-window
+//                 core on warp-level HMMA tiles with the softmax in registers (bias comes in as the accumulator
+//                 initialiser through immediate-offset LDS, the SW-MSA region mask only on windows that touch the
+//                 wrapped border), O_g -> smem as the projection's A operand.
+//
+// Registers are re-balanced with setmaxnreg (issuer / feeder 32, PE 96, A 128).
+// TMEM: two D_qkv buffers + the projection accumulator.  Shared memory: X, Q/K/V, 1-2 O buffers, weight ring.
+// Operand precision: fp16 x fp16 -> fp32 accumulate; softmax, bias, residual in fp32.
+#include "mwa_tc_shared.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kWsWarps = 20;
+constexpr int kWsThreads = kWsWarps * 32;
+constexpr int kMmaWarp = 0, kWgtWarp = 1, kAllocWarp = 2;
+constexpr int kPeWarp0 = 4, kNumPe = 8;
+constexpr int kAtWarp0 = 12, kNumAt = 8;
+constexpr int kPeThreads = kNumPe * 32, kAtThreads = kNumAt * 32;
+constexpr int kRegsCtl = 32, kRegsPe = 96, kRegsAt = 128;
+
+template <class CF>
+struct WsMap {
+    static constexpr int kSlots = 3;                                      // QKV weight slabs in flight
+    static constexpr uint32_t kDqStride = (CF::NQKV + 31) / 32 * 32;      // TMEM columns per D_qkv buffer
+    static constexpr int kDqBufs = (2 * kDqStride + CF::C <= 512) ? 2 : 1;
+    static constexpr uint32_t tDq = 0;
+    static constexpr uint32_t tP = kDqBufs * kDqStride;                   // projection accumulator, C columns
+    static_assert(tP + CF::C <= 512, "TMEM budget");
+    // shared memory map (offsets from a 1024-aligned base)
+    static constexpr uint32_t oX = 0;                                     // KB x [128 x 64] fp16
+    static constexpr uint32_t oQ = oX + CF::KB * 16384;
+    static constexpr uint32_t oK = oQ + 16384;
+    static constexpr uint32_t oV = oK + 16384;
+    static constexpr uint32_t oO = oV + 16384;                            // kOBufs x [128 x 64]
+    static constexpr uint32_t kFixed = CF::KB * 16384 + 3 * 16384 + kSlots * CF::kQkvSlabBytes + CF::kProjSlabBytes;
+    static constexpr uint32_t kSmall = ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16 + CF::NG * CF::NQKV * 4 + CF::C * 4 + 512;
+    static constexpr int kOBufs = (kFixed + 2 * 16384 + kSmall <= 227 * 1024) ? 2 : 1;
+    static constexpr uint32_t oRing = oO + kOBufs * 16384;
+    static constexpr uint32_t oRingP = oRing + kSlots * CF::kQkvSlabBytes;
+    static constexpr uint32_t oTbl = oRingP + CF::kProjSlabBytes;         // fp32 [HEADS][TBL]
+    static constexpr uint32_t oBqkv = oTbl + ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16;   // fp32 [NG][NQKV]
+    static constexpr uint32_t oBproj = oBqkv + CF::NG * CF::NQKV * 4;
+    static constexpr uint32_t oBars = (oBproj + CF::C * 4 + 15) / 16 * 16;
+    static constexpr uint32_t oTmem = oBars + 32 * 8;
+    static constexpr uint32_t oTotal = oTmem + 16;
+    static_assert(oTotal <= 227 * 1024, "shared memory budget");
+    // barrier indices
+    static constexpr int bXFull = 0, bXEmpty = 1, bPjFull = 2, bPjEmpty = 3, bPFull = 4, bPEmpty = 5;
+    static constexpr int bWFull = 6, bWEmpty = bWFull + kSlots;
+    static constexpr int bDqFull = bWEmpty + kSlots, bDqEmpty = bDqFull + 2, bOFull = bDqEmpty + 2, bOEmpty = bOFull + 2;
+    static_assert(bOEmpty + 2 <= 32, "barrier slots");
+};
+
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// One attention task (rows row0..row0+15 of the tile, keys key0..key0+NTOK-1, head at chunk offset cb).
+// tbl: shared address of this lane's entry of the head's relative-position table for (h2 = 0, n = 0, e = 0); the
+// other 31 entries are at compile-time offsets (see the caller).
+template <class CF>
+__device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint32_t sV, uint32_t sO, uint32_t tbl,
+                                                  int row0, int key0, int cb, bool has_mask,
+                                                  const uint32_t (&rowmask)[2], int lane) {
+    constexpr int WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, D = CF::D;
+    constexpr int KS = DPAD / 16, NT = NTOK / 8, PK = NTOK / 16, ON = (D + 7) / 8;
+    constexpr int kRowStep = (8 / WS) * (2 * WS - 1);       // table index step per 8 tokens (rows: +, keys: -)
+    static_assert(8 % WS == 0, "window size must divide 8");
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qa[ks], sQ + swz(row0 + (lane & 15), cb + 2 * ks + (lane >> 4)));
+    float sc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        // accumulator initialised with the relative-position bias (layers/masked_win_attention.py:109-112)
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) sc[n][2 * h2 + e] = ld_shared_f32(tbl + 4 * ((h2 - n) * kRowStep - e));
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t kb[2];
+            ldmatrix_x2(kb, sK + swz(key0 + 8 * n + (lane & 7), cb + 2 * ks + ((lane >> 3) & 1)));
+            mma16816(sc[n], qa[ks], kb);
+        }
+    }
+    if (has_mask) {      // warp-uniform: SW-MSA region mask, only for windows on the wrapped border (:194-216)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * n + 2 * (lane & 3) + e, yj = j / WS, xj = j % WS;
+                if (((rowmask[0] >> yj) | (rowmask[0] >> (8 + xj))) & 1u) sc[n][e] += kNegMask;
+                if (((rowmask[1] >> yj) | (rowmask[1] >> (8 + xj))) & 1u) sc[n][2 + e] += kNegMask;
+            }
+    }
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        ma = fmaxf(ma, fmaxf(sc[n][0], sc[n][1]));
+        mb = fmaxf(mb, fmaxf(sc[n][2], sc[n][3]));
+    }
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    const float mla = ma * kLog2e, mlb = mb * kLog2e;
+    float suma = 0.f, sumb = 0.f;
+    uint32_t pa[PK][4];                                   // un-normalised probabilities as A fragments of P V
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const float p0 = ex2(fmaf(sc[n][0], kLog2e, -mla)), p1 = ex2(fmaf(sc[n][1], kLog2e, -mla));
+        const float p2 = ex2(fmaf(sc[n][2], kLog2e, -mlb)), p3 = ex2(fmaf(sc[n][3], kLog2e, -mlb));
+        suma += p0 + p1;
+        sumb += p2 + p3;
+        pa[n >> 1][(n & 1) * 2 + 0] = pack_f16x2(p0, p1);
+        pa[n >> 1][(n & 1) * 2 + 1] = pack_f16x2(p2, p3);
+    }
+    suma += __shfl_xor_sync(0xffffffffu, suma, 1);
+    suma += __shfl_xor_sync(0xffffffffu, suma, 2);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 1);
+    sumb += __shfl_xor_sync(0xffffffffu, sumb, 2);
+    float oc[ON][4];
+#pragma unroll
+    for (int nt = 0; nt < ON; ++nt) oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < PK; ++j)
+#pragma unroll
+        for (int nt = 0; nt < ON; ++nt) {
+            uint32_t vb[2];
+            ldmatrix_x2_trans(vb, sV + swz(key0 + 16 * j + (lane & 7) + 8 * ((lane >> 3) & 1), cb + nt));
+            mma16816(oc[nt], pa[j], vb);
+        }
+    const float inva = 1.f / suma, invb = 1.f / sumb;
+    const uint32_t ra = row0 + (lane >> 2), rb = ra + 8;
+#pragma unroll
+    for (int nt = 0; nt < ON; ++nt) {
+        const uint32_t coff = (lane & 3) * 4;             // byte offset of the column pair inside its 16-byte chunk
+        st_shared_b32(sO + swz(ra, cb + nt) + coff, pack_f16x2(oc[nt][0] * inva, oc[nt][1] * inva));
+        st_shared_b32(sO + swz(rb, cb + nt) + coff, pack_f16x2(oc[nt][2] * invb, oc[nt][3] * invb));
+    }
+}
+
+// D_qkv columns [part * NQ + COL0, + NCOLS) of this thread's row + bias -> fp16 -> the head-padded chunks of heads
+// [H_LO, H_HI) of the destination operand buffer (pad columns written as zeros, all-pad chunks left untouched:
+// they were zeroed once at kernel start).
+template <class CF, int COL0, int NCOLS, int H_LO, int H_HI>
+__device__ __forceinline__ void drain_part(uint32_t taddr, const float* bias, uint32_t rowaddr, int r) {
+    constexpr int D = CF::D, DPAD = CF::DPAD;
+    static_assert(COL0 % 8 == 0 && NCOLS % 8 == 0 && H_LO * D >= COL0 && H_HI * D <= COL0 + NCOLS, "drain split");
+    float val[NCOLS];
+#pragma unroll
+    for (int cc = 0; cc < NCOLS / 8; ++cc) {
+        uint32_t acc[8];
+        tmem_ld_x8(taddr + COL0 + cc * 8, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) val[cc * 8 + j] = __uint_as_float(acc[j]) + bias[COL0 + cc * 8 + j];
+    }
+#pragma unroll
+    for (int ch = H_LO * DPAD / 8; ch < H_HI * DPAD / 8; ++ch) {
+        if ((8 * ch) % DPAD >= D) continue;                // chunk made of pad columns only
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = 8 * ch + j;
+            v[j] = ((col % DPAD) < D) ? val[(col / DPAD) * D + (col % DPAD) - COL0] : 0.f;
+        }
+        st_shared_v4(rowaddr + ((ch ^ (r & 7)) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
+                     pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+    }
+}
+
+template <class CF, bool kTiming>
+__global__ void __launch_bounds__(kWsThreads, 1)
+mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
+              const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
+              Geom geo, unsigned long long* __restrict__ timing) {
+    using MP = WsMap<CF>;
+    constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
+    constexpr int LOOK = MP::kDqBufs;                   // QKV groups issued ahead of the projection stream
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sb = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MP::oBars);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MP::oTmem);
+    float* s_tbl = reinterpret_cast<float*>(smem + MP::oTbl);
+    float* s_bqkv = reinterpret_cast<float*>(smem + MP::oBqkv);
+    float* s_bproj = reinterpret_cast<float*>(smem + MP::oBproj);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const MwaParamLayout L(C, CF::HEADS, WS);
+
+    // ---- one-time setup (all warps)
+    if (tid == 0) {
+        if (sb & 1023u) __trap();
+        mbar_init(bars + MP::bXFull, kPeThreads);
+        mbar_init(bars + MP::bXEmpty, 1);
+        mbar_init(bars + MP::bPjFull, 1);
+        mbar_init(bars + MP::bPjEmpty, kPeThreads);
+        mbar_init(bars + MP::bPFull, 1);
+        mbar_init(bars + MP::bPEmpty, 1);
+        for (int i = 0; i < MP::kSlots; ++i) {
+            mbar_init(bars + MP::bWFull + i, 1);
+            mbar_init(bars + MP::bWEmpty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + MP::bDqFull + i, 1);
+            mbar_init(bars + MP::bDqEmpty + i, kAtThreads);
+            mbar_init(bars + MP::bOFull + i, kAtThreads);
+            mbar_init(bars + MP::bOEmpty + i, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kAllocWarp) tmem_alloc<512>(tmem_ptr);
+    {
+        const float* bq = reinterpret_cast<const float*>(tcp + TcParams<CF>::bq);
+        for (int i = tid; i < NG * CF::NQKV; i += kWsThreads) s_bqkv[i] = bq[i];
+        const float* bp = reinterpret_cast<const float*>(blk + L.bproj);
+        for (int i = tid; i < C; i += kWsThreads) s_bproj[i] = bp[i];
+        // operand buffers: padding columns must read as exact zeros for the whole kernel
+        for (int i = tid; i < (MP::oRing - MP::oX) / 16; i += kWsThreads)
+            reinterpret_cast<uint4*>(smem + MP::oX)[i] = make_uint4(0, 0, 0, 0);
+        // compact relative-position table s_tbl[h][idx], idx = (yi-yj+WS-1)*(2WS-1) + (xi-xj+WS-1)
+        const float* bexp = reinterpret_cast<const float*>(blk + L.bias);
+        for (int e = tid; e < CF::HEADS * CF::TBL; e += kWsThreads) {
+            const int h = e / CF::TBL, idx = e % CF::TBL;
+            const int dy = idx / (2 * WS - 1) - (WS - 1), dx = idx % (2 * WS - 1) - (WS - 1);
+            const int yi = dy >= 0 ? dy : 0, yj = dy >= 0 ? 0 : -dy;
+            const int xi = dx >= 0 ? dx : 0, xj = dx >= 0 ? 0 : -dx;
+            s_tbl[e] = bexp[(int64_t(h) * NTOK + (yi * WS + xi)) * NTOK + (yj * WS + xj)];
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = *tmem_ptr;
+
+    const int count = *count_p;
+    const int num_tiles = (count + CF::WPT - 1) / CF::WPT;
+    const int64_t hw = int64_t(geo.H) * geo.W;
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
+    const int total = my_tiles * NG;                       // head groups this CTA processes
+    const uint8_t* wimg = tcp + TcParams<CF>::img;
+
+    // development aid (kTiming instantiation only): lane 0 of the first warp of each role of CTA 0 accumulates
+    // clock64() deltas per pipeline stage
+    const bool do_time = kTiming && timing != nullptr && blockIdx.x == 0 && lane == 0 &&
+                         (warp == kMmaWarp || warp == kPeWarp0 || warp == kAtWarp0);
+    long long t_prev = do_time ? clock64() : 0;
+    auto tick = [&](int slot) {
+        if constexpr (kTiming) {
+            if (do_time) {
+                const long long now = clock64();
+                timing[slot] += static_cast<unsigned long long>(now - t_prev);
+                t_prev = now;
+            }
+        }
+    };
+
+    if (warp < 4) {
+        // =========================================================================================== control warps
+        reg_dec<kRegsCtl>();
+        if (warp == kMmaWarp) {
+            constexpr uint32_t idesc_q = umma_idesc(kFmtF16, kFmtF16, kTileM, CF::NQKV);
+            constexpr uint32_t idesc_p = umma_idesc(kFmtF16, kFmtF16, kTileM, C);
+            uint32_t q_used = 0, p_used = 0;
+            for (int G = 0; G < total + LOOK; ++G) {
+                if (G < total) {
+                    const int it = G / NG, g = G % NG, b = G % MP::kDqBufs;
+                    if (g == 0) mbar_wait(bars + MP::bXFull, it & 1);
+                    tick(0);                                                     // 0: wait X
+                    if (G >= MP::kDqBufs) mbar_wait(bars + MP::bDqEmpty + b, ((G / MP::kDqBufs) - 1) & 1);
+                    tick(1);                                                     // 1: wait D_qkv drained
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int kb = 0; kb < CF::KB; ++kb) {
+                        const uint32_t slot = q_used % MP::kSlots;
+                        mbar_wait(bars + MP::bWFull + slot, (q_used / MP::kSlots) & 1);
+                        tc_fence_after_sync();
+                        const uint64_t a0 = umma_desc_k_sw128(sb + MP::oX + kb * 16384);
+                        const uint64_t b0 = umma_desc_k_sw128(sb + MP::oRing + slot * CF::kQkvSlabBytes);
+                        const int nks = (kb == CF::KB - 1) ? (CF::KSTEPS - 4 * (CF::KB - 1)) : 4;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nks)
+                                    umma_f16_ss(tm + MP::tDq + b * MP::kDqStride, a0 + ks * 2, b0 + ks * 2, idesc_q,
+                                                (kb | ks) != 0);
+                            umma_commit(bars + MP::bWEmpty + slot);
+                        }
+                        __syncwarp();
+                        ++q_used;
+                    }
+                    if (elect_one()) {
+                        umma_commit(bars + MP::bDqFull + b);
+                        if (g == NG - 1) umma_commit(bars + MP::bXEmpty);
+                    }
+                    __syncwarp();
+                    tick(2);                                                     // 2: QKV issue incl. slab waits
+                }
+                if (G >= LOOK) {
+                    const int Gp = G - LOOK, itp = Gp / NG, gp = Gp % NG, ob = Gp % MP::kOBufs;
+                    mbar_wait(bars + MP::bOFull + ob, (Gp / MP::kOBufs) & 1);
+                    tick(3);                                                     // 3: wait O_g
+                    if (gp == 0 && itp > 0) mbar_wait(bars + MP::bPjEmpty, (itp - 1) & 1);
+                    tick(4);                                                     // 4: wait projection accumulator free
+                    mbar_wait(bars + MP::bPFull, p_used & 1);
+                    tc_fence_after_sync();
+                    const uint64_t a0 = umma_desc_k_sw128(sb + MP::oO + ob * 16384);
+                    const uint64_t b0 = umma_desc_k_sw128(sb + MP::oRingP);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16_ss(tm + MP::tP, a0 + ks * 2, b0 + ks * 2, idesc_p, (gp | ks) != 0);
+                        umma_commit(bars + MP::bPEmpty);
+                        umma_commit(bars + MP::bOEmpty + ob);
+                        if (gp == NG - 1) umma_commit(bars + MP::bPjFull);
+                    }
+                    __syncwarp();
+                    ++p_used;
+                    tick(5);                                                     // 5: projection issue incl. slab wait
+                }
+            }
+        } else if (warp == kWgtWarp) {
+            uint32_t q_issued = 0, p_issued = 0;
+            for (int G = 0; G < total + LOOK; ++G) {
+                if (G < total) {
+                    const int g = G % NG;
+#pragma unroll
+                    for (int kb = 0; kb < CF::KB; ++kb) {
+                        const uint32_t slot = q_issued % MP::kSlots;
+                        if (q_issued >= uint32_t(MP::kSlots))
+                            mbar_wait(bars + MP::bWEmpty + slot, ((q_issued / MP::kSlots) - 1) & 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(bars + MP::bWFull + slot, CF::kQkvSlabBytes);
+                            bulk_g2s(smem + MP::oRing + slot * CF::kQkvSlabBytes,
+                                     wimg + int64_t(g) * CF::kGroupBytes + int64_t(kb) * CF::kQkvSlabBytes,
+                                     CF::kQkvSlabBytes, bars + MP::bWFull + slot);
+                        }
+                        __syncwarp();
+                        ++q_issued;
+                    }
+                }
+                if (G >= LOOK) {
+                    const int gp = (G - LOOK) % NG;
+                    if (p_issued >= 1) mbar_wait(bars + MP::bPEmpty, (p_issued - 1) & 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bars + MP::bPFull, CF::kProjSlabBytes);
+                        bulk_g2s(smem + MP::oRingP,
+                                 wimg + int64_t(gp) * CF::kGroupBytes + int64_t(CF::KB) * CF::kQkvSlabBytes,
+                                 CF::kProjSlabBytes, bars + MP::bPFull);
+                    }
+                    __syncwarp();
+                    ++p_issued;
+                }
+            }
+        }
+    } else if (warp < kAtWarp0) {
+        // =========================================================================================== x producer + epilogue
+        reg_dec<kRegsPe>();
+        const int pw = warp - kPeWarp0, q = pw & 3, half = pw >> 2;
+        const int r = q * 32 + lane;                        // token row of the tile == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int wslot = r / NTOK, tok = r % NTOK;
+        constexpr int CPH = CF::NCHUNK / 2;                 // 8-channel chunks per thread (half of the row)
+        static_assert(CF::NCHUNK % 2 == 0, "C must be a multiple of 16");
+        constexpr int LB = 3;                               // chunks per load batch (24 loads in flight)
+        uint32_t pk[CPH][4];
+        auto row_base = [&](int tile, bool& valid) -> int64_t {      // NCHW element offset of (b, c = 0, py, px)
+            const int lidx = tile * CF::WPT + wslot;
+            valid = lidx < count;
+            const int win = list[valid ? lidx : (count - 1)];
+            int b, wy, wx, py, px;
+            window_coords(geo, win, b, wy, wx);
+            token_pixel<WS>(geo, wy, wx, tok, py, px);
+            return int64_t(b) * C * hw + int64_t(py) * geo.W + px;
+        };
+        auto load_x = [&](int tile) {
+            bool valid;
+            const float* p = x + row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
+#pragma unroll
+            for (int c0 = 0; c0 < CPH; c0 += LB) {
+                float v[LB][8];
+#pragma unroll
+                for (int i = 0; i < LB; ++i)
+                    if (c0 + i < CPH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[i][j] = valid ? __ldg(p) : 0.f;
+                            p += hw;
+                        }
+                    }
+#pragma unroll
+                for (int i = 0; i < LB; ++i)
+                    if (c0 + i < CPH) {
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp) pk[c0 + i][jp] = pack_f16x2(v[i][2 * jp], v[i][2 * jp + 1]);
+                    }
+            }
+        };
+        auto store_x = [&]() {
+#pragma unroll
+            for (int i = 0; i < CPH; ++i) {
+                const int ci = half * CPH + i;
+                const uint32_t addr = sb + MP::oX + (ci >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 +
+                                      (((ci & 7) ^ (r & 7)) << 4);
+                st_shared_v4(addr, pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bars + MP::bXFull);
+        };
+        if (my_tiles > 0) {
+            load_x(blockIdx.x);
+            store_x();
+            if (my_tiles > 1) load_x(blockIdx.x + gridDim.x);
+        }
+        tick(8);                                                                 // 8: PE prologue
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            if (it + 1 < my_tiles) {
+                mbar_wait(bars + MP::bXEmpty, it & 1);       // QKV MMAs of tile `it` have consumed X
+                tick(9);                                                         // 9: wait X free
+                store_x();
+                tick(10);                                                        // 10: store X
+                if (it + 2 < my_tiles) load_x(tile + 2 * gridDim.x);
+                tick(11);                                                        // 11: load x (tile + 2)
+            }
+            // ---- epilogue of tile `it`: out = x + (proj + bias), thread = token, half of the channels
+            bool valid;
+            const int64_t base = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
+            const float* xr = x + base;
+            float* orow = out + base;
+            constexpr int EB = 2;                            // chunks per residual batch
+            bool waited = false;
+#pragma unroll
+            for (int c0 = 0; c0 < CPH; c0 += EB) {
+                float res[EB][8];
+#pragma unroll
+                for (int i = 0; i < EB; ++i)
+                    if (c0 + i < CPH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            res[i][j] = valid ? __ldg(xr) : 0.f;
+                            xr += hw;
+                        }
+                    }
+                if (!waited) {
+                    mbar_wait(bars + MP::bPjFull, it & 1);
+                    tc_fence_after_sync();
+                    waited = true;
+                    tick(12);                                                    // 12: wait projection complete
+                }
+#pragma unroll
+                for (int i = 0; i < EB; ++i)
+                    if (c0 + i < CPH) {
+                        const int cc = (half * CPH + c0 + i) * 8;
+                        uint32_t acc[8];
+                        tmem_ld_x8(tm + MP::tP + lane_addr + cc, acc);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (valid) *orow = res[i][j] + (__uint_as_float(acc[j]) + s_bproj[cc + j]);
+                            orow += hw;
+                        }
+                    }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(bars + MP::bPjEmpty);
+            tick(13);                                                            // 13: epilogue
+        }
+    } else {
+        // =========================================================================================== attention warps
+        reg_inc<kRegsAt>();
+        const int a = warp - kAtWarp0, q = a & 3, half = a >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        constexpr int TPW = CF::TASKS / kNumAt;
+        static_assert(CF::TASKS % kNumAt == 0 && CF::RB * CF::WPT == kNumAt, "task decomposition");
+        // every task of this warp covers the same (16-row block, window slot); the head of the group is the task index
+        const int rbk = a % CF::RB, tws = (a / CF::RB) % CF::WPT;
+        // this lane's entry of the relative-position table for (h2 = 0, n = 0, e = 0), head 0
+        int tbl_idx;
+        {
+            const int ti = rbk * 16 + (lane >> 2), tj = 2 * (lane & 3);
+            tbl_idx = (ti / WS - tj / WS + WS - 1) * (2 * WS - 1) + (ti % WS - tj % WS + WS - 1);
+        }
+        const uint32_t tbl0 = sb + MP::oTbl + 4 * tbl_idx;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            // SW-MSA region mask bits of this warp's rows (:194-216); zero unless the window touches the wrapped border
+            uint32_t rowmask[2] = {0u, 0u};
+            bool has_mask = false;
+            if (geo.shift > 0) {
+                const int lidx = tile * CF::WPT + tws;
+                int tb_, twy, twx;
+                window_coords(geo, list[lidx < count ? lidx : count - 1], tb_, twy, twx);
+                has_mask = (twy == geo.nwy - 1) || (twx == geo.nwx - 1);
+                if (has_mask) {
+                    const int ys0 = twy * WS, xs0 = twx * WS;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int tk = rbk * 16 + (lane >> 2) + 8 * h2;
+                        const int by = (ys0 + tk / WS >= geo.H - WS) + (ys0 + tk / WS >= geo.H - geo.shift);
+                        const int bx = (xs0 + tk % WS >= geo.W - WS) + (xs0 + tk % WS >= geo.W - geo.shift);
+                        uint32_t mbits = 0;
+#pragma unroll
+                        for (int j = 0; j < WS; ++j) {
+                            const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
+                            const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
+                            mbits |= uint32_t(byj != by) << j;
+                            mbits |= uint32_t(bxj != bx) << (8 + j);
+                        }
+                        rowmask[h2] = mbits;
+                    }
+                }
+            }
+            for (int g = 0; g < NG; ++g) {
+                const int G = it * NG + g, b = G % MP::kDqBufs, ob = G % MP::kOBufs;
+                mbar_wait(bars + MP::bDqFull + b, (G / MP::kDqBufs) & 1);
+                tc_fence_after_sync();
+                tick(16);                                                        // 16: wait D_qkv
+                {   // ---- drain: half 0: q (all heads) + k (first half of the heads); half 1: rest of k + v
+                    constexpr int NQ = CF::NQ, D = CF::D;
+                    constexpr bool kSplitK = (HPG % 2 == 0) && ((HPG / 2) * D % 8 == 0);
+                    constexpr int KLO = kSplitK ? (HPG / 2) * D : NQ;     // k columns loaded by half 0
+                    const uint32_t ta = tm + MP::tDq + b * MP::kDqStride + lane_addr;
+                    const float* bias = s_bqkv + g * CF::NQKV;
+                    const uint32_t rowoff = (r >> 3) * 1024 + (r & 7) * 128;
+                    if (half == 0) {
+                        drain_part<CF, 0, NQ, 0, HPG>(ta, bias, sb + MP::oQ + rowoff, r);
+                        drain_part<CF, 0, KLO, 0, HPG / 2>(ta + NQ, bias + NQ, sb + MP::oK + rowoff, r);
+                    } else {
+                        drain_part<CF, kSplitK ? KLO : 0, kSplitK ? NQ - KLO : NQ, HPG / 2, HPG>(ta + NQ, bias + NQ,
+                                                                                                  sb + MP::oK + rowoff, r);
+                        drain_part<CF, 0, NQ, 0, HPG>(ta + 2 * NQ, bias + 2 * NQ, sb + MP::oV + rowoff, r);
+                    }
+                }
+                tc_fence_before_sync();
+                mbar_arrive(bars + MP::bDqEmpty + b);
+                named_sync(1, kAtThreads);                   // Q / K / V of the group visible to the 8 warps
+                tick(17);                                                        // 17: drain
+                if (G >= MP::kOBufs) mbar_wait(bars + MP::bOEmpty + ob, ((G / MP::kOBufs) - 1) & 1);
+                tick(18);                                                        // 18: wait O buffer free
+#pragma unroll
+                for (int i = 0; i < TPW; ++i) {
+                    const int hh = i;                        // head of the group == task index of this warp
+                    attention_task_ws<CF>(sb + MP::oQ, sb + MP::oK, sb + MP::oV, sb + MP::oO + ob * 16384,
+                                          tbl0 + 4 * (g * HPG + hh) * CF::TBL, tws * NTOK + rbk * 16, tws * NTOK,
+                                          hh * (DPAD / 8), has_mask, rowmask, lane);
+                }
+                fence_proxy_async_smem();                    // O_g is read by the projection MMA (async proxy)
+                mbar_arrive(bars + MP::bOFull + ob);
+                named_sync(2, kAtThreads);                   // all reads of Q / K / V done before the next drain
+                tick(19);                                                        // 19: attention core
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kAllocWarp) tmem_dealloc<512>(tm);
+}
+
+unsigned long long* g_ws_timing = nullptr;
+
+template <class CF>
+int launch_ws(const float* x, const float* alpha, float* out, const void* params, int B, int H, int W, int shift,
+              int32_t* kept_count, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    const Geom geo{B, H, W, shift, W / CF::WS, H / CF::WS, 0};
+    const int64_t nwin64 = int64_t(B) * geo.nwx * geo.nwy;
+    if (nwin64 > 0x3fffffffll) return MWA_ERR_UNSUPPORTED;
+    const int nwin = static_cast<int>(nwin64);
+    const ScanWs ws(nwin);
+    if (!workspace || workspace_bytes < ws.total) return MWA_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return MWA_ERR_ALIGNMENT;
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    int32_t* count = reinterpret_cast<int32_t*>(wsp + ws.count);
+    uint8_t* flags = wsp + ws.flags;
+    int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
+    const uint8_t* blk = static_cast<const uint8_t*>(params);
+    const MwaParamLayout L(CF::C, CF::HEADS, CF::WS);
+    const int vec = (shift % 4 == 0 && W % 4 == 0) ? 4 : (shift % 2 == 0 && W % 2 == 0) ? 2 : 1;
+    if (alpha != nullptr) {
+        if (vec == 4) mwa_scan_kernel<CF::WS, 4><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        else if (vec == 2) mwa_scan_kernel<CF::WS, 2><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        else mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        int rc = check_launch("mwa_forward(scan)");
+        if (rc != MWA_OK) return rc;
+    }
+    mwa_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, count);
+    int rc = check_launch("mwa_forward(compact)");
+    if (rc != MWA_OK) return rc;
+    const int smem = WsMap<CF>::oTotal;
+    const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
+    const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+    if (g_ws_timing != nullptr) {
+        MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                     "mwa_forward(ws attr)");
+        mwa_ws_kernel<CF, true><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
+                                                                g_ws_timing);
+    } else {
+        MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                     "mwa_forward(ws attr)");
+        mwa_ws_kernel<CF, false><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
+                                                                 nullptr);
+    }
+    rc = check_launch("mwa_forward(tcgen05 ws)");
+    if (rc != MWA_OK) return rc;
+    if (kept_count)
+        MWA_TRY_CUDA(cudaMemcpyAsync(kept_count, count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st),
+                     "mwa_forward(kept_count)");
+    return MWA_OK;
+}
+
+using Cfg192h8 = Cfg<192, 8, 8>;
+using Cfg192h6 = Cfg<192, 6, 8>;
+using Cfg80h8 = Cfg<80, 8, 4>;
+
+}  // namespace
+
+bool mwa_ws_supported(int C, int heads, int ws, int channels_last) {
+    if (channels_last) return false;
+    return (C == 192 && heads == 8 && ws == 8) || (C == 192 && heads == 6 && ws == 8) || (C == 80 && heads == 8 && ws == 4);
+}
+void mwa_ws_set_timing_buffer(void* p) { g_ws_timing = static_cast<unsigned long long*>(p); }
+
+int mwa_forward_ws(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                   int heads, int ws, int shift, int32_t* kept_count, void* workspace, int64_t workspace_bytes,
+                   cudaStream_t st) {
+    if (C == 192 && heads == 8 && ws == 8)
+        return launch_ws<Cfg192h8>(x, alpha, out, params, B, H, W, shift, kept_count, workspace, workspace_bytes, st);
+    if (C == 192 && heads == 6 && ws == 8)
+        return launch_ws<Cfg192h6>(x, alpha, out, params, B, H, W, shift, kept_count, workspace, workspace_bytes, st);
+    if (C == 80 && heads == 8 && ws == 4)
+        return launch_ws<Cfg80h8>(x, alpha, out, params, B, H, W, shift, kept_count, workspace, workspace_bytes, st);
+    return MWA_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200

@@ -40,8 +40,9 @@ enum {
     MWA_ERR_CUDA = -5          /* a CUDA runtime call failed (launch error) */
 };
 
-/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel */
-enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2 };
+/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel;
+ * TCGEN05_V1 forces the phase-serial first-generation attention kernel (kept for A/B measurements) */
+enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2, MWA_ALGO_TCGEN05_V1 = 3 };
 
 MWA_API int mwa_b200_abi_version(void);
 MWA_API const char* mwa_b200_status_string(int status);

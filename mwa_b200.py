@@ -34,4 +34,5 @@ patch_model_rounding = _install.patch_model_rounding
 uninstall = _install.uninstall
 build = build_mod.build
 MwaB200Error = _abi.MwaB200Error
-ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = _abi.ALGO_AUTO, _abi.ALGO_SIMT, _abi.ALGO_TCGEN05
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_V1 = (_abi.ALGO_AUTO, _abi.ALGO_SIMT, _abi.ALGO_TCGEN05,
+                                                          _abi.ALGO_TCGEN05_V1)

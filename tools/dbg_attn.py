@@ -31,6 +31,9 @@ def run(C, heads, ws, s, B, H, W, alpha_mode):
     if bad:
         print("   per-channel max (first 80):", [f"{v:.1e}" for v in per_ch[:80:4].tolist()])
         print("   per-token max:", [f"{v:.1e}" for v in per_tok.tolist()[:16]])
-for cfg in [(80, 8, 4, 0, 1, 8, 16, "ones"), (80, 8, 4, 0, 1, 16, 32, "ones"), (80, 8, 4, 2, 1, 16, 32, "ones"), (80, 8, 4, 2, 2, 16, 32, "blob"),
+for cfg in [(192, 8, 8, 0, 1, 8, 16, "ones"), (192, 8, 8, 0, 1, 16, 32, "ones"), (192, 8, 8, 4, 2, 64, 96, "blob"),
+            (192, 8, 8, 4, 16, 128, 192, "blob"), (192, 6, 8, 4, 4, 128, 192, "blob"), (80, 8, 4, 2, 16, 64, 96, "blob"),
+            (192, 8, 8, 4, 3, 24, 40, "blob"), (80, 8, 4, 2, 3, 12, 20, "blob"),
+            (80, 8, 4, 0, 1, 8, 16, "ones"), (80, 8, 4, 0, 1, 16, 32, "ones"), (80, 8, 4, 2, 1, 16, 32, "ones"), (80, 8, 4, 2, 2, 16, 32, "blob"),
             (192, 8, 8, 0, 1, 8, 16, "ones"), (192, 8, 8, 4, 1, 32, 48, "blob"), (192, 6, 8, 4, 1, 32, 48, "blob")]:
     run(*cfg)

@@ -101,7 +101,10 @@ def bench_attn(args, dev, flush):
             flops = kept * R.flops_per_window(C, ws)
             byts = nwin * (2 * ws * ws * C * 4 + ws * ws * 4)
             res = {}
-            for name, algo in (("simt", pkg.ALGO_SIMT), ("tcgen05", pkg.ALGO_TCGEN05)):
+            algos = [("tc-v1", pkg.ALGO_TCGEN05_V1), ("tcgen05", pkg.ALGO_TCGEN05)]
+            if not args.no_simt:
+                algos.insert(0, ("simt", pkg.ALGO_SIMT))
+            for name, algo in algos:
                 m.algo = algo
                 try:
                     with torch.no_grad():
@@ -114,10 +117,11 @@ def bench_attn(args, dev, flush):
                 print(f"attn C={C} h={heads} ws={ws} s={s} kept {kept}/{nwin} {name:8s} median {med:8.3f} ms best {best:8.3f} "
                       f"{flops / med / 1e9:8.1f} TFLOP/s = {flops / med / 1e9 / PEAKS['bf16_tflops'] * 100:5.2f}% tensor peak; "
                       f"{byts / med / 1e6:7.1f} GB/s = {byts / med / 1e6 / PEAKS['hbm_gbs'] * 100:5.1f}% HBM", flush=True)
-            if len(res) == 2:
-                d = (res["simt"] - res["tcgen05"]).abs()
-                print(f"    tcgen05 vs simt: max abs diff {d.max().item():.3e}, "
-                      f"allclose(1e-3,1e-4) {torch.allclose(res['tcgen05'], res['simt'], rtol=1e-3, atol=1e-4)}",
+            base = "simt" if "simt" in res else "tc-v1"
+            if base in res and "tcgen05" in res:
+                d = (res[base] - res["tcgen05"]).abs()
+                print(f"    tcgen05 vs {base}: max abs diff {d.max().item():.3e}, "
+                      f"allclose(1e-3,1e-4) {torch.allclose(res['tcgen05'], res[base], rtol=1e-3, atol=1e-4)}",
                       flush=True)
 
 
@@ -136,6 +140,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="*", default=["gdn", "attn", "round"])
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--no-simt", action="store_true", help="skip the (slow) fp32 SIMT attention kernel")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.zeros(128 * 1024 * 1024, device=dev)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""per-phase clock64 totals of the tcgen05 attention kernel (CTA 0): python tools/phase_times.py [attn8|attn4]"""
+"""per-stage clock64 totals of the warp-specialised attention kernel (CTA 0, first warp of each role):
+python tools/phase_times.py [attn8|attn4]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,16 +13,23 @@ x = torch.randn(16, C, H, W, device=dev); a = torch.ones(16, 1, H, W, device=dev
 lib = pkg._abi.load()
 with torch.no_grad():
     for _ in range(3): m(x, a)
-    buf = torch.zeros(32, dtype=torch.int64, device=dev)
-    lib.mwa_debug_set_timing_buffer(buf.data_ptr())
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
+    plain = e0.elapsed_time(e1)
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
+    lib.mwa_debug_set_timing_buffer(buf.data_ptr())
+    e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
     lib.mwa_debug_set_timing_buffer(None)
-t = buf.cpu().tolist(); tiles = max(t[15], 1)
-names = ["prologue", "x load+convert", "QKV issue group 0 (slab waits)", "QKV MMA wait", "qkv drain", "QKV issue next group", "attention core (HMMA)",
-         "-", "-", "-", "-", "proj issue (slab wait)", "residual loads issue", "last proj wait", "epilogue stores"]
-tot = sum(t[:15])
-print("  acquire_q wait cycles per tile by K block:", [round(v / tiles) for v in t[16:20]])
-print(f"{what}: kernel+scan {e0.elapsed_time(e1)*1e3:.0f} us, CTA0 tiles {tiles}, cycles/tile {sum(t[1:15])/tiles:.0f}")
-for n, v in zip(names, t):
-    print(f"  {n:28s} {v:10d} cyc  {100*v/tot:5.1f}%  per tile {v/tiles:8.0f}")
+t = buf.cpu().tolist()
+nwin = 16 * (H // ws) * (W // ws); tiles_cta = -(-(nwin * ws * ws // 128) // 148)
+print(f"{what}: scan+compact+kernel {plain*1e3:.0f} us (timing build {e0.elapsed_time(e1)*1e3:.0f} us), ~{tiles_cta} tiles per CTA")
+roles = [("MMA issuer", 0, ["wait X full", "wait D_qkv drained", "QKV issue + slab waits", "wait O_g", "wait proj acc free", "proj issue + slab wait"]),
+         ("x producer / epilogue", 8, ["prologue", "wait X free", "store X", "load x (tile+2)", "wait proj complete", "epilogue"]),
+         ("attention", 16, ["wait D_qkv", "drain", "wait O buffer", "attention core"])]
+for role, off, names in roles:
+    tot = sum(t[off:off + len(names)])
+    print(f"  {role}: {tot / tiles_cta:.0f} cycles per tile")
+    for i, n in enumerate(names):
+        v = t[off + i]
+        print(f"    {n:28s} {v:10d} cyc  {100 * v / max(tot, 1):5.1f}%  per tile {v / tiles_cta:8.0f}")
