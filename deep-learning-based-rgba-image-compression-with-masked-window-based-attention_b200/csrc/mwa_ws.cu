@@ -74,26 +74,116 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// L2 eviction-priority policies: x is read exactly once (evict first); the residual pre-stored into `out` must
+// survive in L2 until the epilogue's reduction reaches it two tiles later (evict last), after which the line is final.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_hint(const float* addr, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(addr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_hint(float* addr, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v, uint64_t pol) {
+    (void)pol;
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 
-// One attention task (rows row0..row0+15 of the tile, keys key0..key0+NTOK-1, head at chunk offset cb).
-// tbl: shared address of this lane's entry of the head's relative-position table for (h2 = 0, n = 0, e = 0); the
-// other 31 entries are at compile-time offsets (see the caller).
+// Tile row order.  A warp's 32 TMEM lanes / tile rows hold, for 8x8 windows, image rows 2q and 2q+1 of BOTH windows of
+// the tile (for 4x4 windows: image row q of all 8 windows) instead of 4 rows of one window: when the two windows are
+// horizontal neighbours (the common case in the kept-window list) a warp-wide access of one channel then touches
+// 2 x 64 contiguous bytes instead of 4 x 32 -- the NCHW gather is bound by the number of 128-byte lines a request
+// touches.  The tensor-core side does not care about the row order; the attention warps address rows through
+// ldmatrix's per-lane row pointers.
+template <int WS>
+__device__ __forceinline__ int tile_row(int w, int t) {          // window slot w, token t -> tile row
+    if constexpr (WS == 8) return (t >> 4) * 32 + ((t >> 3) & 1) * 16 + w * 8 + (t & 7);
+    else return (t >> 2) * 32 + w * 4 + (t & 3);
+}
+template <int WS>
+__device__ __forceinline__ void tile_row_inv(int r, int& w, int& t) {
+    if constexpr (WS == 8) {
+        w = (r >> 3) & 1;
+        t = (r >> 5) * 16 + ((r >> 4) & 1) * 8 + (r & 7);
+    } else {
+        w = (r >> 2) & 7;
+        t = (r >> 5) * 4 + (r & 3);
+    }
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+
+// Per-lane shared-memory offsets of the operand rows an attention task touches (relative to the Q / K / V / O buffer
+// and to window slot 0); for 8x8 windows every other address of the task is base + w * 1024 + a compile-time term,
+// optionally XORed with a compile-time chunk bit -- nothing is recomputed (or spilled) per task.
 template <class CF>
-__device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint32_t sV, uint32_t sO, uint32_t tbl,
-                                                  int row0, int key0, int cb, bool has_mask,
-                                                  const uint32_t (&rowmask)[2], int lane) {
+struct TaskAddr {
+    uint32_t q, k, v, o;
+    int rbk, cb;
+    __device__ __forceinline__ TaskAddr(int rbk_, int hh, int lane) : rbk(rbk_), cb(hh * (CF::DPAD / 8)) {
+        if constexpr (CF::WS == 8) {
+            const uint32_t m = lane & 7;
+            q = (rbk * 4 + ((lane >> 3) & 1) * 2) * 1024 + m * 128 + (((cb + (lane >> 4)) ^ m) << 4);
+            k = m * 128 + (((cb + (lane >> 3)) ^ m) << 4);
+            v = ((lane >> 3) & 1) * 2048 + m * 128 + (((cb + (lane >> 4)) ^ m) << 4);
+            const uint32_t mo = lane >> 2;
+            o = rbk * 4096 + mo * 128 + ((cb ^ mo) << 4) + (lane & 3) * 4;
+        } else {
+            q = k = v = o = 0;
+        }
+    }
+};
+
+// One attention task: the 16 query tokens rbk*16 .. rbk*16+15 of window slot w against the window's NTOK keys, for the
+// head at 16-byte-chunk offset cb of the group buffers.  S = Q K^T + bias (accumulator initialiser, `bias` holds this
+// lane's values: index (h2 - n + NT - 1) * 2 + e) + region mask; softmax in registers; O = P V; O / rowsum -> fp16.
+template <class CF>
+__device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint32_t sV, uint32_t sO,
+                                                  const TaskAddr<CF>& ad, const float (&bias)[2 * (CF::NTOK / 8) + 2],
+                                                  int w, bool has_mask, const uint32_t (&rowmask)[2], int lane) {
     constexpr int WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, D = CF::D;
     constexpr int KS = DPAD / 16, NT = NTOK / 8, PK = NTOK / 16, ON = (D + 7) / 8;
-    constexpr int kRowStep = (8 / WS) * (2 * WS - 1);       // table index step per 8 tokens (rows: +, keys: -)
-    static_assert(8 % WS == 0, "window size must divide 8");
+    constexpr bool kHalfStep = (D % 16) != 0 && (D % 16) <= 8;      // last k step of Q K^T only needs 8 columns
+    constexpr bool kFast = (WS == 8) && (DPAD == 32);               // closed-form addresses (see TaskAddr)
+    const int rbk = ad.rbk, cb = ad.cb;
+    const uint32_t wo = w * 1024;
     uint32_t qa[KS][4];
+    if constexpr (kFast) {
+        ldmatrix_x4(qa[0], sQ + ad.q + wo);
+        ldmatrix_x4(qa[1], (sQ + ad.q + wo) ^ 32u);
+    } else {
+        const uint32_t row = tile_row<WS>(w, rbk * 16 + (lane & 15));
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qa[ks], sQ + swz(row0 + (lane & 15), cb + 2 * ks + (lane >> 4)));
+        for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qa[ks], sQ + swz(row, cb + 2 * ks + (lane >> 4)));
+    }
     float sc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
@@ -101,12 +191,27 @@ __device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) sc[n][2 * h2 + e] = ld_shared_f32(tbl + 4 * ((h2 - n) * kRowStep - e));
+            for (int e = 0; e < 2; ++e) sc[n][2 * h2 + e] = bias[(h2 - n + NT - 1) * 2 + e];
+    }
+    if constexpr (KS == 2) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            uint32_t kb[2];
-            ldmatrix_x2(kb, sK + swz(key0 + 8 * n + (lane & 7), cb + 2 * ks + ((lane >> 3) & 1)));
-            mma16816(sc[n], qa[ks], kb);
+        for (int n = 0; n < NT; ++n) {        // one x4 load: both k steps of the 8 keys of n-tile n
+            uint32_t kb[4];
+            if constexpr (kFast) ldmatrix_x4(kb, sK + ad.k + wo + ((n >> 1) * 4 + (n & 1) * 2) * 1024);
+            else ldmatrix_x4(kb, sK + swz(tile_row<WS>(w, 8 * n + (lane & 7)), cb + (lane >> 3)));
+            const uint32_t k0[2] = {kb[0], kb[1]}, k1[2] = {kb[2], kb[3]};
+            mma16816(sc[n], qa[0], k0);
+            if constexpr (kHalfStep) mma1688(sc[n], qa[1][0], qa[1][1], kb[2]);
+            else mma16816(sc[n], qa[1], k1);
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < NT; n += 2) {     // one x4 load: the single k step of n-tiles n and n+1
+            uint32_t kb[4];
+            ldmatrix_x4(kb, sK + swz(tile_row<WS>(w, 8 * (n + (lane >> 4)) + (lane & 7)), cb + ((lane >> 3) & 1)));
+            const uint32_t k0[2] = {kb[0], kb[1]}, k1[2] = {kb[2], kb[3]};
+            mma16816(sc[n], qa[0], k0);
+            mma16816(sc[n + 1], qa[0], k1);
         }
     }
     if (has_mask) {      // warp-uniform: SW-MSA region mask, only for windows on the wrapped border (:194-216)
@@ -149,20 +254,45 @@ __device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint
 #pragma unroll
     for (int nt = 0; nt < ON; ++nt) oc[nt][0] = oc[nt][1] = oc[nt][2] = oc[nt][3] = 0.f;
 #pragma unroll
-    for (int j = 0; j < PK; ++j)
+    for (int j = 0; j < PK; ++j) {
+        // keys 16j .. 16j+15: lanes 0-15 address the two 8-key halves of chunk nt, lanes 16-31 those of chunk nt + 1
+        uint32_t vaddr;
+        if constexpr (kFast) vaddr = sV + ad.v + wo + j * 4096;
+        else vaddr = 0;
+        const uint32_t row = kFast ? 0u : uint32_t(tile_row<WS>(w, 16 * j + (lane & 7) + 8 * ((lane >> 3) & 1)));
+#pragma unroll
+        for (int nt = 0; nt < ON; nt += 2) {
+            if (nt + 1 < ON) {
+                uint32_t vb[4];
+                if constexpr (kFast) ldmatrix_x4_trans(vb, vaddr ^ (uint32_t(nt) << 4));
+                else ldmatrix_x4_trans(vb, sV + swz(row, cb + nt + (lane >> 4)));
+                const uint32_t v0[2] = {vb[0], vb[1]}, v1[2] = {vb[2], vb[3]};
+                mma16816(oc[nt], pa[j], v0);
+                mma16816(oc[nt + 1], pa[j], v1);
+            } else {
+                uint32_t vb[2];
+                if constexpr (kFast) ldmatrix_x2_trans(vb, vaddr ^ (uint32_t(nt) << 4));
+                else ldmatrix_x2_trans(vb, sV + swz(row, cb + nt));
+                mma16816(oc[nt], pa[j], vb);
+            }
+        }
+    }
+    const float inva = rcp_approx(suma), invb = rcp_approx(sumb);
+    if constexpr (kFast) {
+        const uint32_t oa = sO + ad.o + wo;
 #pragma unroll
         for (int nt = 0; nt < ON; ++nt) {
-            uint32_t vb[2];
-            ldmatrix_x2_trans(vb, sV + swz(key0 + 16 * j + (lane & 7) + 8 * ((lane >> 3) & 1), cb + nt));
-            mma16816(oc[nt], pa[j], vb);
+            st_shared_b32(oa ^ (uint32_t(nt) << 4), pack_f16x2(oc[nt][0] * inva, oc[nt][1] * inva));
+            st_shared_b32((oa + 2048) ^ (uint32_t(nt) << 4), pack_f16x2(oc[nt][2] * invb, oc[nt][3] * invb));
         }
-    const float inva = 1.f / suma, invb = 1.f / sumb;
-    const uint32_t ra = row0 + (lane >> 2), rb = ra + 8;
+    } else {
+        const uint32_t ra = tile_row<WS>(w, rbk * 16 + (lane >> 2)), rb = tile_row<WS>(w, rbk * 16 + 8 + (lane >> 2));
 #pragma unroll
-    for (int nt = 0; nt < ON; ++nt) {
-        const uint32_t coff = (lane & 3) * 4;             // byte offset of the column pair inside its 16-byte chunk
-        st_shared_b32(sO + swz(ra, cb + nt) + coff, pack_f16x2(oc[nt][0] * inva, oc[nt][1] * inva));
-        st_shared_b32(sO + swz(rb, cb + nt) + coff, pack_f16x2(oc[nt][2] * invb, oc[nt][3] * invb));
+        for (int nt = 0; nt < ON; ++nt) {
+            const uint32_t coff = (lane & 3) * 4;         // byte offset of the column pair inside its 16-byte chunk
+            st_shared_b32(sO + swz(ra, cb + nt) + coff, pack_f16x2(oc[nt][0] * inva, oc[nt][1] * inva));
+            st_shared_b32(sO + swz(rb, cb + nt) + coff, pack_f16x2(oc[nt][2] * invb, oc[nt][3] * invb));
+        }
     }
 }
 
@@ -174,13 +304,15 @@ __device__ __forceinline__ void drain_part(uint32_t taddr, const float* bias, ui
     constexpr int D = CF::D, DPAD = CF::DPAD;
     static_assert(COL0 % 8 == 0 && NCOLS % 8 == 0 && H_LO * D >= COL0 && H_HI * D <= COL0 + NCOLS, "drain split");
     float val[NCOLS];
+    {
+        uint32_t acc[NCOLS / 8][8];
 #pragma unroll
-    for (int cc = 0; cc < NCOLS / 8; ++cc) {
-        uint32_t acc[8];
-        tmem_ld_x8(taddr + COL0 + cc * 8, acc);
+        for (int cc = 0; cc < NCOLS / 8; ++cc) tmem_ld_x8(taddr + COL0 + cc * 8, acc[cc]);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) val[cc * 8 + j] = __uint_as_float(acc[j]) + bias[COL0 + cc * 8 + j];
+        for (int cc = 0; cc < NCOLS / 8; ++cc)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[cc * 8 + j] = __uint_as_float(acc[cc][j]) + bias[COL0 + cc * 8 + j];
     }
 #pragma unroll
     for (int ch = H_LO * DPAD / 8; ch < H_HI * DPAD / 8; ++ch) {
@@ -388,11 +520,13 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         const int pw = warp - kPeWarp0, q = pw & 3, half = pw >> 2;
         const int r = q * 32 + lane;                        // token row of the tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const int wslot = r / NTOK, tok = r % NTOK;
+        int wslot, tok;
+        tile_row_inv<WS>(r, wslot, tok);
         constexpr int CPH = CF::NCHUNK / 2;                 // 8-channel chunks per thread (half of the row)
         static_assert(CF::NCHUNK % 2 == 0, "C must be a multiple of 16");
-        constexpr int LB = 3;                               // chunks per load batch (24 loads in flight)
+        constexpr int LB = 4;                               // chunks per load batch (32 loads in flight)
         uint32_t pk[CPH][4];
+        const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
         auto row_base = [&](int tile, bool& valid) -> int64_t {      // NCHW element offset of (b, c = 0, py, px)
             const int lidx = tile * CF::WPT + wslot;
             valid = lidx < count;
@@ -402,9 +536,13 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             token_pixel<WS>(geo, wy, wx, tok, py, px);
             return int64_t(b) * C * hw + int64_t(py) * geo.W + px;
         };
+        // x of one tile -> packed fp16 in registers; the fp32 values go straight to `out` (the residual: the epilogue
+        // then only ADDS the projection with a fire-and-forget reduction, no second read of x)
         auto load_x = [&](int tile) {
             bool valid;
-            const float* p = x + row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
+            const int64_t off = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
+            const float* p = x + off;
+            float* po = out + off;
 #pragma unroll
             for (int c0 = 0; c0 < CPH; c0 += LB) {
                 float v[LB][8];
@@ -420,6 +558,11 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
 #pragma unroll
                 for (int i = 0; i < LB; ++i)
                     if (c0 + i < CPH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (valid) stg_hint(po, v[i][j], pol_last);
+                            po += hw;
+                        }
 #pragma unroll
                         for (int jp = 0; jp < 4; ++jp) pk[c0 + i][jp] = pack_f16x2(v[i][2 * jp], v[i][2 * jp + 1]);
                     }
@@ -452,41 +595,28 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 if (it + 2 < my_tiles) load_x(tile + 2 * gridDim.x);
                 tick(11);                                                        // 11: load x (tile + 2)
             }
-            // ---- epilogue of tile `it`: out = x + (proj + bias), thread = token, half of the channels
+            // ---- epilogue of tile `it`: out (= x, stored by this very thread when it loaded the tile) += proj + bias;
+            //      thread = token, half of the channels
             bool valid;
-            const int64_t base = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
-            const float* xr = x + base;
-            float* orow = out + base;
-            constexpr int EB = 2;                            // chunks per residual batch
-            bool waited = false;
+            float* orow = out + row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
+            mbar_wait(bars + MP::bPjFull, it & 1);
+            tc_fence_after_sync();
+            tick(12);                                                            // 12: wait projection complete
+            constexpr int EG = 4;                            // chunks per TMEM round trip
 #pragma unroll
-            for (int c0 = 0; c0 < CPH; c0 += EB) {
-                float res[EB][8];
+            for (int c0 = 0; c0 < CPH; c0 += EG) {
+                uint32_t acc[EG][8];
 #pragma unroll
-                for (int i = 0; i < EB; ++i)
-                    if (c0 + i < CPH) {
+                for (int i = 0; i < EG; ++i)
+                    if (c0 + i < CPH) tmem_ld_x8(tm + MP::tP + lane_addr + (half * CPH + c0 + i) * 8, acc[i]);
+                tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            res[i][j] = valid ? __ldg(xr) : 0.f;
-                            xr += hw;
-                        }
-                    }
-                if (!waited) {
-                    mbar_wait(bars + MP::bPjFull, it & 1);
-                    tc_fence_after_sync();
-                    waited = true;
-                    tick(12);                                                    // 12: wait projection complete
-                }
-#pragma unroll
-                for (int i = 0; i < EB; ++i)
+                for (int i = 0; i < EG; ++i)
                     if (c0 + i < CPH) {
                         const int cc = (half * CPH + c0 + i) * 8;
-                        uint32_t acc[8];
-                        tmem_ld_x8(tm + MP::tP + lane_addr + cc, acc);
-                        tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (valid) *orow = res[i][j] + (__uint_as_float(acc[j]) + s_bproj[cc + j]);
+                            if (valid) red_add_f32(orow, __uint_as_float(acc[i][j]) + s_bproj[cc + j], pol_first);
                             orow += hw;
                         }
                     }
@@ -501,43 +631,54 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         const int a = warp - kAtWarp0, q = a & 3, half = a >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        constexpr int TPW = CF::TASKS / kNumAt;
-        static_assert(CF::TASKS % kNumAt == 0 && CF::RB * CF::WPT == kNumAt, "task decomposition");
-        // every task of this warp covers the same (16-row block, window slot); the head of the group is the task index
-        const int rbk = a % CF::RB, tws = (a / CF::RB) % CF::WPT;
+        // task decomposition: a warp keeps one (16-row block, head of the group) and walks over window slots, so the
+        // bias values it holds in registers serve all of its tasks of a head group
+        constexpr int NSLOT = CF::RB * HPG;                 // (row block, head) combinations
+        static_assert(kNumAt % NSLOT == 0 && CF::WPT % (kNumAt / NSLOT) == 0, "task decomposition");
+        constexpr int GW = kNumAt / NSLOT;                  // warps sharing a combination (split the window slots)
+        constexpr int TPW = CF::WPT / GW;                   // tasks (window slots) per warp and head group
+        constexpr int NT = NTOK / 8, NB = 2 * NT + 2;
+        constexpr int kRowStep = (8 / WS) * (2 * WS - 1);   // table index step per 8 tokens (rows: +, keys: -)
+        static_assert(8 % WS == 0, "window size must divide 8");
+        const int rbk = (a % NSLOT) % CF::RB, hh = (a % NSLOT) / CF::RB, w0 = (a / NSLOT) * TPW;
         // this lane's entry of the relative-position table for (h2 = 0, n = 0, e = 0), head 0
         int tbl_idx;
         {
             const int ti = rbk * 16 + (lane >> 2), tj = 2 * (lane & 3);
             tbl_idx = (ti / WS - tj / WS + WS - 1) * (2 * WS - 1) + (ti % WS - tj % WS + WS - 1);
         }
-        const uint32_t tbl0 = sb + MP::oTbl + 4 * tbl_idx;
+        const uint32_t tbl0 = sb + MP::oTbl + 4 * (tbl_idx + hh * CF::TBL);
+        const TaskAddr<CF> taddr(rbk, hh, lane);
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             // SW-MSA region mask bits of this warp's rows (:194-216); zero unless the window touches the wrapped border
-            uint32_t rowmask[2] = {0u, 0u};
-            bool has_mask = false;
-            if (geo.shift > 0) {
-                const int lidx = tile * CF::WPT + tws;
-                int tb_, twy, twx;
-                window_coords(geo, list[lidx < count ? lidx : count - 1], tb_, twy, twx);
-                has_mask = (twy == geo.nwy - 1) || (twx == geo.nwx - 1);
-                if (has_mask) {
-                    const int ys0 = twy * WS, xs0 = twx * WS;
+            uint32_t rowmask[TPW][2];
+            uint32_t mask_any = 0;
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const int tk = rbk * 16 + (lane >> 2) + 8 * h2;
-                        const int by = (ys0 + tk / WS >= geo.H - WS) + (ys0 + tk / WS >= geo.H - geo.shift);
-                        const int bx = (xs0 + tk % WS >= geo.W - WS) + (xs0 + tk % WS >= geo.W - geo.shift);
-                        uint32_t mbits = 0;
+            for (int i = 0; i < TPW; ++i) {
+                rowmask[i][0] = rowmask[i][1] = 0u;
+                if (geo.shift > 0) {
+                    const int lidx = tile * CF::WPT + w0 + i;
+                    int tb_, twy, twx;
+                    window_coords(geo, list[lidx < count ? lidx : count - 1], tb_, twy, twx);
+                    if ((twy == geo.nwy - 1) || (twx == geo.nwx - 1)) {
+                        mask_any |= 1u << i;
+                        const int ys0 = twy * WS, xs0 = twx * WS;
 #pragma unroll
-                        for (int j = 0; j < WS; ++j) {
-                            const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
-                            const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
-                            mbits |= uint32_t(byj != by) << j;
-                            mbits |= uint32_t(bxj != bx) << (8 + j);
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int tk = rbk * 16 + (lane >> 2) + 8 * h2;
+                            const int by = (ys0 + tk / WS >= geo.H - WS) + (ys0 + tk / WS >= geo.H - geo.shift);
+                            const int bx = (xs0 + tk % WS >= geo.W - WS) + (xs0 + tk % WS >= geo.W - geo.shift);
+                            uint32_t mbits = 0;
+#pragma unroll
+                            for (int j = 0; j < WS; ++j) {
+                                const int byj = (ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift);
+                                const int bxj = (xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift);
+                                mbits |= uint32_t(byj != by) << j;
+                                mbits |= uint32_t(bxj != bx) << (8 + j);
+                            }
+                            rowmask[i][h2] = mbits;
                         }
-                        rowmask[h2] = mbits;
                     }
                 }
             }
@@ -551,15 +692,15 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     constexpr bool kSplitK = (HPG % 2 == 0) && ((HPG / 2) * D % 8 == 0);
                     constexpr int KLO = kSplitK ? (HPG / 2) * D : NQ;     // k columns loaded by half 0
                     const uint32_t ta = tm + MP::tDq + b * MP::kDqStride + lane_addr;
-                    const float* bias = s_bqkv + g * CF::NQKV;
+                    const float* bqkv = s_bqkv + g * CF::NQKV;
                     const uint32_t rowoff = (r >> 3) * 1024 + (r & 7) * 128;
                     if (half == 0) {
-                        drain_part<CF, 0, NQ, 0, HPG>(ta, bias, sb + MP::oQ + rowoff, r);
-                        drain_part<CF, 0, KLO, 0, HPG / 2>(ta + NQ, bias + NQ, sb + MP::oK + rowoff, r);
+                        drain_part<CF, 0, NQ, 0, HPG>(ta, bqkv, sb + MP::oQ + rowoff, r);
+                        drain_part<CF, 0, KLO, 0, HPG / 2>(ta + NQ, bqkv + NQ, sb + MP::oK + rowoff, r);
                     } else {
-                        drain_part<CF, kSplitK ? KLO : 0, kSplitK ? NQ - KLO : NQ, HPG / 2, HPG>(ta + NQ, bias + NQ,
+                        drain_part<CF, kSplitK ? KLO : 0, kSplitK ? NQ - KLO : NQ, HPG / 2, HPG>(ta + NQ, bqkv + NQ,
                                                                                                   sb + MP::oK + rowoff, r);
-                        drain_part<CF, 0, NQ, 0, HPG>(ta + 2 * NQ, bias + 2 * NQ, sb + MP::oV + rowoff, r);
+                        drain_part<CF, 0, NQ, 0, HPG>(ta + 2 * NQ, bqkv + 2 * NQ, sb + MP::oV + rowoff, r);
                     }
                 }
                 tc_fence_before_sync();
@@ -568,13 +709,17 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tick(17);                                                        // 17: drain
                 if (G >= MP::kOBufs) mbar_wait(bars + MP::bOEmpty + ob, ((G / MP::kOBufs) - 1) & 1);
                 tick(18);                                                        // 18: wait O buffer free
+                // relative-position bias of this lane for head g * HPG + hh: value (h2 - n, e) at index (h2-n+NT-1)*2+e
+                float bias[NB];
 #pragma unroll
-                for (int i = 0; i < TPW; ++i) {
-                    const int hh = i;                        // head of the group == task index of this warp
-                    attention_task_ws<CF>(sb + MP::oQ, sb + MP::oK, sb + MP::oV, sb + MP::oO + ob * 16384,
-                                          tbl0 + 4 * (g * HPG + hh) * CF::TBL, tws * NTOK + rbk * 16, tws * NTOK,
-                                          hh * (DPAD / 8), has_mask, rowmask, lane);
-                }
+                for (int dq = 0; dq < NT + 1; ++dq)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        bias[dq * 2 + e] = ld_shared_f32(tbl0 + 4 * (g * HPG * CF::TBL + (dq - (NT - 1)) * kRowStep - e));
+#pragma unroll
+                for (int i = 0; i < TPW; ++i)
+                    attention_task_ws<CF>(sb + MP::oQ, sb + MP::oK, sb + MP::oV, sb + MP::oO + ob * 16384, taddr, bias,
+                                          w0 + i, (mask_any >> i) & 1u, rowmask[i], lane);
                 fence_proxy_async_smem();                    // O_g is read by the projection MMA (async proxy)
                 mbar_arrive(bars + MP::bOFull + ob);
                 named_sync(2, kAtThreads);                   // all reads of Q / K / V done before the next drain

@@ -10,6 +10,13 @@ dev = torch.device("cuda:0")
 C, h, ws, s, H, W = (192, 8, 8, 4, 128, 192) if what == "attn8" else (80, 8, 4, 2, 64, 96)
 m = pkg.MaskedWinBasedAttention(C, h, ws, s).to(dev); m.algo = pkg.ALGO_TCGEN05
 x = torch.randn(16, C, H, W, device=dev); a = torch.ones(16, 1, H, W, device=dev)
+keep_frac = 1.0
+if len(sys.argv) > 2:      # fraction of kept windows (blobs of 4x4 windows in the shifted frame)
+    keep_frac = float(sys.argv[2])
+    torch.manual_seed(1)
+    blob = (torch.rand(16, 1, H // ws // 4, W // ws // 4, device=dev) < keep_frac).float()
+    a = blob.repeat_interleave(4 * ws, 2).repeat_interleave(4 * ws, 3)
+    a = torch.roll(a, (s, s), (2, 3))
 lib = pkg._abi.load()
 with torch.no_grad():
     for _ in range(3): m(x, a)
@@ -22,7 +29,7 @@ with torch.no_grad():
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
     lib.mwa_debug_set_timing_buffer(None)
 t = buf.cpu().tolist()
-nwin = 16 * (H // ws) * (W // ws); tiles_cta = -(-(nwin * ws * ws // 128) // 148)
+nwin = int(16 * (H // ws) * (W // ws) * keep_frac); tiles_cta = max(1, -(-(nwin * ws * ws // 128) // 148))
 print(f"{what}: scan+compact+kernel {plain*1e3:.0f} us (timing build {e0.elapsed_time(e1)*1e3:.0f} us), ~{tiles_cta} tiles per CTA")
 roles = [("MMA issuer", 0, ["wait X full", "wait D_qkv drained", "QKV issue + slab waits", "wait O_g", "wait proj acc free", "proj issue + slab wait"]),
          ("x producer / epilogue", 8, ["prologue", "wait X free", "store X", "load x (tile+2)", "wait proj complete", "epilogue"]),
