@@ -39,6 +39,8 @@ _SIGNATURES = {
                             c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "window_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                          c_void_p]),
+    "mwa_backward": (c_int, [c_void_p] * 12 + [c_int] * 8 + [c_void_p]),
+    "window_attention_backward": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "round_ste_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "quantize_offset_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         c_int, c_int64, c_void_p]),

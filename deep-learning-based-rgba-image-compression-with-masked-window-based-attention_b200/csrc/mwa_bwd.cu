@@ -1,0 +1,358 @@
+// Masked window attention: backward (training), fp32 SIMT, one window per CTA iteration, persistent grid.
+// Reference semantics: autograd through layers/masked_win_attention.py:169-251 (block) and :96-131 (window attention);
+// layers/win_attention.py:153-207 (alpha == NULL); token mode = WindowAttention.forward with an additive mask.
+//
+// Per kept window the kernel re-computes the forward per head (q, k, v, P) and produces
+//   grad_x    = grad_out + dXw            (dropped windows: grad_x = grad_out, the block is the identity there)
+//   grad_table (accumulated over windows in shared memory, flushed once per CTA with atomics)
+// and writes four token-major scratch tensors from which the remaining parameter gradients are PLAIN GEMMs /
+// column sums over all tokens (done by the caller with a library GEMM):
+//   xw_tok  (nwin, N, C)   gathered input tokens          dWqkv = dqkv_tok^T xw_tok      dbqkv = sum dqkv_tok
+//   ao_tok  (nwin, N, C)   head-concatenated P V          dWproj = dy_tok^T ao_tok       dbproj = sum dy_tok
+//   dy_tok  (nwin, N, C)   gathered grad_out tokens
+//   dqkv_tok(nwin, N, 3C)  gradient wrt the qkv Linear output (q part already multiplied by the softmax scale)
+// Rows of dropped windows are written as zeros, so the GEMMs need no compaction.
+//
+// Math per head (q' = scale * q):  S = q' k^T + bias + mask,  P = softmax(S),  AO = P v,  y = AO Wproj^T + b
+//   dAO = dy Wproj          dP = dAO v^T        dv = P^T dAO        dS = P * (dP - rowsum(dP * P))
+//   dq' = dS k              dk = dS^T q'        dbias += dS         dXw = dqkv Wqkv
+#include "common.cuh"
+#include "params.cuh"
+#include "status.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kBT = 256;                            // threads per CTA
+constexpr float kNegMaskB = -100.0f;                // layers/masked_win_attention.py:214
+
+struct BGeo {
+    int B, C, H, W, ws, shift, nwx, nwy, N;
+    int channels_last;
+    int tokens;          // 1: tensors are (K, N, C) window tokens, no geometry / residual / keep predicate
+    int mask_nw;         // token mode: windows in the external additive mask (0 = none)
+    __device__ __forceinline__ void token_pixel(int wy, int wx, int t, int& y, int& x) const {
+        y = wy * ws + t / ws + shift; if (y >= H) y -= H;
+        x = wx * ws + t % ws + shift; if (x >= W) x -= W;
+    }
+    __device__ __forceinline__ int region(int wy, int wx, int t) const {
+        const int ys = wy * ws + t / ws, xs = wx * ws + t % ws;
+        return 3 * ((ys >= H - ws) + (ys >= H - shift)) + (xs >= W - ws) + (xs >= W - shift);
+    }
+    __device__ __forceinline__ int64_t elem(int win, int b, int wy, int wx, int t, int c) const {
+        if (tokens) return (int64_t(win) * N + t) * C + c;
+        int y, xx;
+        token_pixel(wy, wx, t, y, xx);
+        return channels_last ? ((int64_t(b) * H + y) * W + xx) * C + c : ((int64_t(b) * C + c) * H + y) * W + xx;
+    }
+};
+
+// out[n][o] = sum_k A[n][k] * Wm[k * ldw + o] (+ bias[o]);  A in smem (row stride lda); lanes run over o.
+template <int TN, class Epilogue>
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ A, int lda, const float* __restrict__ Wm, int ldw,
+                                          const float* __restrict__ bias, int N, int O, int K, Epilogue epi) {
+    const int nchunks = (N + TN - 1) / TN;
+    for (int item = threadIdx.x; item < O * nchunks; item += kBT) {
+        const int o = item % O, n0 = (item / O) * TN;
+        float acc[TN];
+        const float b = bias ? bias[o] : 0.f;
+#pragma unroll
+        for (int i = 0; i < TN; ++i) acc[i] = b;
+        for (int k = 0; k < K; k += 4) {
+            float w[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = (k + kk < K) ? __ldg(Wm + int64_t(k + kk) * ldw + o) : 0.f;
+#pragma unroll
+            for (int i = 0; i < TN; ++i) {
+                if (n0 + i < N) {
+                    const float* a = A + (n0 + i) * lda + k;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        if (k + kk < K) acc[i] = fmaf(a[kk], w[kk], acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+            if (n0 + i < N) epi(n0 + i, o, acc[i]);
+    }
+}
+
+// shared memory (floats):  R1 [N][C]  dy, then xw | R2 [N][C] dAO | R3 [N][3d+1] q' k v of the head |
+//                          R4 [N][N+1] S / P | R5 [N][N+1] dP / dS | R6 [N][3d+1] dq dk dv | tacc [heads][TBL]
+// after the head loop R1..R6 are re-used as one [N][3C+1] buffer for dqkv.
+__host__ __device__ inline int64_t bwd_smem_floats(int C, int heads, int ws) {
+    const int64_t N = ws * ws, d = C / heads, tbl = (2 * ws - 1) * (2 * ws - 1);
+    const int64_t work = 2 * N * C + 2 * N * (3 * d + 1) + 2 * N * (N + 1);
+    const int64_t dq = N * (3 * C + 1);
+    return (work > dq ? work : dq) + heads * tbl + 8;
+}
+
+__global__ void __launch_bounds__(kBT)
+mwa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ gout,
+               const float* __restrict__ qkv_w, const float* __restrict__ proj_w, const uint8_t* __restrict__ blk,
+               const float* __restrict__ ext_mask, float* __restrict__ gx, float* __restrict__ gtable,
+               float* __restrict__ xw_tok, float* __restrict__ ao_tok, float* __restrict__ dy_tok,
+               float* __restrict__ dqkv_tok, BGeo g, int heads, int nwin) {
+    extern __shared__ float smem[];
+    const int C = g.C, N = g.N, ws = g.ws, d = C / heads;
+    const int ldh = 3 * d + 1, lds = N + 1, ldq = 3 * C + 1, TBL = (2 * ws - 1) * (2 * ws - 1);
+    float* R1 = smem;
+    float* R2 = R1 + N * C;
+    float* R3 = R2 + N * C;
+    float* R4 = R3 + N * ldh;
+    float* R5 = R4 + N * lds;
+    float* R6 = R5 + N * lds;
+    const int64_t work = 2ll * N * C + 2ll * N * ldh + 2ll * N * lds, dqf = int64_t(N) * ldq;
+    float* tacc = smem + (work > dqf ? work : dqf);
+    __shared__ float red[kBT / 32];
+    __shared__ int keep_s;
+
+    const MwaParamLayout L(C, heads, ws);
+    const float scale = reinterpret_cast<const float*>(blk + L.header)[0];
+    const float* wqkvT = reinterpret_cast<const float*>(blk + L.wqkvT);     // [C][3C]
+    const float* bqkv = reinterpret_cast<const float*>(blk + L.bqkv);
+    const float* bias = reinterpret_cast<const float*>(blk + L.bias);       // [heads][N][N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool c_fast = g.channels_last || g.tokens;
+
+    for (int i = tid; i < heads * TBL; i += kBT) tacc[i] = 0.f;
+    __syncthreads();
+
+    for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+        const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+        bool keep = true;
+        if (alpha != nullptr) {
+            float a = 0.f;
+            for (int t = tid; t < N; t += kBT) {
+                int y, xx;
+                g.token_pixel(wy, wx, t, y, xx);
+                a += __ldg(alpha + (int64_t(b) * g.H + y) * g.W + xx);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int i = 0; i < kBT / 32; ++i) tot += red[i];
+                keep_s = (tot != 0.f);
+            }
+            __syncthreads();
+            keep = keep_s != 0;
+        }
+        const int64_t tok0 = int64_t(win) * N;
+        if (!keep) {      // identity block: grad passes through; scratch rows are zeros
+            for (int e = tid; e < N * C; e += kBT) {
+                const int c = c_fast ? e % C : e / N, t = c_fast ? e / C : e % N;
+                const int64_t off = g.elem(win, b, wy, wx, t, c);
+                gx[off] = __ldg(gout + off);
+                if (xw_tok) xw_tok[tok0 * C + e] = 0.f;
+                ao_tok[tok0 * C + e] = 0.f;
+                if (dy_tok) dy_tok[tok0 * C + e] = 0.f;
+            }
+            for (int e = tid; e < N * 3 * C; e += kBT) dqkv_tok[tok0 * 3 * C + e] = 0.f;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- dy -> R1 (+ scratch), dAO = dy Wproj -> R2
+        for (int e = tid; e < N * C; e += kBT) {
+            const int c = c_fast ? e % C : e / N, t = c_fast ? e / C : e % N;
+            const float v = __ldg(gout + g.elem(win, b, wy, wx, t, c));
+            R1[t * C + c] = v;
+            if (dy_tok) dy_tok[(tok0 + t) * C + c] = v;
+        }
+        __syncthreads();
+        gemm_rows<16>(R1, C, proj_w, C, nullptr, N, C, C, [&](int n, int o, float v) { R2[n * C + o] = v; });
+        __syncthreads();
+        // ---- xw -> R1 (+ scratch)
+        for (int e = tid; e < N * C; e += kBT) {
+            const int c = c_fast ? e % C : e / N, t = c_fast ? e / C : e % N;
+            const float v = __ldg(x + g.elem(win, b, wy, wx, t, c));
+            R1[t * C + c] = v;
+            if (xw_tok) xw_tok[(tok0 + t) * C + c] = v;
+        }
+        __syncthreads();
+
+        for (int h = 0; h < heads; ++h) {
+            // q' k v of this head: R3[n][part * d + c] = xw[n] . Wqkv[part*C + h*d + c] + b   (q' pre-scaled)
+            for (int item = tid; item < 3 * d * (N / 4); item += kBT) {
+                const int j = item % (3 * d), n0 = (item / (3 * d)) * 4;
+                const int col = (j / d) * C + h * d + (j % d);
+                float acc[4];
+                const float bb = bqkv[col];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = bb;
+                for (int k = 0; k < C; ++k) {
+                    const float w = __ldg(wqkvT + int64_t(k) * 3 * C + col);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] = fmaf(R1[(n0 + i) * C + k], w, acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) R3[(n0 + i) * ldh + j] = (j < d) ? acc[i] * scale : acc[i];
+            }
+            __syncthreads();
+            // S = q' k^T + bias + mask -> R4
+            const float* bh = bias + int64_t(h) * N * N;
+            for (int e = tid; e < N * N; e += kBT) {
+                const int i = e / N, j = e % N;
+                const float* q = R3 + i * ldh;
+                const float* k = R3 + j * ldh + d;
+                float acc = 0.f;
+                for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
+                acc += __ldg(bh + e);
+                if (g.tokens) {
+                    if (g.mask_nw > 0) acc += __ldg(ext_mask + (int64_t(win % g.mask_nw) * N + i) * N + j);
+                } else if (g.shift > 0 && g.region(wy, wx, i) != g.region(wy, wx, j)) {
+                    acc += kNegMaskB;
+                }
+                R4[i * lds + j] = acc;
+            }
+            __syncthreads();
+            for (int i = warp; i < N; i += kBT / 32) {                 // softmax, warp per row
+                float* row = R4 + i * lds;
+                float m = -INFINITY;
+                for (int j = lane; j < N; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int j = lane; j < N; j += 32) {
+                    const float e = expf(row[j] - m);
+                    row[j] = e;
+                    sum += e;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float inv = 1.f / sum;
+                for (int j = lane; j < N; j += 32) row[j] *= inv;
+            }
+            __syncthreads();
+            // AO_h = P v -> scratch ;  dP = dAO_h v^T -> R5 ;  dv = P^T dAO_h -> R6[:, 2d..3d)
+            for (int e = tid; e < N * d; e += kBT) {
+                const int i = e / d, c = e % d;
+                const float* p = R4 + i * lds;
+                float acc = 0.f;
+                for (int j = 0; j < N; ++j) acc = fmaf(p[j], R3[j * ldh + 2 * d + c], acc);
+                ao_tok[(tok0 + i) * C + h * d + c] = acc;
+                float dv = 0.f;                                       // row i acts as key index here
+                for (int n = 0; n < N; ++n) dv = fmaf(R4[n * lds + i], R2[n * C + h * d + c], dv);
+                R6[i * ldh + 2 * d + c] = dv;
+            }
+            for (int e = tid; e < N * N; e += kBT) {
+                const int i = e / N, j = e % N;
+                const float* da = R2 + i * C + h * d;
+                const float* v = R3 + j * ldh + 2 * d;
+                float acc = 0.f;
+                for (int c = 0; c < d; ++c) acc = fmaf(da[c], v[c], acc);
+                R5[i * lds + j] = acc;
+            }
+            __syncthreads();
+            for (int i = warp; i < N; i += kBT / 32) {                 // dS = P * (dP - sum_j dP P)
+                float dot = 0.f;
+                for (int j = lane; j < N; j += 32) dot = fmaf(R5[i * lds + j], R4[i * lds + j], dot);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                for (int j = lane; j < N; j += 32) R5[i * lds + j] = R4[i * lds + j] * (R5[i * lds + j] - dot);
+            }
+            __syncthreads();
+            // dq' = dS k ; dk = dS^T q'  -> R6 ; relative-position table gradient: one thread per table entry
+            for (int e = tid; e < N * d; e += kBT) {
+                const int i = e / d, c = e % d;
+                float dq = 0.f, dk = 0.f;
+                for (int j = 0; j < N; ++j) {
+                    dq = fmaf(R5[i * lds + j], R3[j * ldh + d + c], dq);
+                    dk = fmaf(R5[j * lds + i], R3[j * ldh + c], dk);
+                }
+                R6[i * ldh + c] = dq * scale;                         // gradient wrt the un-scaled q
+                R6[i * ldh + d + c] = dk;
+            }
+            for (int idx = tid; idx < TBL; idx += kBT) {
+                const int dy = idx / (2 * ws - 1) - (ws - 1), dx = idx % (2 * ws - 1) - (ws - 1);   // yi - yj, xi - xj
+                float acc = 0.f;
+                for (int yj = max(0, -dy); yj < min(ws, ws - dy); ++yj)
+                    for (int xj = max(0, -dx); xj < min(ws, ws - dx); ++xj)
+                        acc += R5[((yj + dy) * ws + xj + dx) * lds + yj * ws + xj];
+                tacc[h * TBL + idx] += acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < N * 3 * d; e += kBT) {               // R6 -> scratch columns (part, h, c)
+                const int n = e / (3 * d), j = e % (3 * d);
+                dqkv_tok[(tok0 + n) * 3 * C + (j / d) * C + h * d + (j % d)] = R6[n * ldh + j];
+            }
+            __syncthreads();
+        }
+
+        // ---- dXw = dqkv Wqkv ; grad_x = grad_out + dXw at the un-shifted position
+        __threadfence_block();
+        float* DQ = smem;                                              // [N][3C+1] over R1..R6
+        for (int e = tid; e < N * 3 * C; e += kBT) DQ[(e / (3 * C)) * ldq + e % (3 * C)] = dqkv_tok[tok0 * 3 * C + e];
+        __syncthreads();
+        // results staged in registers per work item and written straight to global (token rows are disjoint)
+        gemm_rows<16>(DQ, ldq, qkv_w, C, nullptr, N, C, 3 * C, [&](int n, int o, float v) {
+            const int64_t off = g.elem(win, b, wy, wx, n, o);
+            gx[off] = g.tokens ? v : __ldg(gout + off) + v;
+        });
+        __syncthreads();
+    }
+    for (int i = tid; i < heads * TBL; i += kBT) {                     // table layout: [(2ws-1)^2][heads]
+        const int h = i / TBL, idx = i % TBL;
+        atomicAdd(gtable + idx * heads + h, tacc[i]);
+    }
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+static int launch_bwd(const float* x, const float* alpha, const float* gout, const float* qkv_w, const float* proj_w,
+                      const void* params, const float* ext_mask, float* gx, float* gtable, float* xw_tok,
+                      float* ao_tok, float* dy_tok, float* dqkv_tok, BGeo g, int heads, int64_t nwin64,
+                      cudaStream_t st) {
+    if (nwin64 > 0x7fffffffll) return MWA_ERR_UNSUPPORTED;
+    const int nwin = static_cast<int>(nwin64);
+    const int TBL = (2 * g.ws - 1) * (2 * g.ws - 1);
+    MWA_TRY_CUDA(cudaMemsetAsync(gtable, 0, sizeof(float) * TBL * heads, st), "mwa_backward(memset)");
+    if (nwin == 0) return MWA_OK;
+    const int64_t smem = 4 * bwd_smem_floats(g.C, heads, g.ws);
+    if (g.N > 64 || g.N % 4 != 0 || smem > 227 * 1024 - 64) return MWA_ERR_UNSUPPORTED;
+    MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                 "mwa_backward(attr)");
+    const int grid = nwin < kNumSMs ? nwin : kNumSMs;
+    mwa_bwd_kernel<<<grid, kBT, smem, st>>>(x, alpha, gout, qkv_w, proj_w, static_cast<const uint8_t*>(params),
+                                            ext_mask, gx, gtable, xw_tok, ao_tok, dy_tok, dqkv_tok, g, heads, nwin);
+    return check_launch("mwa_backward");
+}
+
+int mwa_backward(const float* x, const float* alpha, const float* grad_out, const float* qkv_w, const float* proj_w,
+                 const void* params, float* grad_x, float* grad_table, float* xw_tok, float* ao_tok, float* dy_tok,
+                 float* dqkv_tok, int B, int C, int H, int W, int heads, int ws, int shift, int channels_last,
+                 void* stream) {
+    if (!x || !grad_out || !qkv_w || !proj_w || !params || !grad_x || !grad_table || !xw_tok || !ao_tok || !dy_tok ||
+        !dqkv_tok)
+        return MWA_ERR_INVALID;
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return MWA_ERR_INVALID;
+    if (shift < 0 || shift >= ws || H % ws != 0 || W % ws != 0) return MWA_ERR_INVALID;
+    BGeo g{B, C, H, W, ws, shift, W / ws, H / ws, ws * ws, channels_last, 0, 0};
+    return launch_bwd(x, alpha, grad_out, qkv_w, proj_w, params, nullptr, grad_x, grad_table, xw_tok, ao_tok, dy_tok,
+                      dqkv_tok, g, heads, int64_t(B) * g.nwx * g.nwy, static_cast<cudaStream_t>(stream));
+}
+
+int window_attention_backward(const float* xw, const float* mask, const float* grad_out, const float* qkv_w,
+                              const float* proj_w, const void* params, float* grad_xw, float* grad_table,
+                              float* ao_tok, float* dqkv_tok, int64_t K, int C, int heads, int ws, int mask_windows,
+                              void* stream) {
+    if (!xw || !grad_out || !qkv_w || !proj_w || !params || !grad_xw || !grad_table || !ao_tok || !dqkv_tok)
+        return MWA_ERR_INVALID;
+    if (K < 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0 || mask_windows < 0) return MWA_ERR_INVALID;
+    if (mask_windows > 0 && (!mask || K % mask_windows != 0)) return MWA_ERR_INVALID;
+    BGeo g{static_cast<int>(K), C, ws, ws, ws, 0, 1, 1, ws * ws, 1, 1, mask_windows};
+    // token mode: xw / grad_out already ARE the token-major tensors the caller's GEMMs need -> no copies of them
+    return launch_bwd(xw, nullptr, grad_out, qkv_w, proj_w, params, mask, grad_xw, grad_table, /*xw_tok=*/nullptr,
+                      ao_tok, /*dy_tok=*/nullptr, dqkv_tok, g, heads, K, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

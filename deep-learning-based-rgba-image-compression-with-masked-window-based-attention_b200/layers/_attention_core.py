@@ -1,10 +1,11 @@
 """Shared machinery of the two window-attention drop-ins (masked / unmasked).
 
 Forward = the fused sm_100a kernel (`mwa_forward`, `window_attention_forward`).
-Backward (training, BASELINE config 5) is INTERIM: it re-computes the block with differentiable
-torch CUDA ops on the saved inputs and back-propagates through that graph.  It is numerically the
-same function (fp32) and keeps training runnable until the hand-written backward kernels land
-("what comes next").  It is never used for forward values.
+Backward (training, BASELINE config 5) = the hand-written `mwa_backward` / `window_attention_backward`
+kernels (fp32; they re-compute q, k, v and the softmax per head, emit grad_x and the relative-position
+table gradient, and leave four token-major scratch tensors), followed by the weight / bias gradients
+as plain GEMMs and column sums over all tokens (library GEMM: `dWqkv = dqkv^T xw`, `dWproj = dy^T ao`).
+`_differentiable_block` is a torch re-statement kept ONLY as a cross-check for the tests.
 """
 from __future__ import annotations
 
@@ -103,20 +104,30 @@ class WindowAttentionFunction(Function):
     def backward(ctx, grad_out):
         x, alpha, qkv_w, qkv_b, proj_w, proj_b, table = ctx.saved_tensors
         attn_mod, ws, shift = ctx.cfg
-        need = ctx.needs_input_grad
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(n) if t is not None else None
-                      for t, n in zip((x, qkv_w, qkv_b, proj_w, proj_b, table),
-                                      (need[0], need[2], need[3], need[4], need[5], need[6]))]
-            xx, w1, b1, w2, b2, tb = leaves
-            y = _differentiable_block(xx, alpha, w1, b1, w2, b2, tb, attn_mod.relative_position_index,
-                                      attn_mod.num_heads, ws, shift, attn_mod.scale)
-            wanted = [t for t in leaves if t is not None and t.requires_grad]
-            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True) if wanted else []
-        it = iter(grads)
-        res = [next(it) if (t is not None and t.requires_grad) else None for t in leaves]
-        gx, gw1, gb1, gw2, gb2, gtb = res
-        return gx, None, gw1, gb1, gw2, gb2, gtb, None, None, None, None
+        lib = _abi.load()
+        _abi.require_cuda_f32(grad_out, "grad_output")
+        B, C, H, W = x.shape
+        channels_last = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
+        grad_out = grad_out.contiguous(memory_format=torch.channels_last) if channels_last else grad_out.contiguous()
+        N, nwin = ws * ws, B * (H // ws) * (W // ws)
+        with torch.cuda.device(x.device):
+            blk = attn_mod._param_block(qkv_w, qkv_b, proj_w, proj_b, table)
+            gx = torch.empty_like(x)
+            gtab = torch.empty_like(table)
+            xw, ao, dy = (torch.empty(nwin * N, C, device=x.device) for _ in range(3))
+            dqkv = torch.empty(nwin * N, 3 * C, device=x.device)
+            qw, pw = qkv_w.contiguous(), proj_w.contiguous()
+            _abi.check(lib.mwa_backward(x.data_ptr(), _abi.ptr(alpha), grad_out.data_ptr(), qw.data_ptr(),
+                                        pw.data_ptr(), blk.data_ptr(), gx.data_ptr(), gtab.data_ptr(), xw.data_ptr(),
+                                        ao.data_ptr(), dy.data_ptr(), dqkv.data_ptr(), B, C, H, W,
+                                        attn_mod.num_heads, ws, shift, int(channels_last), _abi.stream_handle()),
+                       "mwa_backward")
+            need = ctx.needs_input_grad
+            gw1 = dqkv.t() @ xw if need[2] else None
+            gb1 = dqkv.sum(0) if (need[3] and ctx.has_bias) else None
+            gw2 = dy.t() @ ao if need[4] else None
+            gb2 = dy.sum(0) if need[5] else None
+        return (gx if need[0] else None), None, gw1, gb1, gw2, gb2, (gtab if need[6] else None), None, None, None, None
 
 
 class TokenAttentionFunction(Function):
@@ -155,27 +166,30 @@ class TokenAttentionFunction(Function):
     def backward(ctx, grad_out):
         xw, mask, qkv_w, qkv_b, proj_w, proj_b, table = ctx.saved_tensors
         m = ctx.attn_mod
-        need = ctx.needs_input_grad
+        lib = _abi.load()
+        _abi.require_cuda_f32(grad_out, "grad_output")
+        grad_out = grad_out.contiguous()
         K, N, C = xw.shape
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(n) if t is not None else None
-                      for t, n in zip((xw, qkv_w, qkv_b, proj_w, proj_b, table),
-                                      (need[0], need[2], need[3], need[4], need[5], need[6]))]
-            xx, w1, b1, w2, b2, tb = leaves
-            d = C // m.num_heads
-            qkv = torch.nn.functional.linear(xx, w1, b1).reshape(K, N, 3, m.num_heads, d).permute(2, 0, 3, 1, 4)
-            att = (qkv[0] * m.scale) @ qkv[1].transpose(-2, -1)
-            att = att + tb[m.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1).unsqueeze(0)
-            if mask is not None:
-                nw = mask.shape[0]
-                att = (att.view(K // nw, nw, m.num_heads, N, N) + mask[None, :, None]).view(-1, m.num_heads, N, N)
-            y = (torch.softmax(att, dim=-1) @ qkv[2]).transpose(1, 2).reshape(K, N, C)
-            y = torch.nn.functional.linear(y, w2, b2)
-            wanted = [t for t in leaves if t is not None and t.requires_grad]
-            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True) if wanted else []
-        it = iter(grads)
-        res = [next(it) if (t is not None and t.requires_grad) else None for t in leaves]
-        return res[0], None, res[1], res[2], res[3], res[4], res[5], None
+        ws = m.window_size[0]
+        nw = 0 if mask is None else mask.shape[0]
+        with torch.cuda.device(xw.device):
+            blk = m._param_block(qkv_w, qkv_b, proj_w, proj_b, table)
+            gx = torch.empty_like(xw)
+            gtab = torch.empty_like(table)
+            ao = torch.empty(K * N, C, device=xw.device)
+            dqkv = torch.empty(K * N, 3 * C, device=xw.device)
+            qw, pw = qkv_w.contiguous(), proj_w.contiguous()
+            _abi.check(lib.window_attention_backward(xw.data_ptr(), _abi.ptr(mask), grad_out.data_ptr(), qw.data_ptr(),
+                                                     pw.data_ptr(), blk.data_ptr(), gx.data_ptr(), gtab.data_ptr(),
+                                                     ao.data_ptr(), dqkv.data_ptr(), K, C, m.num_heads, ws, nw,
+                                                     _abi.stream_handle()), "window_attention_backward")
+            need = ctx.needs_input_grad
+            xf, dyf = xw.reshape(K * N, C), grad_out.reshape(K * N, C)
+            gw1 = dqkv.t() @ xf if need[2] else None
+            gb1 = dqkv.sum(0) if (need[3] and qkv_b is not None) else None
+            gw2 = dyf.t() @ ao if need[4] else None
+            gb2 = dyf.sum(0) if need[5] else None
+        return (gx if need[0] else None), None, gw1, gb1, gw2, gb2, (gtab if need[6] else None), None
 
 
 class WindowAttentionBase(nn.Module):

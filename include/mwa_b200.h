@@ -108,6 +108,27 @@ MWA_API int mwa_forward(const float* x, const float* alpha, float* out, const vo
 MWA_API int window_attention_forward(const float* xw, const float* mask, float* out, const void* params, int64_t K,
                                      int C, int heads, int ws, int mask_windows, void* stream);
 
+/* mwa_backward : replaces autograd through layers/masked_win_attention.py:169-251 / layers/win_attention.py:153-207.
+ *   grad_x (B,C,H,W) = grad_out + d(window attention) on kept windows (dropped windows: grad_out);
+ *   grad_table ((2ws-1)^2, heads) is OVERWRITTEN with the relative-position table gradient;
+ *   the four token-major scratch tensors (nwin = B*(H/ws)*(W/ws) windows, N = ws*ws; rows of dropped windows are
+ *   zeros) carry everything the remaining parameter gradients need as plain GEMMs / column sums over tokens:
+ *     xw_tok (nwin,N,C), ao_tok (nwin,N,C), dy_tok (nwin,N,C), dqkv_tok (nwin,N,3C)
+ *     grad qkv.weight = dqkv_tok^T xw_tok   grad qkv.bias = colsum(dqkv_tok)
+ *     grad proj.weight = dy_tok^T ao_tok    grad proj.bias = colsum(dy_tok)
+ *   qkv_w (3C,C) / proj_w (C,C) are the un-prepared fp32 weights; `params` the mwa_prepare block of the same weights.
+ * window_attention_backward : same for layers/masked_win_attention.py:96-131 on (K,N,C) tokens with the optional
+ *   additive (mask_windows,N,N) mask; xw / grad_out themselves play the role of xw_tok / dy_tok.
+ * fp32 SIMT kernels; supported: ws*ws <= 64 tokens (multiple of 4), shared-memory footprint <= 227 KB. */
+MWA_API int mwa_backward(const float* x, const float* alpha, const float* grad_out, const float* qkv_w,
+                         const float* proj_w, const void* params, float* grad_x, float* grad_table, float* xw_tok,
+                         float* ao_tok, float* dy_tok, float* dqkv_tok, int B, int C, int H, int W, int heads, int ws,
+                         int shift, int channels_last, void* stream);
+MWA_API int window_attention_backward(const float* xw, const float* mask, const float* grad_out, const float* qkv_w,
+                                      const float* proj_w, const void* params, float* grad_xw, float* grad_table,
+                                      float* ao_tok, float* dqkv_tok, int64_t K, int C, int heads, int ws,
+                                      int mask_windows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Latent rounding   replaces  models/AutoEncoderRGB_Journal.py:31-32 (ste_round; forward value) and its
  *   uses :227-229, :257, :262-264, :212-214  (= models/AutoEncoderMask_Journal.py:142-143, :255-257, :284).

@@ -199,21 +199,71 @@ def test_window_attention_tokens_with_mask(pkg, cuda_dev):
     torch.testing.assert_close(y0, R.window_attention(x, *args, 4, 4), rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["attn_c32_h4_ws4_s2", "attn_c80_h8_ws4_s2"])
+@pytest.mark.parametrize("name", list(G.ATTENTION_CASES))
 def test_attention_backward_vs_golden(pkg, cuda_dev, golden, name):
+    """mwa_backward (hand-written fp32 kernel + token GEMMs) against the reference's autograd gradients."""
     cfg = G.ATTENTION_CASES[name]
     p = G.attention_inputs(cfg)
     m = _mk_attn(pkg, cfg, p, cuda_dev)
+    m.algo = ALGOS["simt"]               # fp32 forward: the committed gradients were taken at fp32
     x = p["x"].to(cuda_dev).requires_grad_(True)
-    y = m(x, p["alpha"].to(cuda_dev))
+    y = m(x, p["alpha"].to(cuda_dev)) if cfg["masked"] else m(x)
     gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(cfg["seed"] + 5)).to(cuda_dev)
     y.backward(gy)
     g = golden["attention"]
     torch.testing.assert_close(x.grad.cpu(), _t(g[name + "/dx"]), rtol=1e-3, atol=1e-4)
-    torch.testing.assert_close(m.attn.qkv.weight.grad.cpu(), _t(g[name + "/dqkv_w"]), rtol=1e-3, atol=1e-3)
-    torch.testing.assert_close(m.attn.proj.weight.grad.cpu(), _t(g[name + "/dproj_w"]), rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(m.attn.relative_position_bias_table.grad.cpu(), _t(g[name + "/dtable"]), rtol=1e-3,
                                atol=1e-3)
+    if name + "/dqkv_w" in g:
+        torch.testing.assert_close(m.attn.qkv.weight.grad.cpu(), _t(g[name + "/dqkv_w"]), rtol=1e-3, atol=1e-3)
+        torch.testing.assert_close(m.attn.proj.weight.grad.cpu(), _t(g[name + "/dproj_w"]), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", ["attn_c80_h8_ws4_s2", "attn_c192_h8_ws8_s4"])
+def test_attention_backward_all_gradients(pkg, cuda_dev, name, channels_last):
+    """every gradient (incl. the two bias vectors, which the golden file does not carry) against autograd through the
+    oracle's fp64 re-statement; NHWC input gives the same gradients."""
+    cfg = G.ATTENTION_CASES[name]
+    p = G.attention_inputs(cfg)
+    m = _mk_attn(pkg, cfg, p, cuda_dev)
+    m.algo = ALGOS["simt"]
+    x = p["x"].to(cuda_dev)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = m(x, p["alpha"].to(cuda_dev))
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3))
+    y.backward(gy.to(cuda_dev))
+    leaves = {k: (None if v is None else v.double().requires_grad_(k != "alpha")) for k, v in p.items()}
+    ref = R.masked_window_attention(leaves["x"], leaves["alpha"], leaves["qkv_w"], leaves["qkv_b"], leaves["proj_w"],
+                                    leaves["proj_b"], leaves["table"], cfg["heads"], cfg["ws"], cfg["shift"])
+    ref.backward(gy.double())
+    got = dict(x=x.grad, qkv_w=m.attn.qkv.weight.grad, qkv_b=m.attn.qkv.bias.grad, proj_w=m.attn.proj.weight.grad,
+               proj_b=m.attn.proj.bias.grad, table=m.attn.relative_position_bias_table.grad)
+    for k, v in got.items():
+        torch.testing.assert_close(v.double().cpu(), leaves[k].grad, rtol=1e-3, atol=2e-4, msg=lambda s_, k=k: f"{k}: {s_}")
+
+
+def test_window_attention_tokens_backward(pkg, cuda_dev):
+    """window_attention_backward: WindowAttention.forward(x, mask) on pre-partitioned tokens."""
+    wa = pkg.WindowAttention(dim=32, window_size=(4, 4), num_heads=4).to(cuda_dev)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(6, 16, 32, generator=g)
+    mask = torch.randn(3, 16, 16, generator=g)
+    gy = torch.randn(6, 16, 32, generator=g)
+    with torch.no_grad():
+        wa.relative_position_bias_table.normal_(0, 0.5)
+    xd = x.to(cuda_dev).requires_grad_(True)
+    wa(xd, mask.to(cuda_dev)).backward(gy.to(cuda_dev))
+    names = ("qkv.weight", "qkv.bias", "proj.weight", "proj.bias", "relative_position_bias_table")
+    params = [dict(wa.named_parameters())[n] for n in names]
+    ref_leaves = [t.detach().double().cpu().requires_grad_(True) for t in params]
+    xr = x.double().requires_grad_(True)
+    R.window_attention(xr, *ref_leaves, 4, 4, mask=mask.double().repeat(2, 1, 1)).backward(gy.double())
+    torch.testing.assert_close(xd.grad.double().cpu(), xr.grad, rtol=1e-3, atol=1e-4)
+    for n, t, r in zip(names, params, ref_leaves):
+        torch.testing.assert_close(t.grad.double().cpu(), r.grad, rtol=1e-3, atol=2e-4, msg=lambda s_, n=n: f"{n}: {s_}")
 
 
 # ------------------------------------------------------------------------------------------------ GDN
