@@ -151,10 +151,11 @@ __device__ __forceinline__ void token_pixel(const Geom& g, int wy, int wx, int t
 
 // one warp per window: keep = (sum alpha != 0); dropped windows are copied through (the block is the identity
 // there).  NCHW copy: lane = 4 consecutive tokens (VEC-wide pieces, as in the main kernel), 8 channels in flight.
+// copy_dropped == 0: flags only (the caller has already copied x -> out wholesale).
 template <int WS, int VEC>
 __global__ void __launch_bounds__(256)
 mwa_scan_kernel(const float* __restrict__ x, const float* __restrict__ alpha, float* __restrict__ out, Geom g, int C,
-                int nwin, uint8_t* __restrict__ flags) {
+                int nwin, uint8_t* __restrict__ flags, int copy_dropped = 1) {
     constexpr int NTOK = WS * WS;
     const int win = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (win >= nwin) return;
@@ -170,7 +171,7 @@ mwa_scan_kernel(const float* __restrict__ x, const float* __restrict__ alpha, fl
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     const bool keep = a != 0.f;
     if (lane == 0) flags[win] = keep;
-    if (keep) return;
+    if (keep || !copy_dropped) return;
     const int64_t hw = int64_t(g.H) * g.W;
     if (!g.channels_last) {
         constexpr int GROUPS = NTOK / 4;                  // token groups of 4 (16 for 8x8, 4 for 4x4 windows)

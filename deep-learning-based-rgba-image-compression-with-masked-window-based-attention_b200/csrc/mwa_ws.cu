@@ -74,29 +74,16 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// L2 eviction-priority policies: x is read exactly once (evict first); the residual pre-stored into `out` must
-// survive in L2 until the epilogue's reduction reaches it two tiles later (evict last), after which the line is final.
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ float ldg_hint(const float* addr, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(addr), "l"(pol));
-    return v;
-}
 __device__ __forceinline__ void stg_hint(float* addr, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void red_add_f32(float* addr, float v, uint64_t pol) {
-    (void)pol;
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float rcp_approx(float v) {
     float r;
@@ -332,7 +319,7 @@ template <class CF, bool kTiming>
 __global__ void __launch_bounds__(kWsThreads, 1)
 mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
               const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
-              Geom geo, unsigned long long* __restrict__ timing) {
+              Geom geo, int prestore, unsigned long long* __restrict__ timing) {
     using MP = WsMap<CF>;
     constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
     constexpr int LOOK = MP::kDqBufs;                   // QKV groups issued ahead of the projection stream
@@ -416,6 +403,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         }
     };
 
+    const long long t_cta0 = (kTiming && timing != nullptr) ? clock64() : 0;
     if (warp < 4) {
         // =========================================================================================== control warps
         reg_dec<kRegsCtl>();
@@ -526,7 +514,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         static_assert(CF::NCHUNK % 2 == 0, "C must be a multiple of 16");
         constexpr int LB = 4;                               // chunks per load batch (32 loads in flight)
         uint32_t pk[CPH][4];
-        const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+        const uint64_t pol_last = l2_policy_evict_last();
         auto row_base = [&](int tile, bool& valid) -> int64_t {      // NCHW element offset of (b, c = 0, py, px)
             const int lidx = tile * CF::WPT + wslot;
             valid = lidx < count;
@@ -536,8 +524,13 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             token_pixel<WS>(geo, wy, wx, tok, py, px);
             return int64_t(b) * C * hw + int64_t(py) * geo.W + px;
         };
-        // x of one tile -> packed fp16 in registers; the fp32 values go straight to `out` (the residual: the epilogue
-        // then only ADDS the projection with a fire-and-forget reduction, no second read of x)
+        // x of one tile -> packed fp16 in registers.  The epilogue only ADDS the projection onto `out` with
+        // fire-and-forget reductions, so `out` must already hold the residual x.  Two ways (measured):
+        //   prestore = 0 (alpha given): the host side has copied x -> out wholesale before the launch, which also
+        //                settles the dropped windows; x is read exactly once here.
+        //   prestore = 1 (no alpha, every window kept): the fp32 values just loaded go straight to `out` (evict-last
+        //                in L2 so that the line is still there when the reduction arrives two tiles later); no copy
+        //                pass at all.  With dropped neighbours these half-sector stores are slow, hence the switch.
         auto load_x = [&](int tile) {
             bool valid;
             const int64_t off = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
@@ -560,7 +553,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     if (c0 + i < CPH) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (valid) stg_hint(po, v[i][j], pol_last);
+                            if (valid && prestore) stg_hint(po, v[i][j], pol_last);
                             po += hw;
                         }
 #pragma unroll
@@ -616,7 +609,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                         const int cc = (half * CPH + c0 + i) * 8;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (valid) red_add_f32(orow, __uint_as_float(acc[i][j]) + s_bproj[cc + j], pol_first);
+                            if (valid) red_add_f32(orow, __uint_as_float(acc[i][j]) + s_bproj[cc + j]);
                             orow += hw;
                         }
                     }
@@ -731,6 +724,12 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kAllocWarp) tmem_dealloc<512>(tm);
+    if constexpr (kTiming) {      // per-CTA totals: [64 + cta] cycles, [64 + 256 + cta] tiles (buffer of 1024 u64)
+        if (timing != nullptr && tid == 0) {
+            timing[64 + blockIdx.x] = static_cast<unsigned long long>(clock64() - t_cta0);
+            timing[64 + 256 + blockIdx.x] = my_tiles;
+        }
+    }
 }
 
 unsigned long long* g_ws_timing = nullptr;
@@ -751,11 +750,14 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
     int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
     const uint8_t* blk = static_cast<const uint8_t*>(params);
     const MwaParamLayout L(CF::C, CF::HEADS, CF::WS);
-    const int vec = (shift % 4 == 0 && W % 4 == 0) ? 4 : (shift % 2 == 0 && W % 2 == 0) ? 2 : 1;
+    // alpha given: out = x wholesale (the block is the identity on dropped windows; kept windows get the projection
+    // added on top), flags-only scan.  No alpha: the kernel pre-stores the residual itself.
+    const int prestore = (alpha == nullptr) ? 1 : 0;
     if (alpha != nullptr) {
-        if (vec == 4) mwa_scan_kernel<CF::WS, 4><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
-        else if (vec == 2) mwa_scan_kernel<CF::WS, 2><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
-        else mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags);
+        if (out != x)
+            MWA_TRY_CUDA(cudaMemcpyAsync(out, x, sizeof(float) * size_t(B) * CF::C * H * W, cudaMemcpyDeviceToDevice, st),
+                         "mwa_forward(residual copy)");
+        mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags, 0);
         int rc = check_launch("mwa_forward(scan)");
         if (rc != MWA_OK) return rc;
     }
@@ -769,12 +771,12 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, true><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                g_ws_timing);
+                                                                prestore, g_ws_timing);
     } else {
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, false><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                 nullptr);
+                                                                 prestore, nullptr);
     }
     rc = check_launch("mwa_forward(tcgen05 ws)");
     if (rc != MWA_OK) return rc;

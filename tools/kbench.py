@@ -117,6 +117,16 @@ def bench_attn(args, dev, flush):
                 print(f"attn C={C} h={heads} ws={ws} s={s} kept {kept}/{nwin} {name:8s} median {med:8.3f} ms best {best:8.3f} "
                       f"{flops / med / 1e9:8.1f} TFLOP/s = {flops / med / 1e9 / PEAKS['bf16_tflops'] * 100:5.2f}% tensor peak; "
                       f"{byts / med / 1e6:7.1f} GB/s = {byts / med / 1e6 / PEAKS['hbm_gbs'] * 100:5.1f}% HBM", flush=True)
+            if drop == 0.0:      # the alpha-free twin (layers/win_attention.py): every window kept, no residual copy pass
+                mu = pkg.WinBasedAttention(C, heads, ws, s)
+                mu.load_state_dict(m.state_dict())
+                mu = mu.to(dev)
+                with torch.no_grad():
+                    yu = mu(x)
+                    med, best = timeit(lambda: mu(x), args.iters, flush)
+                print(f"attn C={C} h={heads} ws={ws} s={s} unmasked twin       tcgen05  median {med:8.3f} ms best {best:8.3f} "
+                      f"{flops / med / 1e9:8.1f} TFLOP/s = {flops / med / 1e9 / PEAKS['bf16_tflops'] * 100:5.2f}% tensor peak; "
+                      f"max |unmasked - masked(alpha=1)| {(yu - res['tcgen05']).abs().max().item():.1e}", flush=True)
             base = "simt" if "simt" in res else "tc-v1"
             if base in res and "tcgen05" in res:
                 d = (res[base] - res["tcgen05"]).abs()

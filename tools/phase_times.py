@@ -24,7 +24,7 @@ with torch.no_grad():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
     plain = e0.elapsed_time(e1)
-    buf = torch.zeros(32, dtype=torch.int64, device=dev)
+    buf = torch.zeros(1024, dtype=torch.int64, device=dev)
     lib.mwa_debug_set_timing_buffer(buf.data_ptr())
     e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
     lib.mwa_debug_set_timing_buffer(None)
@@ -40,3 +40,6 @@ for role, off, names in roles:
     for i, n in enumerate(names):
         v = t[off + i]
         print(f"    {n:28s} {v:10d} cyc  {100 * v / max(tot, 1):5.1f}%  per tile {v / tiles_cta:8.0f}")
+cyc = torch.tensor(t[64:64 + 148], dtype=torch.float64); til = torch.tensor(t[320:320 + 148], dtype=torch.float64)
+print(f"  per-CTA kernel cycles: min {cyc.min():.0f} median {cyc.median():.0f} max {cyc.max():.0f}; tiles per CTA min {til.min():.0f} max {til.max():.0f}; "
+      f"cycles/tile median {(cyc / til.clamp(min=1)).median():.0f} max {(cyc / til.clamp(min=1)).max():.0f}")

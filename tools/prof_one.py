@@ -26,7 +26,13 @@ with torch.no_grad():
         m = pkg.MaskedWinBasedAttention(C, h, ws, s).to(dev)
         m.algo = algo
         x = torch.randn(16, C, H, W, device=dev)
-        a = (torch.rand(16, 1, H // ws, W // ws, device=dev) > 0.4).float().repeat_interleave(ws, 2).repeat_interleave(ws, 3)
+        if len(sys.argv) > 3 and sys.argv[3] == "blob":      # 4x4-window blobs, 50 % kept
+            a = (torch.rand(16, 1, H // ws // 4, W // ws // 4, device=dev) < 0.5).float().repeat_interleave(4 * ws, 2).repeat_interleave(4 * ws, 3)
+            a = torch.roll(a, (s, s), (2, 3))
+        elif len(sys.argv) > 3 and sys.argv[3] == "ones":
+            a = torch.ones(16, 1, H, W, device=dev)
+        else:
+            a = (torch.rand(16, 1, H // ws, W // ws, device=dev) > 0.4).float().repeat_interleave(ws, 2).repeat_interleave(ws, 3)
         for _ in range(5):
             y = m(x, a)
 torch.cuda.synchronize()
