@@ -239,7 +239,7 @@ def reference_arm(args):
     if rank != 0:
         return
     per_step_budget = 4.0
-    ips, cores, sample, n, med_t = cpu_hot_path_images_per_s(per_step_budget * max(args.steps, 1), seed0=0)
+    ips, cores, sample, n, med_t = cpu_hot_path_images_per_s(min(per_step_budget * max(args.steps, 1), 120.0), seed0=0)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": med_t * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -257,7 +257,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,12 +294,20 @@ def main():
         torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
+    sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~0.5 s before its first sample
     with torch.no_grad():
         for _ in range(args.warmup):
             for op in ops:
                 run_op(pkg, op)
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler is not None:                               # keep the GPU under load until the sampler is live
+            t_dead = time.time() + 4.0
+            while not sampler.rows and time.time() < t_dead and sampler.proc is not None:
+                for op in ops:
+                    run_op(pkg, op)
+                torch.cuda.synchronize()
+            barrier() if world == 1 else None
+        barrier()
         # ---- timed region: K steps, device time on the launching stream; per-op events feed the roofline
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(args.steps)]
         t_wall0 = time.time()

@@ -23,7 +23,7 @@
 namespace b200 {
 namespace {
 
-constexpr int kBT = 256;                            // threads per CTA
+constexpr int kBT = 1024;                           // threads per CTA (32 warps: the kernel is latency-bound)
 constexpr float kNegMaskB = -100.0f;                // layers/masked_win_attention.py:214
 
 struct BGeo {
@@ -164,7 +164,7 @@ mwa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha, con
             if (dy_tok) dy_tok[(tok0 + t) * C + c] = v;
         }
         __syncthreads();
-        gemm_rows<16>(R1, C, proj_w, C, nullptr, N, C, C, [&](int n, int o, float v) { R2[n * C + o] = v; });
+        gemm_rows<8>(R1, C, proj_w, C, nullptr, N, C, C, [&](int n, int o, float v) { R2[n * C + o] = v; });
         __syncthreads();
         // ---- xw -> R1 (+ scratch)
         for (int e = tid; e < N * C; e += kBT) {
@@ -289,7 +289,7 @@ mwa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha, con
         for (int e = tid; e < N * 3 * C; e += kBT) DQ[(e / (3 * C)) * ldq + e % (3 * C)] = dqkv_tok[tok0 * 3 * C + e];
         __syncthreads();
         // results staged in registers per work item and written straight to global (token rows are disjoint)
-        gemm_rows<16>(DQ, ldq, qkv_w, C, nullptr, N, C, 3 * C, [&](int n, int o, float v) {
+        gemm_rows<8>(DQ, ldq, qkv_w, C, nullptr, N, C, 3 * C, [&](int n, int o, float v) {
             const int64_t off = g.elem(win, b, wy, wx, n, o);
             gx[off] = g.tokens ? v : __ldg(gout + off) + v;
         });

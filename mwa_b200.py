@@ -19,6 +19,7 @@ _install = importlib.import_module(PACKAGE_NAME + ".install")
 GDN_mod = importlib.import_module(PACKAGE_NAME + ".layers.GDN")
 masked_win_attention = importlib.import_module(PACKAGE_NAME + ".layers.masked_win_attention")
 win_attention = importlib.import_module(PACKAGE_NAME + ".layers.win_attention")
+data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
 
 GDN = GDN_mod.GDN
 LowerBound = GDN_mod.LowerBound
@@ -33,6 +34,7 @@ install = _install.install
 patch_model_rounding = _install.patch_model_rounding
 uninstall = _install.uninstall
 build = build_mod.build
+GradientAllReduce = data_parallel.GradientAllReduce
 MwaB200Error = _abi.MwaB200Error
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_V1 = (_abi.ALGO_AUTO, _abi.ALGO_SIMT, _abi.ALGO_TCGEN05,
                                                           _abi.ALGO_TCGEN05_V1)
