@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi clock sampler (profiling runs)")
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
     args = ap.parse_args()
     if args.impl == "reference":
@@ -294,7 +295,7 @@ def main():
         torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
-    sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~0.5 s before its first sample
+    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None      # needs ~0.5 s to start
     with torch.no_grad():
         for _ in range(args.warmup):
             for op in ops:

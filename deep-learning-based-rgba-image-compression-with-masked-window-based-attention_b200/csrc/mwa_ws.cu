@@ -77,6 +77,24 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+// out = x wholesale -- unless every window is kept (then the main kernel pre-stores the residual itself, see load_x).
+// The decision is taken on the device from the compacted count, so the forward stays free of host synchronisation.
+__global__ void __launch_bounds__(256)
+residual_copy_kernel(const float4* __restrict__ x, float4* __restrict__ out, int64_t n4,
+                     const int32_t* __restrict__ count_p, int nwin) {
+    if (*count_p == nwin) return;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    constexpr int U = 8;
+    for (; i + (U - 1) * stride < n4; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldcs(x + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) out[i + u * stride] = v[u];
+    }
+    for (; i < n4; i += stride) out[i] = __ldcs(x + i);
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -319,7 +337,7 @@ template <class CF, bool kTiming>
 __global__ void __launch_bounds__(kWsThreads, 1)
 mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
               const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
-              Geom geo, int prestore, unsigned long long* __restrict__ timing) {
+              Geom geo, unsigned long long* __restrict__ timing) {
     using MP = WsMap<CF>;
     constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
     constexpr int LOOK = MP::kDqBufs;                   // QKV groups issued ahead of the projection stream
@@ -381,6 +399,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     const uint32_t tm = *tmem_ptr;
 
     const int count = *count_p;
+    const bool prestore = count == geo.B * geo.nwx * geo.nwy;      // every window kept: no residual copy pass ran
     const int num_tiles = (count + CF::WPT - 1) / CF::WPT;
     const int64_t hw = int64_t(geo.H) * geo.W;
     int my_tiles = 0;
@@ -526,11 +545,11 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         };
         // x of one tile -> packed fp16 in registers.  The epilogue only ADDS the projection onto `out` with
         // fire-and-forget reductions, so `out` must already hold the residual x.  Two ways (measured):
-        //   prestore = 0 (alpha given): the host side has copied x -> out wholesale before the launch, which also
+        //   some window dropped: residual_copy_kernel has copied x -> out wholesale before this kernel, which also
         //                settles the dropped windows; x is read exactly once here.
-        //   prestore = 1 (no alpha, every window kept): the fp32 values just loaded go straight to `out` (evict-last
-        //                in L2 so that the line is still there when the reduction arrives two tiles later); no copy
-        //                pass at all.  With dropped neighbours these half-sector stores are slow, hence the switch.
+        //   every window kept (prestore): the fp32 values just loaded go straight to `out` (evict-last in L2 so that
+        //                the line is still there when the reduction arrives two tiles later); no copy pass at all.
+        //                With dropped neighbours these half-sector stores are slow, hence the switch.
         auto load_x = [&](int tile) {
             bool valid;
             const int64_t off = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
@@ -750,13 +769,7 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
     int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
     const uint8_t* blk = static_cast<const uint8_t*>(params);
     const MwaParamLayout L(CF::C, CF::HEADS, CF::WS);
-    // alpha given: out = x wholesale (the block is the identity on dropped windows; kept windows get the projection
-    // added on top), flags-only scan.  No alpha: the kernel pre-stores the residual itself.
-    const int prestore = (alpha == nullptr) ? 1 : 0;
     if (alpha != nullptr) {
-        if (out != x)
-            MWA_TRY_CUDA(cudaMemcpyAsync(out, x, sizeof(float) * size_t(B) * CF::C * H * W, cudaMemcpyDeviceToDevice, st),
-                         "mwa_forward(residual copy)");
         mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags, 0);
         int rc = check_launch("mwa_forward(scan)");
         if (rc != MWA_OK) return rc;
@@ -764,6 +777,15 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
     mwa_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, count);
     int rc = check_launch("mwa_forward(compact)");
     if (rc != MWA_OK) return rc;
+    // out = x wholesale if any window was dropped (the block is the identity there; kept windows get the projection
+    // added on top); the kernel returns at once when every window is kept
+    if (alpha != nullptr && out != x) {
+        const int64_t n = int64_t(B) * CF::C * H * W;            // multiple of 4: C % 16 == 0
+        residual_copy_kernel<<<kNumSMs * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(x),
+                                                           reinterpret_cast<float4*>(out), n / 4, count, nwin);
+        rc = check_launch("mwa_forward(residual copy)");
+        if (rc != MWA_OK) return rc;
+    }
     const int smem = WsMap<CF>::oTotal;
     const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
     const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
@@ -771,12 +793,12 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, true><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                prestore, g_ws_timing);
+                                                                g_ws_timing);
     } else {
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, false><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                 prestore, nullptr);
+                                                                 nullptr);
     }
     rc = check_launch("mwa_forward(tcgen05 ws)");
     if (rc != MWA_OK) return rc;
