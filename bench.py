@@ -127,7 +127,8 @@ def run_op(pkg, op, t=None):
     return outs
 
 
-LAUNCHES_PER_STEP = 4 + 6 + (2 + 20)
+# our kernels per step: 4 attention calls x (scan, compact, residual copy, main) + 6 GDN + 22 rounding
+LAUNCHES_PER_STEP = 4 * 4 + 6 + (2 + 20)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -263,6 +264,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi clock sampler (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the informational CUDA-graph replay leg")
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
     args = ap.parse_args()
     if args.impl == "reference":
@@ -362,6 +364,49 @@ def main():
     roofline["peak_source"] = pk["source"] + " (MEASURED_PEAKS.json burst figures)" if pk["source"] == "measured" \
         else "fallback (B200_PROFILING.md)"
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command
+    # (profiles/r01_bench_top_kernels_ncu_raw_v2.csv: dram__bytes_read.sum + dram__bytes_write.sum of the three GDN
+    # shapes, x2 for IGDN), in GB per step like the algorithmic 6.34 GB behind `achieved`
+    roofs[1]["traffic"] = 2 * (1.209217 + 1.149369 + 0.302184 + 0.244376 + 0.075694 + 0.018719)
+    roofs[1]["traffic_unit"] = "GB per step (6 launches), ncu capture under profiles/"
+    if dominant is roofs[1]:
+        roofline["traffic"] = roofs[1]["traffic"]
+        roofline["traffic_unit"] = roofs[1]["traffic_unit"]
+
+    # ---- informational: the same step replayed as ONE CUDA graph (the forward has no host synchronisation, unlike the
+    #      reference's three nonzero() calls per attention block), i.e. without per-launch CPU overhead
+    graph_info = None
+    if not args.no_graph:
+        try:
+            with torch.no_grad():
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for op in ops:
+                        run_op(pkg, op)
+                torch.cuda.current_stream().wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for op in ops:
+                        run_op(pkg, op)
+                for _ in range(3):
+                    g.replay()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    g.replay()
+                e1.record()
+                barrier()
+            tg = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            graph_info = {"ms_per_step": float(tg.item()), "value": BATCH_PER_GPU * world / (float(tg.item()) * 1e-3),
+                          "unit": UNIT, "note": "whole step captured once, replayed `steps` times"}
+            del g
+        except Exception as exc:      # noqa: BLE001 -- informational leg only
+            graph_info = {"error": str(exc)[:200]}
+
     # ---- e2e: same step through the nn.Module API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -388,7 +433,7 @@ def main():
                        "attention_windows_kept": {op["name"]: f'{op["kept"]}/{op["windows"]}' for op in ops
                                                   if op["kind"] == "attn"}},
             "roofline": roofline, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks,
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks, "cuda_graph": graph_info,
             "per_op_ms": {op["name"]: ms for op, ms in zip(ops, per_op_ms)},
         }
         print(json.dumps(line), flush=True)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the bench command: launch list (durations) + one full capture of each top kernel
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-clocks"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-clocks --no-graph"
 $CMD > gpurun_out/bench_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 140 -c 90 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 $CMD > gpurun_out/bench_plain2.log 2>&1 && \
