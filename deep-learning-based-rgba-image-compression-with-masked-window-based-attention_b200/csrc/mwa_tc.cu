@@ -722,10 +722,10 @@ int launch_tc(const float* x, const float* alpha, float* out, const void* params
 }
 
 template <class CF>
-void prepare_tc(const float* qkv_w, const float* qkv_b, const float* proj_w, float scale, uint8_t* dst,
-                cudaStream_t st) {
+void prepare_tc(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, float scale,
+                uint8_t* dst, cudaStream_t st) {
     zero16_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), TcParams<CF>::total / 16);
-    mwa_tc_prepare_kernel<CF><<<148, 256, 0, st>>>(qkv_w, qkv_b, proj_w, scale, dst);
+    mwa_tc_prepare_kernel<CF><<<148, 256, 0, st>>>(qkv_w, qkv_b, proj_w, proj_b, scale, dst);
 }
 
 using Cfg192h8 = Cfg<192, 8, 8>;
@@ -751,12 +751,11 @@ void mwa_tc_set_timing_buffer(void* p) { g_timing = static_cast<unsigned long lo
 
 void mwa_tc_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b, int C,
                            int heads, int ws, float scale, uint8_t* blk, cudaStream_t st) {
-    (void)proj_b;
     const MwaParamLayout L(C, heads, ws);
     uint8_t* dst = blk + L.img_wqkv;
-    if (C == 192 && heads == 8 && ws == 8) prepare_tc<Cfg192h8>(qkv_w, qkv_b, proj_w, scale, dst, st);
-    else if (C == 192 && heads == 6 && ws == 8) prepare_tc<Cfg192h6>(qkv_w, qkv_b, proj_w, scale, dst, st);
-    else if (C == 80 && heads == 8 && ws == 4) prepare_tc<Cfg80h8>(qkv_w, qkv_b, proj_w, scale, dst, st);
+    if (C == 192 && heads == 8 && ws == 8) prepare_tc<Cfg192h8>(qkv_w, qkv_b, proj_w, proj_b, scale, dst, st);
+    else if (C == 192 && heads == 6 && ws == 8) prepare_tc<Cfg192h6>(qkv_w, qkv_b, proj_w, proj_b, scale, dst, st);
+    else if (C == 80 && heads == 8 && ws == 4) prepare_tc<Cfg80h8>(qkv_w, qkv_b, proj_w, proj_b, scale, dst, st);
 }
 
 int mwa_forward_tc(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,

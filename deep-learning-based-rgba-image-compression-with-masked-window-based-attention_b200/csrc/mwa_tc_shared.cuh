@@ -78,13 +78,18 @@ template <class CF>
 struct TcParams {
     static constexpr int64_t img = 0;                                          // NG x kGroupBytes
     static constexpr int64_t bq = img + int64_t(CF::NG) * CF::kGroupBytes;     // fp32 [NG][192] padded order
-    static constexpr int64_t total = bq + CF::NG * CF::NQKV * 4;
+    // proj.bias + Wproj * b_v: the v bias adds the same vector to every row of P V (rows of P sum to 1), so it can be
+    // folded into the projection bias; the k bias shifts every logit of a row by the same amount and drops out of the
+    // softmax altogether.  The warp-specialised kernel therefore only adds the q bias when it drains D_qkv.
+    static constexpr int64_t bpf = bq + CF::NG * CF::NQKV * 4;                  // fp32 [C]
+    static constexpr int64_t total = bpf + CF::C * 4;
 };
 
 // ------------------------------------------------------------------------------------------------ prepare
 template <class CF>
 __global__ void mwa_tc_prepare_kernel(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
-                                      const float* __restrict__ proj_w, float scale, uint8_t* __restrict__ out) {
+                                      const float* __restrict__ proj_w, const float* __restrict__ proj_b, float scale,
+                                      uint8_t* __restrict__ out) {
     constexpr int C = CF::C, D = CF::D, DPAD = CF::DPAD, HPG = CF::HPG;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     // qkv slabs: row n of group g = part (q|k|v) * NQ + head-in-group * D + c   (no padding inside the slab; rows
@@ -115,6 +120,12 @@ __global__ void mwa_tc_prepare_kernel(const float* __restrict__ qkv_w, const flo
             if (part == 0) v *= scale;
         }
         reinterpret_cast<float*>(out + TcParams<CF>::bq)[e] = v;
+    }
+    for (int o = tid; o < C; o += nth) {
+        float v = proj_b[o];
+        if (qkv_b != nullptr)
+            for (int c = 0; c < C; ++c) v = fmaf(proj_w[int64_t(o) * C + c], qkv_b[2 * C + c], v);
+        reinterpret_cast<float*>(out + TcParams<CF>::bpf)[o] = v;
     }
 }
 

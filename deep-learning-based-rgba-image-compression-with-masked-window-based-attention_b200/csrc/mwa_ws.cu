@@ -304,7 +304,7 @@ __device__ __forceinline__ void attention_task_ws(uint32_t sQ, uint32_t sK, uint
 // D_qkv columns [part * NQ + COL0, + NCOLS) of this thread's row + bias -> fp16 -> the head-padded chunks of heads
 // [H_LO, H_HI) of the destination operand buffer (pad columns written as zeros, all-pad chunks left untouched:
 // they were zeroed once at kernel start).
-template <class CF, int COL0, int NCOLS, int H_LO, int H_HI>
+template <class CF, int COL0, int NCOLS, int H_LO, int H_HI, bool kBias>
 __device__ __forceinline__ void drain_part(uint32_t taddr, const float* bias, uint32_t rowaddr, int r) {
     constexpr int D = CF::D, DPAD = CF::DPAD;
     static_assert(COL0 % 8 == 0 && NCOLS % 8 == 0 && H_LO * D >= COL0 && H_HI * D <= COL0 + NCOLS, "drain split");
@@ -317,7 +317,8 @@ __device__ __forceinline__ void drain_part(uint32_t taddr, const float* bias, ui
 #pragma unroll
         for (int cc = 0; cc < NCOLS / 8; ++cc)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) val[cc * 8 + j] = __uint_as_float(acc[cc][j]) + bias[COL0 + cc * 8 + j];
+            for (int j = 0; j < 8; ++j)
+                val[cc * 8 + j] = kBias ? __uint_as_float(acc[cc][j]) + bias[COL0 + cc * 8 + j] : __uint_as_float(acc[cc][j]);
     }
 #pragma unroll
     for (int ch = H_LO * DPAD / 8; ch < H_HI * DPAD / 8; ++ch) {
@@ -377,7 +378,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     {
         const float* bq = reinterpret_cast<const float*>(tcp + TcParams<CF>::bq);
         for (int i = tid; i < NG * CF::NQKV; i += kWsThreads) s_bqkv[i] = bq[i];
-        const float* bp = reinterpret_cast<const float*>(blk + L.bproj);
+        const float* bp = reinterpret_cast<const float*>(tcp + TcParams<CF>::bpf);      // proj.bias + Wproj * b_v
         for (int i = tid; i < C; i += kWsThreads) s_bproj[i] = bp[i];
         // operand buffers: padding columns must read as exact zeros for the whole kernel
         for (int i = tid; i < (MP::oRing - MP::oX) / 16; i += kWsThreads)
@@ -699,7 +700,8 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 mbar_wait(bars + MP::bDqFull + b, (G / MP::kDqBufs) & 1);
                 tc_fence_after_sync();
                 tick(16);                                                        // 16: wait D_qkv
-                {   // ---- drain: half 0: q (all heads) + k (first half of the heads); half 1: rest of k + v
+                {   // ---- drain: half 0: q (all heads, + bias) + k (first half of the heads); half 1: rest of k + v.
+                    //      k and v biases are not added here (TcParams<>::bpf explains why that is exact)
                     constexpr int NQ = CF::NQ, D = CF::D;
                     constexpr bool kSplitK = (HPG % 2 == 0) && ((HPG / 2) * D % 8 == 0);
                     constexpr int KLO = kSplitK ? (HPG / 2) * D : NQ;     // k columns loaded by half 0
@@ -707,12 +709,12 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     const float* bqkv = s_bqkv + g * CF::NQKV;
                     const uint32_t rowoff = (r >> 3) * 1024 + (r & 7) * 128;
                     if (half == 0) {
-                        drain_part<CF, 0, NQ, 0, HPG>(ta, bqkv, sb + MP::oQ + rowoff, r);
-                        drain_part<CF, 0, KLO, 0, HPG / 2>(ta + NQ, bqkv + NQ, sb + MP::oK + rowoff, r);
+                        drain_part<CF, 0, NQ, 0, HPG, true>(ta, bqkv, sb + MP::oQ + rowoff, r);
+                        drain_part<CF, 0, KLO, 0, HPG / 2, false>(ta + NQ, bqkv + NQ, sb + MP::oK + rowoff, r);
                     } else {
-                        drain_part<CF, kSplitK ? KLO : 0, kSplitK ? NQ - KLO : NQ, HPG / 2, HPG>(ta + NQ, bqkv + NQ,
-                                                                                                  sb + MP::oK + rowoff, r);
-                        drain_part<CF, 0, NQ, 0, HPG>(ta + 2 * NQ, bqkv + 2 * NQ, sb + MP::oV + rowoff, r);
+                        drain_part<CF, kSplitK ? KLO : 0, kSplitK ? NQ - KLO : NQ, HPG / 2, HPG, false>(
+                            ta + NQ, bqkv + NQ, sb + MP::oK + rowoff, r);
+                        drain_part<CF, 0, NQ, 0, HPG, false>(ta + 2 * NQ, bqkv + 2 * NQ, sb + MP::oV + rowoff, r);
                     }
                 }
                 tc_fence_before_sync();

@@ -35,14 +35,15 @@ struct GdnParamLayout {
 };
 
 // ---------------------------------------------------------------- masked window attention
-// size of the tcgen05 section (fp16 weight operand images per head group + padded-order qkv bias); mirrors Cfg<> /
+// size of the tcgen05 section (fp16 weight operand images per head group + padded-order qkv bias + the projection bias
+// with the v bias folded in); mirrors Cfg<> /
 // TcParams<> in mwa_tc.cu.  0 when the head geometry has no tcgen05 mapping.
 __host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
     const int d = C / heads, dpad = (d + 15) / 16 * 16;
     if (dpad > 64 || 64 % dpad != 0 || heads % (64 / dpad) != 0 || C % 16 != 0) return 0;
     const int64_t hpg = 64 / dpad, ng = heads / hpg, kb = (C + 63) / 64;
     const int64_t nqkv = (3 * hpg * d + 15) / 16 * 16;
-    return ng * (kb * nqkv * 128 + int64_t(C) * 128) + ng * nqkv * 4;
+    return ng * (kb * nqkv * 128 + int64_t(C) * 128) + ng * nqkv * 4 + int64_t(C) * 4;
 }
 
 struct MwaParamLayout {

@@ -84,7 +84,8 @@ def bench_attn(args, dev, flush):
     from oracle import golden_cases as G
     from oracle import ref_ops as R
     for (C, heads, ws, s, H, W) in ((192, 8, 8, 4, 128, 192), (192, 6, 8, 4, 128, 192), (80, 8, 4, 2, 64, 96)):
-        for drop in (0.0, 0.5):
+        # BASELINE config 4 (C=192, 6 heads): masked-out fraction 25 ... 100 %; the model configs: 0 and 50 %
+        for drop in ((0.0, 0.25, 0.5, 0.75, 1.0) if heads == 6 else (0.0, 0.5)):
             cfg = dict(C=C, heads=heads, ws=ws, shift=s, B=16, H=H, W=W, drop=drop, masked=True, seed=5)
             p = G.attention_inputs(cfg)
             if drop == 0.0:
