@@ -30,6 +30,13 @@ _SIGNATURES = {
     "gdn_backward_workspace_bytes": (c_int64, [c_int64, c_int, c_int64]),
     "gdn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),
+    "gdn_param_offset": (c_int64, [c_int, c_int]),
+    "gdn_bwd_square": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "gdn_bwd_dn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int,
+                           c_void_p]),
+    "gdn_bwd_dx": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gdn_bwd_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
     "mwa_param_bytes": (c_int64, [c_int, c_int, c_int]),
     "mwa_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                             c_void_p, c_int64, c_void_p]),
@@ -41,6 +48,9 @@ _SIGNATURES = {
                                          c_void_p]),
     "mwa_backward": (c_int, [c_void_p] * 12 + [c_int] * 8 + [c_void_p]),
     "window_attention_backward": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mwa_bwd_gather": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
+    "mwa_bwd_core": (c_int, [c_void_p] * 8 + [c_int64] + [c_int] * 7 + [c_void_p]),
+    "mwa_bwd_scatter": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "round_ste_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "quantize_offset_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         c_int, c_int64, c_void_p]),

@@ -317,6 +317,67 @@ gdn_bwd_dgamma_kernel(const float* __restrict__ x, const float* __restrict__ dn_
         }
 }
 
+// ------------------------------------------------------------------ GEMM-composed backward: elementwise stages
+// The three C x C contractions of the backward (n = gamma x^2, t = gamma^T dn, dgamma = dn (x^2)^T) are plain GEMMs over
+// the pixel dimension; the caller runs them with a library GEMM on the fp32 gamma / gamma^T of the parameter block and
+// uses these kernels for everything in between (128-bit vectorised, grid-stride, one pass each).
+__global__ void __launch_bounds__(256) gdn_bwd_square_kernel(const float4* __restrict__ x, float4* __restrict__ x2, int64_t n4) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        x2[i] = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+    }
+}
+// in: nb = gamma x^2 (without beta).  out: dn, and nb overwritten with term1 = g * n^(-/+ 1/2).  Same arithmetic as
+// gdn_bwd_tile_kernel.  Channel of flat element i: (i / hw) % C (NCHW) or i % C (NHWC).
+__global__ void __launch_bounds__(256)
+gdn_bwd_dn_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ nb,
+                  const float* __restrict__ beta, float* __restrict__ dn, int64_t n, int C, int64_t hw, int inverse,
+                  int channels_last) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int c = channels_last ? int(i % C) : int((i / hw) % C);
+        const float nn = nb[i] + __ldg(beta + c), gv = __ldg(g + i), xv = __ldg(x + i);
+        const float r = sqrtf(nn);
+        float t1, d;
+        if (inverse) { t1 = gv * r;  d = 0.5f * gv * xv / r; }
+        else         { t1 = gv / r;  d = -0.5f * gv * xv / (nn * r); }
+        nb[i] = t1;
+        dn[i] = d;
+    }
+}
+__global__ void __launch_bounds__(256)
+gdn_bwd_dx_kernel(const float4* __restrict__ term1, const float4* __restrict__ x, const float4* __restrict__ t,
+                  float4* __restrict__ dx, int64_t n4) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 a = __ldg(term1 + i), b = __ldg(x + i), c = __ldg(t + i);
+        dx[i] = make_float4(fmaf(2.f * b.x, c.x, a.x), fmaf(2.f * b.y, c.y, a.y), fmaf(2.f * b.z, c.z, a.z),
+                            fmaf(2.f * b.w, c.w, a.w));
+    }
+}
+// dbeta[c] = sum over images and pixels of dn.  NCHW: one warp per (image, channel) row; NHWC: block-strided columns.
+__global__ void __launch_bounds__(256)
+gdn_bwd_dbeta_kernel(const float* __restrict__ dn, float* __restrict__ dbeta, int64_t n_img, int C, int64_t hw,
+                     int channels_last) {
+    const int lane = threadIdx.x & 31;
+    if (!channels_last) {
+        const int64_t rows = n_img * C;
+        for (int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += int64_t(gridDim.x) * 8) {
+            const float* p = dn + row * hw;
+            float a = 0.f;
+            for (int64_t i = lane; i < hw; i += 32) a += __ldg(p + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) atomicAdd(dbeta + row % C, a);
+        }
+    } else {
+        const int64_t px = n_img * hw;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float a = 0.f;
+            for (int64_t p = blockIdx.x; p < px; p += gridDim.x) a += __ldg(dn + p * C + c);
+            atomicAdd(dbeta + c, a);
+        }
+    }
+}
+
 // LowerBound backward (layers/GDN.py:17-23): pass where param >= bound or the incoming gradient is negative
 __global__ void gdn_bwd_finalize_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
                                         const float* __restrict__ dbeta_eff, const float* __restrict__ dgamma_eff,
@@ -450,6 +511,60 @@ int gdn_backward(const float* x, const float* grad_y, const float* beta_p, const
     gdn_bwd_finalize_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(beta_p, gamma_p, dbeta, dgamma, grad_beta_p,
                                                                  grad_gamma_p, C, beta_bound, gamma_bound);
     return check_launch("gdn_backward(finalize)");
+}
+
+int64_t gdn_param_offset(int C, int which) {
+    if (C <= 0 || which < 0 || which > 2) return MWA_ERR_INVALID;
+    const GdnParamLayout L(C);
+    return which == 0 ? L.beta : which == 1 ? L.gamma : L.gammaT;
+}
+
+int gdn_bwd_square(const float* x, float* x2, int64_t n, void* stream) {
+    if (!x || !x2 || n < 0 || n % 4 != 0) return MWA_ERR_INVALID;
+    if (!aligned16(x) || !aligned16(x2)) return MWA_ERR_ALIGNMENT;
+    if (n == 0) return MWA_OK;
+    gdn_bwd_square_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(x2), n / 4);
+    return check_launch("gdn_bwd_square");
+}
+
+int gdn_bwd_dn(const float* grad_y, const float* x, float* n_to_term1, const void* params, float* dn, int64_t n_img,
+               int C, int64_t hw, int inverse, int channels_last, void* stream) {
+    if (!grad_y || !x || !n_to_term1 || !params || !dn || n_img < 0 || C <= 0 || hw < 0) return MWA_ERR_INVALID;
+    const int64_t n = n_img * C * hw;
+    if (n == 0) return MWA_OK;
+    const GdnParamLayout L(C);
+    const float* beta = reinterpret_cast<const float*>(static_cast<const uint8_t*>(params) + L.beta);
+    gdn_bwd_dn_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_y, x, n_to_term1, beta, dn, n, C,
+                                                                                 hw, inverse, channels_last);
+    return check_launch("gdn_bwd_dn");
+}
+
+int gdn_bwd_dx(const float* term1, const float* x, const float* t, float* grad_x, int64_t n, void* stream) {
+    if (!term1 || !x || !t || !grad_x || n < 0 || n % 4 != 0) return MWA_ERR_INVALID;
+    if (!aligned16(term1) || !aligned16(x) || !aligned16(t) || !aligned16(grad_x)) return MWA_ERR_ALIGNMENT;
+    if (n == 0) return MWA_OK;
+    gdn_bwd_dx_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(term1), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(t),
+        reinterpret_cast<float4*>(grad_x), n / 4);
+    return check_launch("gdn_bwd_dx");
+}
+
+int gdn_bwd_finalize(const float* dn, const float* dgamma_eff, const float* beta_p, const float* gamma_p,
+                     float beta_bound, float gamma_bound, float* grad_beta_p, float* grad_gamma_p, float* dbeta_scratch,
+                     int64_t n_img, int C, int64_t hw, int channels_last, void* stream) {
+    if (!dn || !dgamma_eff || !beta_p || !gamma_p || !grad_beta_p || !grad_gamma_p || !dbeta_scratch) return MWA_ERR_INVALID;
+    if (n_img < 0 || C <= 0 || hw < 0) return MWA_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MWA_TRY_CUDA(cudaMemsetAsync(dbeta_scratch, 0, sizeof(float) * C, st), "gdn_bwd_finalize(memset)");
+    if (n_img > 0 && hw > 0) {
+        gdn_bwd_dbeta_kernel<<<kNumSMs * 4, 256, 0, st>>>(dn, dbeta_scratch, n_img, C, hw, channels_last);
+        int rc = check_launch("gdn_bwd_finalize(dbeta)");
+        if (rc != MWA_OK) return rc;
+    }
+    gdn_bwd_finalize_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(beta_p, gamma_p, dbeta_scratch, dgamma_eff, grad_beta_p,
+                                                                 grad_gamma_p, C, beta_bound, gamma_bound);
+    return check_launch("gdn_bwd_finalize");
 }
 
 }  // extern "C"

@@ -123,7 +123,6 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
         const int cg = warp >> 2;             // 16-channel group inside every 64-channel chunk
         const int p = q * 32 + lane;          // pixel within the tile == TMEM lane == A row
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        mbar_wait(bar_gamma, 0);              // beta in smem (also orders the first MMA after the gamma copy)
 
         float xr[kChunks * 16];               // this thread's 48 values of the tile being converted
         const int64_t chunk_stride = int64_t(kChunkK) * hw;
@@ -178,8 +177,10 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
             }
         };
 
+        // first tile's HBM loads go out BEFORE waiting for the 147 KB parameter copy: the two latencies overlap
         if (int64_t(blockIdx.x) < num_tiles) load_tile(blockIdx.x);
         prefetch_tile(int64_t(blockIdx.x) + gridDim.x);
+        mbar_wait(bar_gamma, 0);              // beta in smem (also orders the first MMA after the gamma copy)
 
         uint32_t g = 0, it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {

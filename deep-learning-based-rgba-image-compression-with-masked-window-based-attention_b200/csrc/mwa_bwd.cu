@@ -301,6 +301,209 @@ mwa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha, con
     }
 }
 
+
+// ================================================================================================================
+// GEMM-composed backward: the three token GEMMs of the backward (qkv = xw Wqkv^T + b, dAO = dy Wproj, dXw = dqkv Wqkv)
+// are plain GEMMs over ALL tokens and run in a library GEMM on the caller's side; these kernels do the rest:
+//   mwa_bwd_gather_kernel   x, grad_out (image layout) -> xw_tok, dy_tok (token-major, zeros for dropped windows), flags
+//   mwa_bwd_core_kernel     per window and head, from qkv_tok and dao_tok: P, AO (-> ao_tok), dS, dq / dk / dv
+//                           (-> dqkv_tok) and the relative-position table gradient
+//   mwa_bwd_scatter_kernel  grad_x = grad_out + dxw_tok at the un-shifted pixel (dropped windows carry zeros)
+// ================================================================================================================
+__global__ void __launch_bounds__(256)
+mwa_bwd_gather_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ gout,
+                      float* __restrict__ xw_tok, float* __restrict__ dy_tok, uint8_t* __restrict__ flags, BGeo g,
+                      int nwin) {
+    __shared__ float red[8];
+    __shared__ int keep_s;
+    const int C = g.C, N = g.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+        const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+        bool keep = true;
+        if (alpha != nullptr) {
+            float a = 0.f;
+            for (int t = tid; t < N; t += 256) {
+                int y, xx;
+                g.token_pixel(wy, wx, t, y, xx);
+                a += __ldg(alpha + (int64_t(b) * g.H + y) * g.W + xx);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int i = 0; i < 8; ++i) tot += red[i];
+                keep_s = (tot != 0.f);
+            }
+            __syncthreads();
+            keep = keep_s != 0;
+            __syncthreads();
+        }
+        if (tid == 0) flags[win] = keep;
+        const int64_t tok0 = int64_t(win) * N;
+        for (int e = tid; e < N * C; e += 256) {
+            // NCHW: pixel-fastest iteration coalesces the reads; NHWC: channel-fastest coalesces both sides
+            const int c = g.channels_last ? e % C : e / N, t = g.channels_last ? e / C : e % N;
+            float xv = 0.f, gv = 0.f;
+            if (keep) {
+                const int64_t off = g.elem(win, b, wy, wx, t, c);
+                xv = __ldg(x + off);
+                gv = __ldg(gout + off);
+            }
+            xw_tok[(tok0 + t) * C + c] = xv;
+            dy_tok[(tok0 + t) * C + c] = gv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mwa_bwd_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ dxw_tok, float* __restrict__ gx, BGeo g,
+                       int nwin) {
+    const int C = g.C, N = g.N, tid = threadIdx.x;
+    for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+        const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+        const int64_t tok0 = int64_t(win) * N;
+        for (int e = tid; e < N * C; e += 256) {
+            const int c = g.channels_last ? e % C : e / N, t = g.channels_last ? e / C : e % N;
+            const int64_t off = g.elem(win, b, wy, wx, t, c);
+            gx[off] = __ldg(gout + off) + dxw_tok[(tok0 + t) * C + c];
+        }
+    }
+}
+
+// shared memory (floats): R3 [N][3d+1] q' k v | R2 [N][d+1] dAO_h | R4, R5 [N][N+1] | R6 [N][3d+1] | tacc [heads][TBL]
+__host__ __device__ inline int64_t bwd_core_smem_floats(int C, int heads, int ws) {
+    const int64_t N = ws * ws, d = C / heads, tbl = (2 * ws - 1) * (2 * ws - 1);
+    return 2 * N * (3 * d + 1) + N * (d + 1) + 2 * N * (N + 1) + heads * tbl + 8;
+}
+
+__global__ void __launch_bounds__(256)
+mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__ dao_tok, const uint8_t* __restrict__ blk,
+                    const float* __restrict__ ext_mask, const uint8_t* __restrict__ flags, float* __restrict__ ao_tok,
+                    float* __restrict__ dqkv_tok, float* __restrict__ gtable, BGeo g, int heads, int nwin) {
+    extern __shared__ float smem[];
+    constexpr int kT = 256;
+    const int C = g.C, N = g.N, ws = g.ws, d = C / heads;
+    const int ldh = 3 * d + 1, ld2 = d + 1, lds = N + 1, TBL = (2 * ws - 1) * (2 * ws - 1);
+    float* R3 = smem;
+    float* R2 = R3 + N * ldh;
+    float* R4 = R2 + N * ld2;
+    float* R5 = R4 + N * lds;
+    float* R6 = R5 + N * lds;
+    float* tacc = R6 + N * ldh;
+    const MwaParamLayout L(C, heads, ws);
+    const float scale = reinterpret_cast<const float*>(blk + L.header)[0];
+    const float* bias = reinterpret_cast<const float*>(blk + L.bias);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < heads * TBL; i += kT) tacc[i] = 0.f;
+    __syncthreads();
+    for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+        const int wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+        const int64_t tok0 = int64_t(win) * N;
+        if (flags != nullptr && !flags[win]) {
+            for (int e = tid; e < N * C; e += kT) ao_tok[tok0 * C + e] = 0.f;
+            for (int e = tid; e < N * 3 * C; e += kT) dqkv_tok[tok0 * 3 * C + e] = 0.f;
+            continue;
+        }
+        for (int h = 0; h < heads; ++h) {
+            for (int e = tid; e < N * 3 * d; e += kT) {
+                const int n = e / (3 * d), j = e % (3 * d);
+                const float v = __ldg(qkv_tok + (tok0 + n) * 3 * C + (j / d) * C + h * d + (j % d));
+                R3[n * ldh + j] = (j < d) ? v * scale : v;
+            }
+            for (int e = tid; e < N * d; e += kT) R2[(e / d) * ld2 + e % d] = __ldg(dao_tok + (tok0 + e / d) * C + h * d + e % d);
+            __syncthreads();
+            const float* bh = bias + int64_t(h) * N * N;
+            for (int e = tid; e < N * N; e += kT) {
+                const int i = e / N, j = e % N;
+                const float* q = R3 + i * ldh;
+                const float* k = R3 + j * ldh + d;
+                float acc = 0.f;
+                for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
+                acc += __ldg(bh + e);
+                if (g.tokens) {
+                    if (g.mask_nw > 0) acc += __ldg(ext_mask + (int64_t(win % g.mask_nw) * N + i) * N + j);
+                } else if (g.shift > 0 && g.region(wy, wx, i) != g.region(wy, wx, j)) {
+                    acc += kNegMaskB;
+                }
+                R4[i * lds + j] = acc;
+            }
+            __syncthreads();
+            for (int i = warp; i < N; i += kT / 32) {
+                float* row = R4 + i * lds;
+                float m = -INFINITY;
+                for (int j = lane; j < N; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int j = lane; j < N; j += 32) {
+                    const float e = expf(row[j] - m);
+                    row[j] = e;
+                    sum += e;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float inv = 1.f / sum;
+                for (int j = lane; j < N; j += 32) row[j] *= inv;
+            }
+            __syncthreads();
+            for (int e = tid; e < N * d; e += kT) {
+                const int i = e / d, c = e % d;
+                const float* p = R4 + i * lds;
+                float acc = 0.f;
+                for (int j = 0; j < N; ++j) acc = fmaf(p[j], R3[j * ldh + 2 * d + c], acc);
+                ao_tok[(tok0 + i) * C + h * d + c] = acc;
+                float dv = 0.f;
+                for (int n = 0; n < N; ++n) dv = fmaf(R4[n * lds + i], R2[n * ld2 + c], dv);
+                R6[i * ldh + 2 * d + c] = dv;
+            }
+            for (int e = tid; e < N * N; e += kT) {
+                const int i = e / N, j = e % N;
+                const float* da = R2 + i * ld2;
+                const float* v = R3 + j * ldh + 2 * d;
+                float acc = 0.f;
+                for (int c = 0; c < d; ++c) acc = fmaf(da[c], v[c], acc);
+                R5[i * lds + j] = acc;
+            }
+            __syncthreads();
+            for (int i = warp; i < N; i += kT / 32) {
+                float dot = 0.f;
+                for (int j = lane; j < N; j += 32) dot = fmaf(R5[i * lds + j], R4[i * lds + j], dot);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                for (int j = lane; j < N; j += 32) R5[i * lds + j] = R4[i * lds + j] * (R5[i * lds + j] - dot);
+            }
+            __syncthreads();
+            for (int e = tid; e < N * d; e += kT) {
+                const int i = e / d, c = e % d;
+                float dq = 0.f, dk = 0.f;
+                for (int j = 0; j < N; ++j) {
+                    dq = fmaf(R5[i * lds + j], R3[j * ldh + d + c], dq);
+                    dk = fmaf(R5[j * lds + i], R3[j * ldh + c], dk);
+                }
+                R6[i * ldh + c] = dq * scale;
+                R6[i * ldh + d + c] = dk;
+            }
+            for (int idx = tid; idx < TBL; idx += kT) {
+                const int dy = idx / (2 * ws - 1) - (ws - 1), dx = idx % (2 * ws - 1) - (ws - 1);
+                float acc = 0.f;
+                for (int yj = max(0, -dy); yj < min(ws, ws - dy); ++yj)
+                    for (int xj = max(0, -dx); xj < min(ws, ws - dx); ++xj)
+                        acc += R5[((yj + dy) * ws + xj + dx) * lds + yj * ws + xj];
+                tacc[h * TBL + idx] += acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < N * 3 * d; e += kT) {
+                const int n = e / (3 * d), j = e % (3 * d);
+                dqkv_tok[(tok0 + n) * 3 * C + (j / d) * C + h * d + (j % d)] = R6[n * ldh + j];
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < heads * TBL; i += kT) atomicAdd(gtable + (i % TBL) * heads + i / TBL, tacc[i]);
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -353,6 +556,61 @@ int window_attention_backward(const float* xw, const float* mask, const float* g
     // token mode: xw / grad_out already ARE the token-major tensors the caller's GEMMs need -> no copies of them
     return launch_bwd(xw, nullptr, grad_out, qkv_w, proj_w, params, mask, grad_xw, grad_table, /*xw_tok=*/nullptr,
                       ao_tok, /*dy_tok=*/nullptr, dqkv_tok, g, heads, K, static_cast<cudaStream_t>(stream));
+}
+
+int mwa_bwd_gather(const float* x, const float* alpha, const float* grad_out, float* xw_tok, float* dy_tok,
+                   uint8_t* keep_flags, int B, int C, int H, int W, int ws, int shift, int channels_last, void* stream) {
+    if (!x || !grad_out || !xw_tok || !dy_tok || !keep_flags) return MWA_ERR_INVALID;
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || ws <= 0 || shift < 0 || shift >= ws || H % ws || W % ws) return MWA_ERR_INVALID;
+    BGeo g{B, C, H, W, ws, shift, W / ws, H / ws, ws * ws, channels_last, 0, 0};
+    const int64_t nwin = int64_t(B) * g.nwx * g.nwy;
+    if (nwin > 0x7fffffffll) return MWA_ERR_UNSUPPORTED;
+    if (nwin == 0) return MWA_OK;
+    const int grid = static_cast<int>(nwin < kNumSMs * 8 ? nwin : kNumSMs * 8);
+    mwa_bwd_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, alpha, grad_out, xw_tok, dy_tok,
+                                                                               keep_flags, g, static_cast<int>(nwin));
+    return check_launch("mwa_bwd_gather");
+}
+
+int mwa_bwd_core(const float* qkv_tok, const float* dao_tok, const void* params, const float* mask,
+                 const uint8_t* keep_flags, float* ao_tok, float* dqkv_tok, float* grad_table, int64_t nwin, int C,
+                 int H, int W, int heads, int ws, int shift, int mask_windows, void* stream) {
+    if (!qkv_tok || !dao_tok || !params || !ao_tok || !dqkv_tok || !grad_table) return MWA_ERR_INVALID;
+    if (nwin < 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0 || mask_windows < 0) return MWA_ERR_INVALID;
+    if (nwin > 0x7fffffffll) return MWA_ERR_UNSUPPORTED;
+    const bool tokens = H <= 0;                                   // token mode: no image geometry, optional mask
+    if (tokens && mask_windows > 0 && (!mask || nwin % mask_windows != 0)) return MWA_ERR_INVALID;
+    if (!tokens && (W <= 0 || shift < 0 || shift >= ws || H % ws || W % ws)) return MWA_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int TBL = (2 * ws - 1) * (2 * ws - 1);
+    MWA_TRY_CUDA(cudaMemsetAsync(grad_table, 0, sizeof(float) * TBL * heads, st), "mwa_bwd_core(memset)");
+    if (nwin == 0) return MWA_OK;
+    BGeo g = tokens ? BGeo{static_cast<int>(nwin), C, ws, ws, ws, 0, 1, 1, ws * ws, 1, 1, mask_windows}
+                    : BGeo{0, C, H, W, ws, shift, W / ws, H / ws, ws * ws, 0, 0, 0};
+    const int64_t smem = 4 * bwd_core_smem_floats(C, heads, ws);
+    if (g.N > 64 || smem > 227 * 1024 - 64) return MWA_ERR_UNSUPPORTED;
+    MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_bwd_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                 "mwa_bwd_core(attr)");
+    const int per_sm = smem > 0 ? static_cast<int>((220 * 1024) / smem) : 1;
+    const int64_t cap = int64_t(kNumSMs) * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
+    const int grid = static_cast<int>(nwin < cap ? nwin : cap);
+    mwa_bwd_core_kernel<<<grid, 256, smem, st>>>(qkv_tok, dao_tok, static_cast<const uint8_t*>(params), mask, keep_flags,
+                                                 ao_tok, dqkv_tok, grad_table, g, heads, static_cast<int>(nwin));
+    return check_launch("mwa_bwd_core");
+}
+
+int mwa_bwd_scatter(const float* grad_out, const float* dxw_tok, float* grad_x, int B, int C, int H, int W, int ws,
+                    int shift, int channels_last, void* stream) {
+    if (!grad_out || !dxw_tok || !grad_x) return MWA_ERR_INVALID;
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || ws <= 0 || shift < 0 || shift >= ws || H % ws || W % ws) return MWA_ERR_INVALID;
+    BGeo g{B, C, H, W, ws, shift, W / ws, H / ws, ws * ws, channels_last, 0, 0};
+    const int64_t nwin = int64_t(B) * g.nwx * g.nwy;
+    if (nwin > 0x7fffffffll) return MWA_ERR_UNSUPPORTED;
+    if (nwin == 0) return MWA_OK;
+    const int grid = static_cast<int>(nwin < kNumSMs * 8 ? nwin : kNumSMs * 8);
+    mwa_bwd_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, dxw_tok, grad_x, g,
+                                                                                static_cast<int>(nwin));
+    return check_launch("mwa_bwd_scatter");
 }
 
 }  // extern "C"

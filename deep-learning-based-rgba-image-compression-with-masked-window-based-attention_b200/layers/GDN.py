@@ -38,6 +38,52 @@ class LowerBound(Function):
         return keep.type(grad_output.dtype) * grad_output, None
 
 
+def _composed_backward(lib, x, grad_y, beta, gamma, blk, mod, channels_last, gx, gb, gg):
+    """GDN backward as hand-written elementwise stages around three plain GEMMs over the pixel dimension
+    (n = gamma x^2, t = gamma^T dn, dgamma = dn (x^2)^T; include/mwa_b200.h, "GEMM-composed GDN backward").
+    The GEMMs run on the fp32 effective gamma / gamma^T stored in the parameter block."""
+    B, C = x.shape[0], x.shape[1]
+    hw = x.shape[2] * x.shape[3]
+    st = _abi.stream_handle()
+
+    def mat(which):
+        off = int(lib.gdn_param_offset(C, which))
+        return blk[off:off + 4 * C * C].view(torch.float32).view(C, C)
+
+    g_eff, gT_eff = mat(1), mat(2)                       # gamma[i][j], gamma^T[j][i]
+
+    def tok(t):      # (B, C, H, W) tensor -> GEMM view: NCHW (B, C, HW); NHWC (B*HW, C)
+        return t.permute(0, 2, 3, 1).reshape(B * hw, C) if channels_last else t.view(B, C, hw)
+
+    x2 = torch.empty_like(x)
+    _abi.check(lib.gdn_bwd_square(x.data_ptr(), x2.data_ptr(), x.numel(), st), "gdn_bwd_square")
+    nb = torch.empty_like(x)
+    if channels_last:
+        torch.matmul(tok(x2), gT_eff, out=tok(nb))       # n_i = sum_j x2_j gamma[i][j]
+    else:
+        torch.matmul(g_eff, tok(x2), out=tok(nb))
+    dn = torch.empty_like(x)
+    _abi.check(lib.gdn_bwd_dn(grad_y.data_ptr(), x.data_ptr(), nb.data_ptr(), blk.data_ptr(), dn.data_ptr(), B, C, hw,
+                              int(mod.inverse), int(channels_last), st), "gdn_bwd_dn")
+    t = torch.empty_like(x)
+    if channels_last:
+        torch.matmul(tok(dn), g_eff, out=tok(t))         # t_j = sum_i dn_i gamma[i][j]
+    else:
+        torch.matmul(gT_eff, tok(dn), out=tok(t))
+    _abi.check(lib.gdn_bwd_dx(nb.data_ptr(), x.data_ptr(), t.data_ptr(), gx.data_ptr(), x.numel(), st), "gdn_bwd_dx")
+    if channels_last:
+        dg = tok(dn).t() @ tok(x2)                       # (C, BHW) x (BHW, C)
+    else:
+        dg = torch.zeros(C, C, device=x.device)
+        dnv, x2v = tok(dn), tok(x2)
+        for b in range(B):                               # accumulating GEMMs: no reduction kernel
+            dg.addmm_(dnv[b], x2v[b].t())
+    scratch = torch.empty(C, device=x.device)
+    _abi.check(lib.gdn_bwd_finalize(dn.data_ptr(), dg.data_ptr(), beta.data_ptr(), gamma.data_ptr(), mod.beta_bound,
+                                    mod.gamma_bound, gb.data_ptr(), gg.data_ptr(), scratch.data_ptr(), B, C, hw,
+                                    int(channels_last), st), "gdn_bwd_finalize")
+
+
 class _GDNFunction(Function):
     @staticmethod
     def forward(ctx, x, beta, gamma, mod):
@@ -77,6 +123,9 @@ class _GDNFunction(Function):
             gx = torch.empty_like(x)
             gb = torch.empty_like(beta)
             gg = torch.empty_like(gamma)
+            if mod.algo != _abi.ALGO_SIMT and x.numel() % 4 == 0 and x.numel() > 0:
+                _composed_backward(lib, x, grad_y, beta, gamma, blk, mod, ctx.channels_last, gx, gb, gg)
+                return gx, gb, gg, None
             ws_bytes = lib.gdn_backward_workspace_bytes(B, C, hw)
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
             _abi.check(lib.gdn_backward(x.data_ptr(), grad_y.data_ptr(), beta.data_ptr(), gamma.data_ptr(),

@@ -5,7 +5,10 @@ Backward (training, BASELINE config 5) = the hand-written `mwa_backward` / `wind
 kernels (fp32; they re-compute q, k, v and the softmax per head, emit grad_x and the relative-position
 table gradient, and leave four token-major scratch tensors), followed by the weight / bias gradients
 as plain GEMMs and column sums over all tokens (library GEMM: `dWqkv = dqkv^T xw`, `dWproj = dy^T ao`).
-`_differentiable_block` is a torch re-statement kept ONLY as a cross-check for the tests.
+With `algo = ALGO_SIMT` one all-in-one kernel does the token GEMMs too; otherwise (default) the three token GEMMs
+(qkv recompute, dAO = dy Wproj, dXw = dqkv Wqkv) run in the library GEMM as well and hand-written gather / per-window
+core / scatter kernels do the rest (3.5x faster).  `_differentiable_block` is a torch re-statement kept ONLY as a
+cross-check for the tests.
 """
 from __future__ import annotations
 
@@ -96,6 +99,7 @@ class WindowAttentionFunction(Function):
                                        attn_mod.num_heads, ws, shift, int(channels_last), algo, None,
                                        wsp.data_ptr(), wsp.numel(), _abi.stream_handle()), "mwa_forward")
         ctx.cfg = (attn_mod, ws, shift)
+        ctx.algo = algo
         ctx.has_bias = qkv_b is not None
         ctx.save_for_backward(x, alpha, qkv_w, qkv_b, proj_w, proj_b, table)
         return out
@@ -117,11 +121,27 @@ class WindowAttentionFunction(Function):
             xw, ao, dy = (torch.empty(nwin * N, C, device=x.device) for _ in range(3))
             dqkv = torch.empty(nwin * N, 3 * C, device=x.device)
             qw, pw = qkv_w.contiguous(), proj_w.contiguous()
-            _abi.check(lib.mwa_backward(x.data_ptr(), _abi.ptr(alpha), grad_out.data_ptr(), qw.data_ptr(),
-                                        pw.data_ptr(), blk.data_ptr(), gx.data_ptr(), gtab.data_ptr(), xw.data_ptr(),
-                                        ao.data_ptr(), dy.data_ptr(), dqkv.data_ptr(), B, C, H, W,
-                                        attn_mod.num_heads, ws, shift, int(channels_last), _abi.stream_handle()),
-                       "mwa_backward")
+            st = _abi.stream_handle()
+            if ctx.algo == _abi.ALGO_SIMT:
+                # everything in one hand-written kernel (token GEMMs included)
+                _abi.check(lib.mwa_backward(x.data_ptr(), _abi.ptr(alpha), grad_out.data_ptr(), qw.data_ptr(),
+                                            pw.data_ptr(), blk.data_ptr(), gx.data_ptr(), gtab.data_ptr(),
+                                            xw.data_ptr(), ao.data_ptr(), dy.data_ptr(), dqkv.data_ptr(), B, C, H, W,
+                                            attn_mod.num_heads, ws, shift, int(channels_last), st), "mwa_backward")
+            else:
+                # gather -> token GEMMs (library) -> per-window core kernel -> token GEMM -> scatter
+                flags = torch.empty(max(nwin, 1), dtype=torch.uint8, device=x.device)
+                _abi.check(lib.mwa_bwd_gather(x.data_ptr(), _abi.ptr(alpha), grad_out.data_ptr(), xw.data_ptr(),
+                                              dy.data_ptr(), flags.data_ptr(), B, C, H, W, ws, shift,
+                                              int(channels_last), st), "mwa_bwd_gather")
+                qkv = torch.addmm(qkv_b, xw, qw.t()) if qkv_b is not None else xw @ qw.t()
+                dao = dy @ pw
+                _abi.check(lib.mwa_bwd_core(qkv.data_ptr(), dao.data_ptr(), blk.data_ptr(), None, flags.data_ptr(),
+                                            ao.data_ptr(), dqkv.data_ptr(), gtab.data_ptr(), nwin, C, H, W,
+                                            attn_mod.num_heads, ws, shift, 0, st), "mwa_bwd_core")
+                dxw = dqkv @ qw
+                _abi.check(lib.mwa_bwd_scatter(grad_out.data_ptr(), dxw.data_ptr(), gx.data_ptr(), B, C, H, W, ws,
+                                               shift, int(channels_last), st), "mwa_bwd_scatter")
             need = ctx.needs_input_grad
             gw1 = dqkv.t() @ xw if need[2] else None
             gb1 = dqkv.sum(0) if (need[3] and ctx.has_bias) else None
@@ -179,12 +199,21 @@ class TokenAttentionFunction(Function):
             ao = torch.empty(K * N, C, device=xw.device)
             dqkv = torch.empty(K * N, 3 * C, device=xw.device)
             qw, pw = qkv_w.contiguous(), proj_w.contiguous()
-            _abi.check(lib.window_attention_backward(xw.data_ptr(), _abi.ptr(mask), grad_out.data_ptr(), qw.data_ptr(),
-                                                     pw.data_ptr(), blk.data_ptr(), gx.data_ptr(), gtab.data_ptr(),
-                                                     ao.data_ptr(), dqkv.data_ptr(), K, C, m.num_heads, ws, nw,
-                                                     _abi.stream_handle()), "window_attention_backward")
-            need = ctx.needs_input_grad
             xf, dyf = xw.reshape(K * N, C), grad_out.reshape(K * N, C)
+            if getattr(m, "algo", _abi.ALGO_AUTO) == _abi.ALGO_SIMT:
+                _abi.check(lib.window_attention_backward(xw.data_ptr(), _abi.ptr(mask), grad_out.data_ptr(),
+                                                         qw.data_ptr(), pw.data_ptr(), blk.data_ptr(), gx.data_ptr(),
+                                                         gtab.data_ptr(), ao.data_ptr(), dqkv.data_ptr(), K, C,
+                                                         m.num_heads, ws, nw, _abi.stream_handle()),
+                           "window_attention_backward")
+            else:
+                qkv = torch.addmm(qkv_b, xf, qw.t()) if qkv_b is not None else xf @ qw.t()
+                dao = dyf @ pw
+                _abi.check(lib.mwa_bwd_core(qkv.data_ptr(), dao.data_ptr(), blk.data_ptr(), _abi.ptr(mask), None,
+                                            ao.data_ptr(), dqkv.data_ptr(), gtab.data_ptr(), K, C, 0, 0, m.num_heads,
+                                            ws, 0, nw, _abi.stream_handle()), "mwa_bwd_core")
+                torch.matmul(dqkv, qw, out=gx.view(K * N, C))
+            need = ctx.needs_input_grad
             gw1 = dqkv.t() @ xf if need[2] else None
             gb1 = dqkv.sum(0) if (need[3] and qkv_b is not None) else None
             gw2 = dyf.t() @ ao if need[4] else None

@@ -72,6 +72,28 @@ MWA_API int gdn_backward(const float* x, const float* grad_y, const float* beta_
                  float* grad_gamma_p, void* workspace, int64_t workspace_bytes, int64_t n_img, int C, int64_t hw,
                  int inverse, int channels_last, void* stream);
 
+/* GEMM-composed GDN backward (what the Python layer uses for C == 192 when algo != SIMT): the three C x C contractions
+ * are plain GEMMs over the pixel dimension, run by the caller with a library GEMM on the fp32 effective gamma / gamma^T
+ * inside the parameter block (byte offsets from gdn_param_offset: which = 0 beta, 1 gamma [i][j], 2 gamma^T [j][i]);
+ * these entry points are the hand-written stages in between, one pass over the tensors each:
+ *   gdn_bwd_square   x2 = x * x
+ *   (GEMM)           nb = gamma . x2          per pixel, without beta
+ *   gdn_bwd_dn       n = nb + beta; dn = d loss / d n; nb is overwritten with term1 = grad_y * n^(-/+ 1/2)
+ *   (GEMM)           t  = gamma^T . dn
+ *   gdn_bwd_dx       grad_x = term1 + 2 x t
+ *   (GEMM)           dgamma_eff = sum over pixels of dn (x2)^T
+ *   gdn_bwd_finalize dbeta_eff = sum dn (dbeta_scratch: C floats), then the LowerBound / reparametrisation chain rule
+ *                    (layers/GDN.py:17-23, :74-80) -> grad_beta_p, grad_gamma_p
+ * Same arithmetic as gdn_backward; n = n_img * C * hw elements (multiple of 4 for the vectorised stages). */
+MWA_API int64_t gdn_param_offset(int C, int which);
+MWA_API int gdn_bwd_square(const float* x, float* x2, int64_t n, void* stream);
+MWA_API int gdn_bwd_dn(const float* grad_y, const float* x, float* n_to_term1, const void* params, float* dn,
+                       int64_t n_img, int C, int64_t hw, int inverse, int channels_last, void* stream);
+MWA_API int gdn_bwd_dx(const float* term1, const float* x, const float* t, float* grad_x, int64_t n, void* stream);
+MWA_API int gdn_bwd_finalize(const float* dn, const float* dgamma_eff, const float* beta_p, const float* gamma_p,
+                             float beta_bound, float gamma_bound, float* grad_beta_p, float* grad_gamma_p,
+                             float* dbeta_scratch, int64_t n_img, int C, int64_t hw, int channels_last, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Masked window attention   replaces  layers/masked_win_attention.py:169-251 (WinBasedAttention.forward,
  *   with its helpers window_partition :6-18, window_reverse :20-33, remove_zero_windows :35-47 and
@@ -129,6 +151,23 @@ MWA_API int window_attention_backward(const float* xw, const float* mask, const 
                                       const float* proj_w, const void* params, float* grad_xw, float* grad_table,
                                       float* ao_tok, float* dqkv_tok, int64_t K, int C, int heads, int ws,
                                       int mask_windows, void* stream);
+
+/* GEMM-composed attention backward (what the Python layer uses when algo != SIMT): the token GEMMs
+ *   qkv_tok = xw_tok Wqkv^T + b,  dao_tok = dy_tok Wproj,  dxw_tok = dqkv_tok Wqkv  (+ the weight-gradient GEMMs above)
+ * are plain GEMMs over all tokens and run in the caller's library GEMM; these are the hand-written stages around them:
+ *   mwa_bwd_gather   x, grad_out (B,C,H,W) -> xw_tok, dy_tok (nwin,N,C; zero rows for dropped windows) + keep flags (nwin)
+ *   mwa_bwd_core     per window and head: softmax recompute, ao_tok, dqkv_tok (zero rows where !keep), grad_table
+ *                    (OVERWRITTEN).  H > 0: image geometry (region mask from H, W, shift); H == 0: token mode with the
+ *                    optional additive (mask_windows,N,N) mask and keep_flags == NULL.
+ *   mwa_bwd_scatter  grad_x = grad_out + dxw_tok at the un-shifted pixel positions */
+MWA_API int mwa_bwd_gather(const float* x, const float* alpha, const float* grad_out, float* xw_tok, float* dy_tok,
+                           uint8_t* keep_flags, int B, int C, int H, int W, int ws, int shift, int channels_last,
+                           void* stream);
+MWA_API int mwa_bwd_core(const float* qkv_tok, const float* dao_tok, const void* params, const float* mask,
+                         const uint8_t* keep_flags, float* ao_tok, float* dqkv_tok, float* grad_table, int64_t nwin,
+                         int C, int H, int W, int heads, int ws, int shift, int mask_windows, void* stream);
+MWA_API int mwa_bwd_scatter(const float* grad_out, const float* dxw_tok, float* grad_x, int B, int C, int H, int W,
+                            int ws, int shift, int channels_last, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Latent rounding   replaces  models/AutoEncoderRGB_Journal.py:31-32 (ste_round; forward value) and its

@@ -199,13 +199,16 @@ def test_window_attention_tokens_with_mask(pkg, cuda_dev):
     torch.testing.assert_close(y0, R.window_attention(x, *args, 4, 4), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("algo", list(ALGOS))
 @pytest.mark.parametrize("name", list(G.ATTENTION_CASES))
-def test_attention_backward_vs_golden(pkg, cuda_dev, golden, name):
-    """mwa_backward (hand-written fp32 kernel + token GEMMs) against the reference's autograd gradients."""
+def test_attention_backward_vs_golden(pkg, cuda_dev, golden, name, algo):
+    """attention backward against the reference's autograd gradients: `simt` = the all-in-one mwa_backward kernel,
+    `auto` = gather / core / scatter kernels around library token GEMMs.  Both are fp32 and re-compute from x, so the
+    gradients do not depend on the precision of the forward kernel."""
     cfg = G.ATTENTION_CASES[name]
     p = G.attention_inputs(cfg)
     m = _mk_attn(pkg, cfg, p, cuda_dev)
-    m.algo = ALGOS["simt"]               # fp32 forward: the committed gradients were taken at fp32
+    m.algo = ALGOS[algo]
     x = p["x"].to(cuda_dev).requires_grad_(True)
     y = m(x, p["alpha"].to(cuda_dev)) if cfg["masked"] else m(x)
     gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(cfg["seed"] + 5)).to(cuda_dev)
@@ -219,15 +222,16 @@ def test_attention_backward_vs_golden(pkg, cuda_dev, golden, name):
         torch.testing.assert_close(m.attn.proj.weight.grad.cpu(), _t(g[name + "/dproj_w"]), rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("algo", list(ALGOS))
 @pytest.mark.parametrize("channels_last", [False, True])
 @pytest.mark.parametrize("name", ["attn_c80_h8_ws4_s2", "attn_c192_h8_ws8_s4"])
-def test_attention_backward_all_gradients(pkg, cuda_dev, name, channels_last):
+def test_attention_backward_all_gradients(pkg, cuda_dev, name, channels_last, algo):
     """every gradient (incl. the two bias vectors, which the golden file does not carry) against autograd through the
     oracle's fp64 re-statement; NHWC input gives the same gradients."""
     cfg = G.ATTENTION_CASES[name]
     p = G.attention_inputs(cfg)
     m = _mk_attn(pkg, cfg, p, cuda_dev)
-    m.algo = ALGOS["simt"]
+    m.algo = ALGOS[algo]
     x = p["x"].to(cuda_dev)
     if channels_last:
         x = x.contiguous(memory_format=torch.channels_last)
@@ -245,9 +249,12 @@ def test_attention_backward_all_gradients(pkg, cuda_dev, name, channels_last):
         torch.testing.assert_close(v.double().cpu(), leaves[k].grad, rtol=1e-3, atol=2e-4, msg=lambda s_, k=k: f"{k}: {s_}")
 
 
-def test_window_attention_tokens_backward(pkg, cuda_dev):
-    """window_attention_backward: WindowAttention.forward(x, mask) on pre-partitioned tokens."""
+@pytest.mark.parametrize("algo", list(ALGOS))
+def test_window_attention_tokens_backward(pkg, cuda_dev, algo):
+    """window_attention_backward / mwa_bwd_core in token mode: WindowAttention.forward(x, mask) on pre-partitioned
+    tokens."""
     wa = pkg.WindowAttention(dim=32, window_size=(4, 4), num_heads=4).to(cuda_dev)
+    wa.algo = ALGOS[algo]
     g = torch.Generator().manual_seed(9)
     x = torch.randn(6, 16, 32, generator=g)
     mask = torch.randn(3, 16, 16, generator=g)
