@@ -1,0 +1,183 @@
+// TMA probe (development tool, B200): can cp.async.bulk.tensor gather / scatter the 8x8-pixel windows of an NCHW fp32
+// tensor (32-byte inner extent, 16-byte-offset box origins for shift 4) at a useful rate?  Decides whether the attention
+// kernel's global traffic can move from the LSU (2.3 cycles per request x 128-byte line, tools/sm_probe.cu) to the TMA
+// engine.  Measures, for all 6144 windows of a (16,192,128,192) tensor:
+//   copy   : tiled load of a [CB ch][8][8] box per window -> smem -> tiled store to `out`            (read + write)
+//   reduce : same, but the store is cp.reduce.async.bulk.tensor ... .add.f32 onto a pre-filled `out`  (the epilogue)
+// and checks the results (shift 0 and 4, interior windows and windows that hang over the right / bottom border:
+// out-of-bound elements are zero-filled on load and skipped on store).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/tma_probe tools/tma_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load4(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store4(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_red4(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// One CTA walks over windows (grid-stride).  Per window: C / CB boxes of [CB][8][8] floats through a ring of STAGES
+// buffers.  Thread 0 issues the loads (STAGES - 1 ahead) and the stores; the other threads add 1.0 to the staged values
+// in the `reduce` mode (so the result is checkable) -- a stand-in for the epilogue's writes into the staging buffer.
+template <int CB, int STAGES>
+__global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__ CUtensorMap in_map,
+                                                         const __grid_constant__ CUtensorMap out_map, int nwx, int nwy,
+                                                         int nwin, int C, int shift, int mode) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* stage = reinterpret_cast<float*>(smem);                       // STAGES x [CB][64]
+    __shared__ uint64_t full[STAGES];
+    const int tid = threadIdx.x;
+    constexpr uint32_t kBoxBytes = CB * 64 * 4;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int chunks = C / CB;
+    int my = 0;
+    for (int w = blockIdx.x; w < nwin; w += gridDim.x) ++my;
+    const int total = my * chunks;
+    auto coords = [&](int job, int& x0, int& y0, int& c0, int& b) {
+        const int win = blockIdx.x + (job / chunks) * gridDim.x;
+        b = win / (nwx * nwy);
+        const int r = win % (nwx * nwy);
+        y0 = (r / nwx) * 8 + shift;
+        x0 = (r % nwx) * 8 + shift;
+        c0 = (job % chunks) * CB;
+    };
+    if (tid == 0) {
+        for (int j = 0; j < STAGES - 1 && j < total; ++j) {
+            int x0, y0, c0, b;
+            coords(j, x0, y0, c0, b);
+            mbar_expect(full + j % STAGES, kBoxBytes);
+            tma_load4(stage + (j % STAGES) * CB * 64, &in_map, x0, y0, c0, b, full + j % STAGES);
+        }
+    }
+    for (int j = 0; j < total; ++j) {
+        const int s = j % STAGES;
+        // refill the stage that job j - 1 used: its store must have finished READING the buffer
+        if (tid == 0) {
+            const int jn = j + STAGES - 1;
+            if (jn < total) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                int x0, y0, c0, b;
+                coords(jn, x0, y0, c0, b);
+                mbar_expect(full + jn % STAGES, kBoxBytes);
+                tma_load4(stage + (jn % STAGES) * CB * 64, &in_map, x0, y0, c0, b, full + jn % STAGES);
+            }
+        }
+        mbar_wait(full + s, (j / STAGES) & 1);
+        float* buf = stage + s * CB * 64;
+        if (mode == 1) {
+            for (int e = tid; e < CB * 64; e += 128) buf[e] = 1.0f;      // "projection" contribution
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            int x0, y0, c0, b;
+            coords(j, x0, y0, c0, b);
+            if (mode == 0) tma_store4(&out_map, buf, x0, y0, c0, b);
+            else tma_red4(&out_map, buf, x0, y0, c0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+int main() {
+    const int B = 16, C = 192, H = 128, W = 192;
+    const size_t n = (size_t)B * C * H * W;
+    EncodeTiled encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres));
+    if (!encode) { printf("no cuTensorMapEncodeTiled\n"); return 1; }
+    float *x, *y, *flush;
+    CK(cudaMalloc(&x, n * 4)); CK(cudaMalloc(&y, n * 4)); CK(cudaMalloc(&flush, 512u << 20));
+    std::vector<float> hx(n);
+    for (size_t i = 0; i < n; ++i) hx[i] = float((i * 2654435761u) % 1000) * 0.001f;
+    CK(cudaMemcpy(x, hx.data(), n * 4, cudaMemcpyHostToDevice));
+    auto make_map = [&](float* base, int cb, CUtensorMap* m) -> bool {
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+        cuuint32_t box[4] = {8, 8, (cuuint32_t)cb, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return false; }
+        return true;
+    };
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int nwx = W / 8, nwy = H / 8, nwin = B * nwx * nwy;
+    std::vector<float> hy(n);
+    bool all_ok = true;
+    for (int cb : {16, 32, 64}) {
+        CUtensorMap in_map, out_map;
+        if (!make_map(x, cb, &in_map) || !make_map(y, cb, &out_map)) return 1;
+        for (int shift : {0, 4}) for (int mode : {0, 1}) for (int grid : {148, 296}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 3; ++rep) {
+                if (mode == 1) CK(cudaMemcpy(y, x, n * 4, cudaMemcpyDeviceToDevice));
+                else CK(cudaMemset(y, 0, n * 4));
+                CK(cudaMemsetAsync(flush, rep, 512u << 20));
+                cudaEventRecord(e0);
+                const int stages = 4;
+                const int smem = stages * cb * 64 * 4;
+                if (cb == 16) {
+                    cudaFuncSetAttribute(tma_window_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<16, 4><<<grid, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, mode);
+                } else if (cb == 32) {
+                    cudaFuncSetAttribute(tma_window_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<32, 4><<<grid, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, mode);
+                } else {
+                    cudaFuncSetAttribute(tma_window_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<64, 4><<<grid, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, mode);
+                }
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            // check: windows cover [shift, H) x [shift, W) (the parts hanging over the border are clipped)
+            CK(cudaMemcpy(hy.data(), y, n * 4, cudaMemcpyDeviceToHost));
+            size_t bad = 0;
+            for (size_t i = 0; i < n; i += 97) {
+                const int px = i % W, py = (i / W) % H;
+                const bool covered = px >= shift && py >= shift;
+                const float want = mode == 0 ? (covered ? hx[i] : 0.f) : (covered ? hx[i] + 1.0f : hx[i]);
+                if (hy[i] != want) ++bad;
+            }
+            if (bad) all_ok = false;
+            printf("TMA window %s  box [%2d ch][8][8]  shift %d  grid %3d: %.3f ms  %.0f GB/s (read+write)  %s\n",
+                   mode == 0 ? "copy  " : "reduce", cb, shift, grid, best, 2.0 * n * 4 / best / 1e6, bad ? "MISMATCH" : "ok");
+        }
+    }
+    printf(all_ok ? "PROBE PASSED\n" : "PROBE FAILED\n");
+    return 0;
+}
