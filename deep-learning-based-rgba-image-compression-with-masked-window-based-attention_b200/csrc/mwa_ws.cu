@@ -95,14 +95,6 @@ residual_copy_kernel(const float4* __restrict__ x, float4* __restrict__ out, int
     }
     for (; i < n4; i += stride) out[i] = __ldcs(x + i);
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void stg_hint(float* addr, float v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(pol) : "memory");
-}
 __device__ __forceinline__ float rcp_approx(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -534,7 +526,6 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         static_assert(CF::NCHUNK % 2 == 0, "C must be a multiple of 16");
         constexpr int LB = 4;                               // chunks per load batch (32 loads in flight)
         uint32_t pk[CPH][4];
-        const uint64_t pol_last = l2_policy_evict_last();
         auto row_base = [&](int tile, bool& valid) -> int64_t {      // NCHW element offset of (b, c = 0, py, px)
             const int lidx = tile * CF::WPT + wslot;
             valid = lidx < count;
@@ -548,9 +539,10 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         // fire-and-forget reductions, so `out` must already hold the residual x.  Two ways (measured):
         //   some window dropped: residual_copy_kernel has copied x -> out wholesale before this kernel, which also
         //                settles the dropped windows; x is read exactly once here.
-        //   every window kept (prestore): the fp32 values just loaded go straight to `out` (evict-last in L2 so that
-        //                the line is still there when the reduction arrives two tiles later); no copy pass at all.
-        //                With dropped neighbours these half-sector stores are slow, hence the switch.
+        //   every window kept (prestore): the fp32 values just loaded go straight to `out`; no copy pass at all.
+        //                With dropped neighbours these half-sector stores are slow, hence the switch.  (An L2
+        //                evict-last hint on these stores changed nothing measurable and would leave persisting lines
+        //                behind for the next kernel, so they are plain stores.)
         auto load_x = [&](int tile) {
             bool valid;
             const int64_t off = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
@@ -573,7 +565,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     if (c0 + i < CPH) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (valid && prestore) stg_hint(po, v[i][j], pol_last);
+                            if (valid && prestore) *po = v[i][j];
                             po += hw;
                         }
 #pragma unroll
