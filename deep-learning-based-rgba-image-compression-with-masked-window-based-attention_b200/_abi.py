@@ -51,6 +51,8 @@ _SIGNATURES = {
     "mwa_bwd_gather": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "mwa_bwd_core": (c_int, [c_void_p] * 8 + [c_int64] + [c_int] * 7 + [c_void_p]),
     "mwa_bwd_scatter": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    "gate_residual_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gate_residual_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "round_ste_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "quantize_offset_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         c_int, c_int64, c_void_p]),

@@ -1,0 +1,113 @@
+"""B200 drop-in for the reference's `layers/Masked_Attention.py` (first widening step).
+
+    Win_noShift_Attention(dim, num_heads=8, window_size=8, shift_size=0).forward(x, mask)
+        a = conv_a(x) ; b = conv_b(attn(x, mask)) ; out = a * sigmoid(b) + x          (reference :143-189)
+
+Same constructor, children and state-dict keys as the reference (`conv_a.{0,1,2}.conv.{0,2,4}.*`, `attn.attn.*`,
+`conv_b.{0,1,2}.conv.{0,2,4}.*`, `conv_b.3.*`).  The two residual-unit stacks are ordinary convolutions and stay with
+cuDNN (they are callers of the hot path, not part of it); `attn` is the fused sm_100a masked window attention, and the
+gate + residual `a * sigmoid(b) + x` -- three elementwise kernels and eight tensor passes in the reference -- is ONE
+hand-written kernel (`gate_residual`, csrc/gate.cu), forward and backward.
+Only the names the Journal models use are provided (`conv1x1`, `Win_noShift_Attention`); the reference file's legacy
+blocks (`ResBlockMask`, `AttentionMask`: they reference an undefined `CustomConv2DPyMV3`) are not reproduced.
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .. import _abi
+from .masked_win_attention import *  # noqa: F401,F403  (the reference file star-imports it too, :6)
+from .masked_win_attention import WinBasedAttention
+
+
+def conv1x1(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
+    """1x1 convolution (reference :11-13)."""
+    return nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=stride)
+
+
+def conv3x3(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
+    """3x3 convolution with padding (compressai.layers.conv3x3, imported by the reference :8-10)."""
+    return nn.Conv2d(in_ch, out_ch, kernel_size=3, stride=stride, padding=1)
+
+
+class _GateResidual(Function):
+    @staticmethod
+    def forward(ctx, a, b, x):
+        lib = _abi.load()
+        for name, t in (("a", a), ("b", b), ("x", x)):
+            _abi.require_cuda_f32(t, f"gate_residual {name}")
+        if not (a.shape == b.shape == x.shape):
+            raise RuntimeError(f"gate_residual: shape mismatch {tuple(a.shape)} {tuple(b.shape)} {tuple(x.shape)}")
+        # one dense memory format for all three (x decides); the kernel is layout-agnostic
+        fmt = torch.channels_last if (x.dim() == 4 and not x.is_contiguous()
+                                      and x.is_contiguous(memory_format=torch.channels_last)) else torch.contiguous_format
+        a, b, x = (t.contiguous(memory_format=fmt) for t in (a, b, x))
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _abi.check(lib.gate_residual_forward(a.data_ptr(), b.data_ptr(), x.data_ptr(), out.data_ptr(), x.numel(),
+                                                 _abi.stream_handle()), "gate_residual_forward")
+        ctx.fmt = fmt
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _abi.load()
+        a, b = ctx.saved_tensors
+        g = g.contiguous(memory_format=ctx.fmt)
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        with torch.cuda.device(a.device):
+            _abi.check(lib.gate_residual_backward(a.data_ptr(), b.data_ptr(), g.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                                  a.numel(), _abi.stream_handle()), "gate_residual_backward")
+        return ga, gb, g
+
+
+def gate_residual(a, b, x):
+    """a * sigmoid(b) + x in one pass (reference layers/Masked_Attention.py:186-188)."""
+    return _GateResidual.apply(a, b, x)
+
+
+class Win_noShift_Attention(nn.Module):
+    """Window-based self-attention module (reference :143-189)."""
+
+    def __init__(self, dim, num_heads=8, window_size=8, shift_size=0):
+        super().__init__()
+        N = dim
+
+        class ResidualUnit(nn.Module):
+            """Simple residual unit."""
+
+            def __init__(self):
+                super().__init__()
+                self.conv = nn.Sequential(
+                    conv1x1(N, N // 2),
+                    nn.GELU(),
+                    conv3x3(N // 2, N // 2),
+                    nn.GELU(),
+                    conv1x1(N // 2, N),
+                )
+                self.relu = nn.GELU()
+
+            def forward(self, x):
+                identity = x
+                out = self.conv(x)
+                out += identity
+                out = self.relu(out)
+                return out
+
+        self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
+
+        self.attn = WinBasedAttention(dim=dim, num_heads=num_heads, window_size=window_size, shift_size=shift_size)
+
+        self.conv_b = nn.Sequential(
+            ResidualUnit(),
+            ResidualUnit(),
+            ResidualUnit(),
+            conv1x1(N, N),
+        )
+
+    def forward(self, x, mask):
+        a = self.conv_a(x)
+        b = self.attn(x, mask)
+        b = self.conv_b(b)
+        return gate_residual(a, b, x)

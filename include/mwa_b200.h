@@ -190,6 +190,16 @@ MWA_API int lrp_add_forward(const float* y_hat, const float* lrp, float* out, in
                     int64_t y_row_stride, int64_t lrp_row_stride, int64_t out_row_stride, void* stream);
 MWA_API int quantize_levels_forward(const float* m, float* out, int64_t n, float levels, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Attention wrapper gate (first widening step)   replaces  layers/Masked_Attention.py:186-188
+ *   (Win_noShift_Attention.forward:  out = a * torch.sigmoid(b); out += identity) -- one pass instead of three kernels.
+ * gate_residual_forward  : out = a * sigmoid(b) + x          n contiguous floats each (any memory format, same for all)
+ * gate_residual_backward : grad_a = g * s, grad_b = g * a * s * (1 - s), s = sigmoid(b);  grad_x = g (caller's alias)
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int gate_residual_forward(const float* a, const float* b, const float* x, float* out, int64_t n, void* stream);
+MWA_API int gate_residual_backward(const float* a, const float* b, const float* grad_out, float* grad_a, float* grad_b,
+                                   int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ _install = importlib.import_module(PACKAGE_NAME + ".install")
 GDN_mod = importlib.import_module(PACKAGE_NAME + ".layers.GDN")
 masked_win_attention = importlib.import_module(PACKAGE_NAME + ".layers.masked_win_attention")
 win_attention = importlib.import_module(PACKAGE_NAME + ".layers.win_attention")
+Masked_Attention = importlib.import_module(PACKAGE_NAME + ".layers.Masked_Attention")
 data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
 
 GDN = GDN_mod.GDN
@@ -26,6 +27,8 @@ LowerBound = GDN_mod.LowerBound
 MaskedWinBasedAttention = masked_win_attention.WinBasedAttention
 WinBasedAttention = win_attention.WinBasedAttention
 WindowAttention = masked_win_attention.WindowAttention
+Win_noShift_Attention = Masked_Attention.Win_noShift_Attention
+gate_residual = Masked_Attention.gate_residual
 ste_round = quant.ste_round
 quantize_offset = quant.quantize_offset
 lrp_add = quant.lrp_add

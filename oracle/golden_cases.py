@@ -81,6 +81,39 @@ def attention_inputs(cfg):
     return p
 
 
+WRAPPER_CASES = {
+    # Win_noShift_Attention(dim, heads, ws, shift) on (B, dim, H, W) with a blob alpha
+    "wrap_c32_h4_ws4_s2": dict(C=32, heads=4, ws=4, shift=2, B=2, H=8, W=12, drop=0.3, seed=41),
+    "wrap_c80_h8_ws4_s2": dict(C=80, heads=8, ws=4, shift=2, B=1, H=8, W=16, drop=0.4, seed=42),
+}
+
+
+def wrapper_inputs(cfg):
+    """returns dict(x, alpha, state): `state` = a reference-style state dict with seeded values"""
+    g = _gen(cfg["seed"])
+    C, h, ws = cfg["C"], cfg["heads"], cfg["ws"]
+    x = torch.randn(cfg["B"], C, cfg["H"], cfg["W"], generator=g)
+    state = {}
+    for br in ("conv_a", "conv_b"):
+        for i in range(3):
+            state[f"{br}.{i}.conv.0.weight"] = torch.randn(C // 2, C, 1, 1, generator=g) * C ** -0.5
+            state[f"{br}.{i}.conv.0.bias"] = torch.randn(C // 2, generator=g) * 0.1
+            state[f"{br}.{i}.conv.2.weight"] = torch.randn(C // 2, C // 2, 3, 3, generator=g) * (9 * C / 2) ** -0.5
+            state[f"{br}.{i}.conv.2.bias"] = torch.randn(C // 2, generator=g) * 0.1
+            state[f"{br}.{i}.conv.4.weight"] = torch.randn(C, C // 2, 1, 1, generator=g) * (C / 2) ** -0.5
+            state[f"{br}.{i}.conv.4.bias"] = torch.randn(C, generator=g) * 0.1
+    state["conv_b.3.weight"] = torch.randn(C, C, 1, 1, generator=g) * C ** -0.5
+    state["conv_b.3.bias"] = torch.randn(C, generator=g) * 0.1
+    s = C ** -0.5
+    state["attn.attn.qkv.weight"] = torch.randn(3 * C, C, generator=g) * s
+    state["attn.attn.qkv.bias"] = torch.randn(3 * C, generator=g) * 0.1
+    state["attn.attn.proj.weight"] = torch.randn(C, C, generator=g) * s
+    state["attn.attn.proj.bias"] = torch.randn(C, generator=g) * 0.1
+    state["attn.attn.relative_position_bias_table"] = torch.randn((2 * ws - 1) ** 2, h, generator=g) * 0.3
+    alpha = blob_alpha(cfg["B"], cfg["H"], cfg["W"], ws, cfg["shift"], cfg["drop"], cfg["seed"] + 1000)
+    return dict(x=x, alpha=alpha, state=state)
+
+
 GDN_CASES = {
     "gdn_c192": dict(C=192, B=2, H=8, W=12, inverse=False, seed=21),
     "igdn_c192": dict(C=192, B=2, H=8, W=12, inverse=True, seed=22),

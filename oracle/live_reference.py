@@ -23,6 +23,7 @@ class _RefModules:
         self.masked = importlib.import_module("layers.masked_win_attention")
         self.unmasked = importlib.import_module("layers.win_attention")
         self.gdn = importlib.import_module("layers.GDN")
+        self.wrapper = importlib.import_module("layers.Masked_Attention")
 
     def model(self, which: str):
         """'rgb' -> models.AutoEncoderRGB_Journal, 'mask' -> models.AutoEncoderMask_Journal."""

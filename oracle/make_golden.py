@@ -74,6 +74,28 @@ def make_gdn(ref):
     return out
 
 
+def make_wrapper(ref):
+    out = {}
+    for name, cfg in G.WRAPPER_CASES.items():
+        p = G.wrapper_inputs(cfg)
+        m = ref.wrapper.Win_noShift_Attention(cfg["C"], num_heads=cfg["heads"], window_size=cfg["ws"],
+                                              shift_size=cfg["shift"])
+        missing, unexpected = m.load_state_dict(p["state"], strict=False)
+        assert not unexpected and all(k.endswith("relative_position_index") for k in missing), (missing, unexpected)
+        x = p["x"].clone().requires_grad_(True)
+        y = m(x, p["alpha"])
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(cfg["seed"] + 5))
+        y.backward(gy)
+        out[name + "/y"] = _np(y)
+        out[name + "/dx"] = _np(x.grad)
+        out[name + "/dconv_b3_w"] = _np(m.conv_b[3].weight.grad)
+        out[name + "/dconv_a0_w"] = _np(m.conv_a[0].conv[0].weight.grad)
+        out[name + "/keys"] = np.array(sorted(m.state_dict().keys()))
+        out[name + "/crc"] = np.array(G.checksum(p["x"], p["alpha"], *[p["state"][k] for k in sorted(p["state"])]),
+                                      dtype=np.int64)
+    return out
+
+
 def make_rounding(ref):
     p = G.rounding_inputs()
     rgb = ref.model("rgb")
@@ -91,8 +113,11 @@ def main():
     ref = live_reference.load()
     torch.set_num_threads(1)           # fixed reduction order
     os.makedirs(OUT_DIR, exist_ok=True)
-    for fname, data in (("attention.npz", make_attention(ref)), ("gdn.npz", make_gdn(ref)),
-                        ("rounding.npz", make_rounding(ref))):
+    import sys
+    only = set(sys.argv[1:])
+    makers = (("attention.npz", make_attention), ("gdn.npz", make_gdn), ("rounding.npz", make_rounding),
+              ("wrapper.npz", make_wrapper))
+    for fname, data in ((f, mk(ref)) for f, mk in makers if not only or f in only):
         path = os.path.join(OUT_DIR, fname)
         np.savez_compressed(path, **data)
         print(f"wrote {path}: {len(data)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

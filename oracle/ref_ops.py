@@ -244,6 +244,36 @@ def quantize_levels(m, levels: int = 255):
 # --------------------------------------------------------------------------------------
 # alpha pyramid feeding a1   (layers/SupplyMask.py:7-18) -- input generator for the benches
 # --------------------------------------------------------------------------------------
+def gate_residual(a, b, x):
+    """layers/Masked_Attention.py:186-188:  out = a * torch.sigmoid(b); out += identity."""
+    return a * torch.sigmoid(b) + x
+
+
+def _residual_unit(x, w, prefix):
+    """layers/Masked_Attention.py:150-171: conv1x1 -> GELU -> conv3x3 -> GELU -> conv1x1, + identity, GELU."""
+    F = torch.nn.functional
+    out = F.conv2d(x, w[prefix + "conv.0.weight"], w[prefix + "conv.0.bias"])
+    out = F.gelu(out)
+    out = F.conv2d(out, w[prefix + "conv.2.weight"], w[prefix + "conv.2.bias"], padding=1)
+    out = F.gelu(out)
+    out = F.conv2d(out, w[prefix + "conv.4.weight"], w[prefix + "conv.4.bias"])
+    return F.gelu(out + x)
+
+
+def win_noshift_attention(x, mask, w, heads: int, ws: int, shift: int):
+    """layers/Masked_Attention.py:182-189 (Win_noShift_Attention.forward) on a reference-style state dict `w`."""
+    a = x
+    for i in range(3):
+        a = _residual_unit(a, w, f"conv_a.{i}.")
+    b = masked_window_attention(x, mask, w["attn.attn.qkv.weight"], w.get("attn.attn.qkv.bias"),
+                                w["attn.attn.proj.weight"], w["attn.attn.proj.bias"],
+                                w["attn.attn.relative_position_bias_table"], heads, ws, shift)
+    for i in range(3):
+        b = _residual_unit(b, w, f"conv_b.{i}.")
+    b = torch.nn.functional.conv2d(b, w["conv_b.3.weight"], w["conv_b.3.bias"])
+    return gate_residual(a, b, x)
+
+
 def alpha_pyramid(alpha, levels: int = 6):
     out = []
     a = alpha

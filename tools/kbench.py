@@ -136,6 +136,17 @@ def bench_attn(args, dev, flush):
                       flush=True)
 
 
+def bench_gate(args, dev, flush):
+    a, b, x = (torch.randn(16, 192, 128, 192, device=dev) for _ in range(3))
+    byts = a.numel() * 16
+    with torch.no_grad():
+        med, _ = timeit(lambda: pkg.gate_residual(a, b, x), args.iters, flush)
+        print(f"gate_residual (16,192,128,192) fused kernel : median {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s = "
+              f"{byts / med / 1e6 / PEAKS['hbm_gbs'] * 100:5.1f}% HBM", flush=True)
+        med2, _ = timeit(lambda: a * torch.sigmoid(b) + x, args.iters, flush)
+        print(f"    the reference's three torch kernels     : median {med2 * 1e3:8.1f} us  ({med2 / med:.2f}x)", flush=True)
+
+
 def bench_round(args, dev, flush):
     y = torch.randn(16, 80, 64, 96, device=dev) * 4
     mu = torch.randn_like(y)
@@ -156,4 +167,4 @@ if __name__ == "__main__":
     dev = torch.device("cuda:0")
     flush = torch.zeros(128 * 1024 * 1024, device=dev)
     for w in args.what:
-        {"gdn": bench_gdn, "attn": bench_attn, "round": bench_round}[w](args, dev, flush)
+        {"gdn": bench_gdn, "attn": bench_attn, "round": bench_round, "gate": bench_gate}[w](args, dev, flush)
