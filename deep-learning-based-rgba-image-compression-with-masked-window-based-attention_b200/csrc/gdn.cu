@@ -451,8 +451,9 @@ int gdn_prepare(const float* beta_p, const float* gamma_p, int C, float beta_bou
 
 int gdn_forward(const float* x, float* y, const void* params, int64_t n_img, int C, int64_t hw, int inverse,
                 int channels_last, int algo, void* stream) {
-    if (!x || !y || !params || n_img < 0 || hw < 0 || C <= 0) return MWA_ERR_INVALID;
-    if (n_img == 0 || hw == 0) return MWA_OK;
+    if (n_img < 0 || hw < 0 || C <= 0) return MWA_ERR_INVALID;
+    if (n_img == 0 || hw == 0) return MWA_OK;               // empty tensors carry null data pointers
+    if (!x || !y || !params) return MWA_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (algo == MWA_ALGO_TCGEN05 || (algo == MWA_ALGO_AUTO && gdn_tc_supported(C, hw, channels_last))) {
         if (!gdn_tc_supported(C, hw, channels_last)) return MWA_ERR_UNSUPPORTED;

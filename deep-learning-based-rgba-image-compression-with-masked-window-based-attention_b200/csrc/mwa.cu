@@ -300,13 +300,13 @@ int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
 int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
                 int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* workspace,
                 int64_t workspace_bytes, void* stream) {
-    if (!x || !out || !params) return MWA_ERR_INVALID;
     if (B < 0 || C <= 0 || H <= 0 || W <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return MWA_ERR_INVALID;
     if (shift < 0 || shift >= ws) return MWA_ERR_INVALID;
     if (H % ws != 0 || W % ws != 0) return MWA_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kept_count) MWA_TRY_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st), "mwa_forward(memset)");
-    if (B == 0) return MWA_OK;
+    if (B == 0) return MWA_OK;                              // empty batch: x / out may be null
+    if (!x || !out || !params) return MWA_ERR_INVALID;
     const bool tc_ok = mwa_tc_supported(C, heads, ws, H, W, shift, channels_last);
     if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || (algo == MWA_ALGO_AUTO && tc_ok)) {
         if (!tc_ok) return MWA_ERR_UNSUPPORTED;

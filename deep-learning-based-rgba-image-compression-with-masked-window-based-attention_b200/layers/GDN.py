@@ -98,6 +98,10 @@ class _GDNFunction(Function):
         if not channels_last:
             x = x.contiguous()
         hw = x.shape[2] * x.shape[3]
+        if x.numel() == 0:                   # empty batch: nothing to launch
+            ctx.mod, ctx.channels_last = mod, channels_last
+            ctx.save_for_backward(x, beta, gamma, beta)
+            return torch.empty_like(x)
         with torch.cuda.device(x.device):
             blk = mod._param_block(beta, gamma)
             y = torch.empty_like(x)          # preserves the memory format
@@ -113,6 +117,8 @@ class _GDNFunction(Function):
         lib = _abi.load()
         x, beta, gamma, blk = ctx.saved_tensors
         mod = ctx.mod
+        if x.numel() == 0:
+            return grad_y, torch.zeros_like(beta), torch.zeros_like(gamma), None
         B, C = x.shape[0], x.shape[1]
         hw = x.shape[2] * x.shape[3]
         if ctx.channels_last:

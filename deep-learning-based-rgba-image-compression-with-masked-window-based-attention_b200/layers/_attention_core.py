@@ -84,6 +84,10 @@ class WindowAttentionFunction(Function):
             # the reference fails in window_partition's .view (layers/masked_win_attention.py:15)
             raise RuntimeError(f"shape '[{B}, {H // ws}, {ws}, {W // ws}, {ws}, {C}]' is invalid for input of size "
                                f"{x.numel()}: H={H}, W={W} must be multiples of window_size={ws}")
+        if x.numel() == 0:                   # empty batch: nothing to launch (data_ptr() of an empty tensor is null)
+            ctx.empty = True
+            return torch.empty_like(x)
+        ctx.empty = False
         channels_last = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
         if not channels_last:
             x = x.contiguous()
@@ -106,6 +110,8 @@ class WindowAttentionFunction(Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.empty:
+            return (grad_out,) + (None,) * 10
         x, alpha, qkv_w, qkv_b, proj_w, proj_b, table = ctx.saved_tensors
         attn_mod, ws, shift = ctx.cfg
         lib = _abi.load()
