@@ -89,7 +89,7 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
     uint64_t* bar_empty = bars + 3;         // [kSlots]  MMAs reading the slot have completed
     uint64_t* bar_dfull = bars + 5;         // accumulator of the current tile complete
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::tmem_ptr);
-    const float* s_beta = reinterpret_cast<const float*>(smem + Smem::beta);
+    const uint32_t s_beta = sbase + Smem::beta;          // shared-window address: beta is read with ld.shared
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const GdnParamLayout L(kC);
@@ -276,7 +276,9 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                     float bt[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4*>(bt + 4 * j) = *reinterpret_cast<const float4*>(s_beta + ch0 + 4 * j);
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(bt[4 * j]), "=f"(bt[4 * j + 1]), "=f"(bt[4 * j + 2]), "=f"(bt[4 * j + 3])
+                                     : "r"(s_beta + 4 * (ch0 + 4 * j)));
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -316,7 +318,9 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                 float bt[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(bt + 4 * j) = *reinterpret_cast<const float4*>(s_beta + ch0 + 4 * j);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(bt[4 * j]), "=f"(bt[4 * j + 1]), "=f"(bt[4 * j + 2]), "=f"(bt[4 * j + 3])
+                                     : "r"(s_beta + 4 * (ch0 + 4 * j)));
                 tmem_wait_ld();
                 float* yj = yc;
 #pragma unroll
