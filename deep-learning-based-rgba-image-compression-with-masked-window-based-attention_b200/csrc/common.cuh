@@ -204,6 +204,88 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (tcgen05 cta_group::2) and clusters
+// Verified on the hardware by tools/umma2_probe.cu: a cluster of 2 CTAs, each holding its own 128 A rows and HALF of
+// the B rows, one M = 256 MMA issued by the leader, accumulator rows in each CTA's own TMEM, completion multicast to the
+// mbarrier at the same shared-memory offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_addr` (a shared::cta address) inside CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // arrive on another CTA's mbarrier
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {           // one warp in EACH CTA of the pair
+    static_assert(kCols == 32 || kCols == 64 || kCols == 128 || kCols == 256 || kCols == 512, "pow2 >= 32");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]^T; issued by ONE thread of the leader CTA.
+// idesc: umma_idesc(fmt, fmt, 256, N).
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued pair MMAs of this thread arrive on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask = 3) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- TMA tensor copies (4-D tiled), verified by tools/tma_probe.cu
+// `map` points at a CUtensorMap passed to the kernel as a __grid_constant__ parameter; coordinates innermost first.
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, const void* src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// global[box] += smem[box] (fp32), element-wise inside the L2; out-of-bound elements are skipped
+__device__ __forceinline__ void tma_reduce_add_4d(const void* map, const void* src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {   // smem sources of all but the last kPending groups consumed
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // ---------------------------------------------------------------- small math / packing helpers
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;

@@ -13,6 +13,7 @@
 #include <vector>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include "../deep-learning-based-rgba-image-compression-with-masked-window-based-attention_b200/csrc/common.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
@@ -20,27 +21,16 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c) : "memory"); }
-__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    } while (!ok);
-}
+using namespace b200;
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) { mbar_arrive_expect_tx(b, bytes); }
 __device__ __forceinline__ void tma_load4(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+    tma_load_4d(dst, map, c0, c1, c2, c3, bar);
 }
 __device__ __forceinline__ void tma_store4(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    tma_store_4d(map, src, c0, c1, c2, c3);
 }
 __device__ __forceinline__ void tma_red4(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    tma_reduce_add_4d(map, src, c0, c1, c2, c3);
 }
 
 // One CTA walks over windows (grid-stride).  Per window: C / CB boxes of [CB][8][8] floats through a ring of STAGES
@@ -57,7 +47,7 @@ __global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__
     constexpr uint32_t kBoxBytes = CB * 64 * 4;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     __syncthreads();
     const int chunks = C / CB;
@@ -86,7 +76,7 @@ __global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__
         if (tid == 0) {
             const int jn = j + STAGES - 1;
             if (jn < total) {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                bulk_wait_group_read<0>();
                 int x0, y0, c0, b;
                 coords(jn, x0, y0, c0, b);
                 mbar_expect(full + jn % STAGES, kBoxBytes);
@@ -98,17 +88,17 @@ __global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__
         if (mode == 1) {
             for (int e = tid; e < CB * 64; e += 128) buf[e] = 1.0f;      // "projection" contribution
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
             int x0, y0, c0, b;
             coords(j, x0, y0, c0, b);
             if (mode == 0) tma_store4(&out_map, buf, x0, y0, c0, b);
             else tma_red4(&out_map, buf, x0, y0, c0, b);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            bulk_commit_group();
         }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == 0) bulk_wait_group<0>();
 }
 
 int main() {

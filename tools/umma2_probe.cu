@@ -23,16 +23,6 @@ using namespace b200;
         }                                                                                  \
     } while (0)
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 probe2_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, float* __restrict__ D, int N, int K) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -58,8 +48,7 @@ probe2_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, fl
         fence_mbar_init();
     }
     if (warp == 0) {      // both CTAs of the pair allocate (collective over the pair)
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        tmem_alloc_pair<256>(&tmem_base_s);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -70,23 +59,17 @@ probe2_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, fl
 
     if (rank == 0 && tid == 0) {
         // instruction descriptor: M = 256 (the pair), N columns
-        const uint32_t idesc = (1u << 4) | (kFmtF16 << 7) | (kFmtF16 << 10) | ((uint32_t(N) >> 3) << 17) | ((256u >> 4) << 24);
+        const uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, 256, N);
         for (int kb = 0; kb < kblocks; ++kb) {
             const uint64_t a0 = umma_desc_k_sw128(smem_u32(sA + kb * 128 * 128));
             const uint64_t b0 = umma_desc_k_sw128(smem_u32(sB + kb * NH * 128));
             const int nks = (K - kb * 64 >= 64) ? 4 : (K - kb * 64 + 15) / 16;
             for (int ks = 0; ks < nks; ++ks) {
-                const uint32_t acc = (kb | ks) != 0;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-                    "l"(a0 + ks * 2), "l"(b0 + ks * 2), "r"(idesc), "r"(acc)
-                    : "memory");
+                umma_f16_ss_pair(tmem_d, a0 + ks * 2, b0 + ks * 2, idesc, (kb | ks) != 0);
             }
         }
         // completion -> the mbarrier at this smem offset in BOTH CTAs
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(smem_u32(&bar)), "h"(uint16_t(3)) : "memory");
+        umma_commit_pair(&bar, 3);
     }
     mbar_wait(&bar, 0);
     tc_fence_after_sync();
@@ -101,7 +84,7 @@ probe2_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, fl
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(256) : "memory");
+    if (warp == 0) tmem_dealloc_pair<256>(tmem_d);
 }
 
 int main() {
