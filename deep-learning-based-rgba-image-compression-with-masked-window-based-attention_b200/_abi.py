@@ -112,3 +112,25 @@ def require_cuda_f32(t: torch.Tensor, name: str) -> None:
                            "and has no CPU fallback")
     if t.dtype != torch.float32:
         raise MwaB200Error(f"{name} must be float32 (got {t.dtype})")
+
+
+class tf32_reduction:
+    """Context for the LARGE-K parameter-gradient GEMMs of the backward (dW = dY^T X over all tokens, dgamma = dn (x^2)^T
+    over all pixels: K = 10^4 ... 10^6): lets the library GEMM use TF32 tensor-core products with fp32 accumulation.
+    A 2^-11 relative error per product averages out over that many terms (observed ~1e-5 relative on the sums), while the
+    fp32 SIMT SGEMM these shapes otherwise fall to was 27 % of the training step.  The per-pixel / per-token contractions
+    (K = C) stay in full fp32."""
+
+    MIN_K = 8192        # below this the averaging argument is weak and the fp32 GEMM is cheap anyway
+
+    def __init__(self, k: int):
+        self.on = k >= self.MIN_K
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False

@@ -71,13 +71,14 @@ def _composed_backward(lib, x, grad_y, beta, gamma, blk, mod, channels_last, gx,
     else:
         torch.matmul(gT_eff, tok(dn), out=tok(t))
     _abi.check(lib.gdn_bwd_dx(nb.data_ptr(), x.data_ptr(), t.data_ptr(), gx.data_ptr(), x.numel(), st), "gdn_bwd_dx")
-    if channels_last:
-        dg = tok(dn).t() @ tok(x2)                       # (C, BHW) x (BHW, C)
-    else:
-        dg = torch.zeros(C, C, device=x.device)
-        dnv, x2v = tok(dn), tok(x2)
-        for b in range(B):                               # accumulating GEMMs: no reduction kernel
-            dg.addmm_(dnv[b], x2v[b].t())
+    with _abi.tf32_reduction(hw if not channels_last else B * hw):   # K = pixels: TF32 products, fp32 accumulation
+        if channels_last:
+            dg = tok(dn).t() @ tok(x2)                   # (C, BHW) x (BHW, C)
+        else:
+            dg = torch.zeros(C, C, device=x.device)
+            dnv, x2v = tok(dn), tok(x2)
+            for b in range(B):                           # accumulating GEMMs: no reduction kernel
+                dg.addmm_(dnv[b], x2v[b].t())
     scratch = torch.empty(C, device=x.device)
     _abi.check(lib.gdn_bwd_finalize(dn.data_ptr(), dg.data_ptr(), beta.data_ptr(), gamma.data_ptr(), mod.beta_bound,
                                     mod.gamma_bound, gb.data_ptr(), gg.data_ptr(), scratch.data_ptr(), B, C, hw,

@@ -149,9 +149,10 @@ class WindowAttentionFunction(Function):
                 _abi.check(lib.mwa_bwd_scatter(grad_out.data_ptr(), dxw.data_ptr(), gx.data_ptr(), B, C, H, W, ws,
                                                shift, int(channels_last), st), "mwa_bwd_scatter")
             need = ctx.needs_input_grad
-            gw1 = dqkv.t() @ xw if need[2] else None
+            with _abi.tf32_reduction(nwin * N):          # K = all tokens
+                gw1 = dqkv.t() @ xw if need[2] else None
+                gw2 = dy.t() @ ao if need[4] else None
             gb1 = dqkv.sum(0) if (need[3] and ctx.has_bias) else None
-            gw2 = dy.t() @ ao if need[4] else None
             gb2 = dy.sum(0) if need[5] else None
         return (gx if need[0] else None), None, gw1, gb1, gw2, gb2, (gtab if need[6] else None), None, None, None, None
 
@@ -220,9 +221,10 @@ class TokenAttentionFunction(Function):
                                             ws, 0, nw, _abi.stream_handle()), "mwa_bwd_core")
                 torch.matmul(dqkv, qw, out=gx.view(K * N, C))
             need = ctx.needs_input_grad
-            gw1 = dqkv.t() @ xf if need[2] else None
+            with _abi.tf32_reduction(K * N):
+                gw1 = dqkv.t() @ xf if need[2] else None
+                gw2 = dyf.t() @ ao if need[4] else None
             gb1 = dqkv.sum(0) if (need[3] and qkv_b is not None) else None
-            gw2 = dyf.t() @ ao if need[4] else None
             gb2 = dyf.sum(0) if need[5] else None
         return (gx if need[0] else None), None, gw1, gb1, gw2, gb2, (gtab if need[6] else None), None
 
