@@ -67,6 +67,14 @@ struct WsMap {
     static_assert(bOEmpty + 2 <= 32, "barrier slots");
 };
 
+// tuning knobs (defaults = the measured best; tools/build_variants.py builds side-by-side variants)
+#ifndef MWA_WS_LB
+#define MWA_WS_LB 4
+#endif
+#ifndef MWA_WS_MASK_PREFETCH
+#define MWA_WS_MASK_PREFETCH 0
+#endif
+
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -404,18 +412,19 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     // clock64() deltas per pipeline stage
     const bool do_time = kTiming && timing != nullptr && blockIdx.x == 0 && lane == 0 &&
                          (warp == kMmaWarp || warp == kPeWarp0 || warp == kAtWarp0);
-    long long t_prev = do_time ? clock64() : 0;
+    const long long t_cta0 = (kTiming && timing != nullptr) ? clock64() : 0;
+    // event trace of CTA 0: [1024 + role * 1024 + i] = stage << 48 | cycles since kernel start at the END of the stage.
+    // Plain stores only (fire and forget): a read-modify-write per stage costs the single-warp roles ~1k cycles per
+    // event and distorts the very pipeline it measures.
+    int n_ev = 0;
     auto tick = [&](int slot) {
         if constexpr (kTiming) {
-            if (do_time) {
-                const long long now = clock64();
-                timing[slot] += static_cast<unsigned long long>(now - t_prev);
-                t_prev = now;
-            }
+            if (do_time && n_ev < 1024)
+                timing[1024 + (slot >> 3) * 1024 + n_ev++] =
+                    (static_cast<unsigned long long>(slot) << 48) | static_cast<unsigned long long>(clock64() - t_cta0);
         }
     };
 
-    const long long t_cta0 = (kTiming && timing != nullptr) ? clock64() : 0;
     if (warp < 4) {
         // =========================================================================================== control warps
         reg_dec<kRegsCtl>();
@@ -524,7 +533,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         tile_row_inv<WS>(r, wslot, tok);
         constexpr int CPH = CF::NCHUNK / 2;                 // 8-channel chunks per thread (half of the row)
         static_assert(CF::NCHUNK % 2 == 0, "C must be a multiple of 16");
-        constexpr int LB = 4;                               // chunks per load batch (32 loads in flight)
+        constexpr int LB = MWA_WS_LB;                       // chunks per load batch (8 * LB loads in flight per thread)
         uint32_t pk[CPH][4];
         auto row_base = [&](int tile, bool& valid) -> int64_t {      // NCHW element offset of (b, c = 0, py, px)
             const int lidx = tile * CF::WPT + wslot;
@@ -654,18 +663,36 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         }
         const uint32_t tbl0 = sb + MP::oTbl + 4 * (tbl_idx + hh * CF::TBL);
         const TaskAddr<CF> taddr(rbk, hh, lane);
+        // window ids of this warp's tasks, fetched one tile ahead: the list read (L2 latency on a busy LSU) plus the
+        // mask set-up sat on the attention warps' critical path once per tile (~2.5 k cycles, tools/phase_times.py)
+        int win_next[TPW];
+        auto fetch_wins = [&](int tile) {
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+                const int lidx = tile * CF::WPT + w0 + i;
+                win_next[i] = (geo.shift > 0) ? __ldg(list + (lidx < count ? lidx : count - 1)) : 0;
+            }
+        };
+        if (my_tiles > 0) fetch_wins(blockIdx.x);
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             // SW-MSA region mask bits of this warp's rows (:194-216); zero unless the window touches the wrapped border
             uint32_t rowmask[TPW][2];
             uint32_t mask_any = 0;
+            int win_cur[TPW];
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) win_cur[i] = win_next[i];
+            if (MWA_WS_MASK_PREFETCH && it + 1 < my_tiles) fetch_wins(tile + gridDim.x);
 #pragma unroll
             for (int i = 0; i < TPW; ++i) {
                 rowmask[i][0] = rowmask[i][1] = 0u;
                 if (geo.shift > 0) {
-                    const int lidx = tile * CF::WPT + w0 + i;
                     int tb_, twy, twx;
-                    window_coords(geo, list[lidx < count ? lidx : count - 1], tb_, twy, twx);
+                    if (!MWA_WS_MASK_PREFETCH) {
+                        const int lidx = tile * CF::WPT + w0 + i;
+                        win_cur[i] = list[lidx < count ? lidx : count - 1];
+                    }
+                    window_coords(geo, win_cur[i], tb_, twy, twx);
                     if ((twy == geo.nwy - 1) || (twx == geo.nwx - 1)) {
                         mask_any |= 1u << i;
                         const int ys0 = twy * WS, xs0 = twx * WS;
@@ -687,6 +714,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     }
                 }
             }
+            tick(20);                                                            // 20: per-tile set-up (mask bits)
             for (int g = 0; g < NG; ++g) {
                 const int G = it * NG + g, b = G % MP::kDqBufs, ob = G % MP::kOBufs;
                 mbar_wait(bars + MP::bDqFull + b, (G / MP::kDqBufs) & 1);
@@ -737,7 +765,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kAllocWarp) tmem_dealloc<512>(tm);
-    if constexpr (kTiming) {      // per-CTA totals: [64 + cta] cycles, [64 + 256 + cta] tiles (buffer of 1024 u64)
+    if constexpr (kTiming) {      // per-CTA totals: [64 + cta] cycles, [64 + 256 + cta] tiles (buffer of 4096 u64)
         if (timing != nullptr && tid == 0) {
             timing[64 + blockIdx.x] = static_cast<unsigned long long>(clock64() - t_cta0);
             timing[64 + 256 + blockIdx.x] = my_tiles;

@@ -117,7 +117,7 @@ MWA_API int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* pro
                 const float* bias_table, int C, int heads, int ws, float scale, void* params,
                 int64_t params_bytes, void* stream);
 MWA_API int64_t mwa_workspace_bytes(int B, int H, int W, int ws);
-/* development aid: device buffer of 1024 uint64 that the tcgen05 attention kernels fill with clock64() totals
+/* development aid: device buffer of 4096 uint64 that the tcgen05 attention kernels fill with clock64() totals
  * ([0,32): per-stage totals of CTA 0; [64,320): cycles per CTA; [320,576): tiles per CTA).  NULL switches it off
  * (the default). */
 MWA_API void mwa_debug_set_timing_buffer(void* device_u64x32);

@@ -163,7 +163,11 @@ if __name__ == "__main__":
     ap.add_argument("what", nargs="*", default=["gdn", "attn", "round"])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-simt", action="store_true", help="skip the (slow) fp32 SIMT attention kernel")
+    ap.add_argument("--lib", default=None, help="development: time a variant library (tools/build_variants.py)")
     args = ap.parse_args()
+    if args.lib:
+        pkg._abi.LIB_PATH = os.path.abspath(args.lib)
+        print(f"variant library {args.lib}")
     dev = torch.device("cuda:0")
     flush = torch.zeros(128 * 1024 * 1024, device=dev)
     for w in args.what:
