@@ -68,12 +68,27 @@ def synthetic_alpha(batch: int, seed0: int) -> torch.Tensor:
     return out
 
 
+def _host_pyramid(alpha: torch.Tensor, levels: int = 6):
+    """me1..me6 of the synthetic alpha (plain torch on the host: input generation, layers/SupplyMask.py:10-18)"""
+    out, a = [], alpha
+    for _ in range(levels):
+        a = torch.nn.functional.avg_pool2d(a, 3, stride=2, padding=1)
+        out.append(a)
+    return out
+
+
+def _host_kept_windows(alpha: torch.Tensor, ws: int, s: int) -> torch.Tensor:
+    """bool (B * nW,): which windows of the cyclically shifted alpha are not all-zero (bookkeeping for the FLOP count)"""
+    B, _, H, W = alpha.shape
+    a = torch.roll(alpha[:, 0], shifts=(-s, -s), dims=(1, 2)) if s > 0 else alpha[:, 0]
+    return (a.reshape(B, H // ws, ws, W // ws, ws) != 0).any(dim=4).any(dim=2).reshape(-1)
+
+
 def build_workload(pkg, dev, batch: int, seed0: int):
     """modules with random-init weights (torch.manual_seed(234), the scripts' default) + synthetic inputs"""
-    from oracle import ref_ops as R
     torch.manual_seed(234)
     alpha = synthetic_alpha(batch, seed0)
-    pyr = R.alpha_pyramid(alpha)                      # me1..me6 (CPU, input generation only)
+    pyr = _host_pyramid(alpha)                        # me1..me6 (CPU, input generation only)
     gen = torch.Generator().manual_seed(seed0 + 999)
     ops = []
     for name, C, heads, ws, shift, div, lvl in ATTN_SITES:
@@ -82,7 +97,7 @@ def build_workload(pkg, dev, batch: int, seed0: int):
             m.attn.relative_position_bias_table.normal_(0, 0.02, generator=gen)
         x = torch.randn(batch, C, IMG_H // div, IMG_W // div, generator=gen)
         a = pyr[lvl].contiguous()
-        keep = R.window_keep(a, ws, shift)
+        keep = _host_kept_windows(a, ws, shift)
         ops.append(dict(kind="attn", name=name, mod=m.to(dev), x=x, alpha=a, kept=int(keep.sum()),
                         windows=int(keep.numel()), C=C, ws=ws, heads=heads, shift=shift))
     for name, div, inverse in GDN_SITES:

@@ -5,6 +5,7 @@ The reference imports its hot-path layers by module name:
     layers/Attention.py:6          from .win_attention import *
     layers/TransformRGB.py:4       from .GDN import *          (also layers/SupplyMask.py:4)
     layers/TransformRGB.py:10      from .Masked_Attention import *   (optional: the wrapper with the fused gate)
+    models/*.py:3                  from layers.SupplyMask import *   (optional: the alpha pyramid in two launches)
 `install(reference_root)` puts the reference tree on sys.path and pre-seeds `sys.modules` with this
 package's drop-ins under those three names, so every later `import layers.X` / `from .X import *`
 inside the reference resolves to the CUDA-backed modules.  `patch_model_rounding(model_module)`
@@ -24,9 +25,11 @@ import types
 _DROPINS = ("GDN", "masked_win_attention", "win_attention")
 
 
-def install(reference_root: str, extra_paths=(), fuse_gate: bool = True) -> None:
+def install(reference_root: str, extra_paths=(), fuse_gate: bool = True, fuse_pyramid: bool = True) -> None:
     """fuse_gate: also replace `layers.Masked_Attention` (the Win_noShift_Attention wrapper, layers/TransformRGB.py:10)
-    with the drop-in whose gate `a * sigmoid(b) + x` is one fused kernel (same state-dict keys)."""
+    with the drop-in whose gate `a * sigmoid(b) + x` is one fused kernel (same state-dict keys).
+    fuse_pyramid: also replace `layers.SupplyMask` (the alpha pyramid, layers/SupplyMask.py:7-18) with the two-launch
+    CUDA pyramid (bit-exact with the six AvgPool2d calls)."""
     reference_root = os.path.abspath(reference_root)
     if not os.path.isdir(os.path.join(reference_root, "layers")):
         raise FileNotFoundError(f"{reference_root} does not look like the reference tree (no layers/)")
@@ -44,7 +47,7 @@ def install(reference_root: str, extra_paths=(), fuse_gate: bool = True) -> None
         sys.modules["layers"] = pkg
     # ... but whose three hot-path submodules are ours.
     ours = importlib.import_module(__package__ + ".layers")
-    for name in _DROPINS + (("Masked_Attention",) if fuse_gate else ()):
+    for name in _DROPINS + (("Masked_Attention",) if fuse_gate else ()) + (("SupplyMask",) if fuse_pyramid else ()):
         mod = importlib.import_module(f"{__package__}.layers.{name}")
         sys.modules[f"layers.{name}"] = mod
         setattr(sys.modules["layers"], name, mod)
@@ -65,5 +68,5 @@ def patch_model_rounding(model_module) -> None:
 
 
 def uninstall() -> None:
-    for name in ("layers",) + tuple(f"layers.{n}" for n in _DROPINS + ("Masked_Attention",)):
+    for name in ("layers",) + tuple(f"layers.{n}" for n in _DROPINS + ("Masked_Attention", "SupplyMask")):
         sys.modules.pop(name, None)

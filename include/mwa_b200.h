@@ -200,6 +200,21 @@ MWA_API int gate_residual_forward(const float* a, const float* b, const float* x
 MWA_API int gate_residual_backward(const float* a, const float* b, const float* grad_out, float* grad_a, float* grad_b,
                                    int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Alpha pyramid (Appendix A "Alpha pyramid feeding a1")   replaces  layers/SupplyMask.py:7-18
+ *   (SupplyMaskToTransform.forward: six cascaded AvgPool2d(3, stride 2, padding 1), count_include_pad) and, with
+ *   quant_levels > 0, the decoder's mask quantisation in front of it (models/AutoEncoderRGB_Journal.py:212-214:
+ *   reconmask = round(reconmask * 255) / 255).  Three levels per launch (halo recomputed in shared memory).
+ * alpha  : (B, H, W) fp32 plane (the reference's (B, 1, H, W)), contiguous
+ * recon  : NULL, or (B, H, W): receives the quantised plane when quant_levels > 0
+ * levels : packed output, level k (1-based) = (B, H_k, W_k) at element offset alpha_pyramid_level_offset(B, H, W, k - 1),
+ *          H_k = (H_{k-1} - 1) / 2 + 1; total elements = alpha_pyramid_level_offset(B, H, W, nlevels);  1 <= nlevels <= 6
+ * Each output is the row-major fp32 sum of its in-range taps divided by 9 (bit-exact with torch.nn.AvgPool2d).
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int64_t alpha_pyramid_level_offset(int B, int H, int W, int level);
+MWA_API int alpha_pyramid_forward(const float* alpha, float* recon, float* levels, int B, int H, int W, int nlevels,
+                                  int quant_levels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

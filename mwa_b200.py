@@ -20,6 +20,7 @@ GDN_mod = importlib.import_module(PACKAGE_NAME + ".layers.GDN")
 masked_win_attention = importlib.import_module(PACKAGE_NAME + ".layers.masked_win_attention")
 win_attention = importlib.import_module(PACKAGE_NAME + ".layers.win_attention")
 Masked_Attention = importlib.import_module(PACKAGE_NAME + ".layers.Masked_Attention")
+SupplyMask = importlib.import_module(PACKAGE_NAME + ".layers.SupplyMask")
 data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
 
 GDN = GDN_mod.GDN
@@ -29,6 +30,8 @@ WinBasedAttention = win_attention.WinBasedAttention
 WindowAttention = masked_win_attention.WindowAttention
 Win_noShift_Attention = Masked_Attention.Win_noShift_Attention
 gate_residual = Masked_Attention.gate_residual
+SupplyMaskToTransform = SupplyMask.SupplyMaskToTransform
+alpha_pyramid = SupplyMask.alpha_pyramid
 ste_round = quant.ste_round
 quantize_offset = quant.quantize_offset
 lrp_add = quant.lrp_add

@@ -114,6 +114,27 @@ def wrapper_inputs(cfg):
     return dict(x=x, alpha=alpha, state=state)
 
 
+PYRAMID_CASES = {
+    # SupplyMaskToTransform on (B, 1, H, W): even sizes, odd sizes (windows hang over the right / bottom padding), tiny
+    "pyr_2x64x96": dict(B=2, H=64, W=96, seed=51),
+    "pyr_1x37x53": dict(B=1, H=37, W=53, seed=52),
+    "pyr_3x5x7": dict(B=3, H=5, W=7, seed=53),
+    "pyr_1x130x70": dict(B=1, H=130, W=70, seed=54),
+}
+
+
+def pyramid_inputs(cfg):
+    """alpha: k/255 values with all-zero and all-one regions (what the dataset feeds); raw: un-quantised values in
+    [0, 1] (what the mask decoder emits before models/AutoEncoderRGB_Journal.py:212-214 rounds them)"""
+    g = _gen(cfg["seed"])
+    B, H, W = cfg["B"], cfg["H"], cfg["W"]
+    raw = torch.rand(B, 1, H, W, generator=g)
+    raw[:, :, : H // 3, : W // 2] = 0.0
+    raw[:, :, H - H // 4:, W - W // 3:] = 1.0
+    alpha = torch.round(raw * 255) / 255
+    return dict(alpha=alpha, raw=raw)
+
+
 GDN_CASES = {
     "gdn_c192": dict(C=192, B=2, H=8, W=12, inverse=False, seed=21),
     "igdn_c192": dict(C=192, B=2, H=8, W=12, inverse=True, seed=22),

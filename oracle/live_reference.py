@@ -24,6 +24,7 @@ class _RefModules:
         self.unmasked = importlib.import_module("layers.win_attention")
         self.gdn = importlib.import_module("layers.GDN")
         self.wrapper = importlib.import_module("layers.Masked_Attention")
+        self.supply = importlib.import_module("layers.SupplyMask")
 
     def model(self, which: str):
         """'rgb' -> models.AutoEncoderRGB_Journal, 'mask' -> models.AutoEncoderMask_Journal."""

@@ -96,6 +96,24 @@ def make_wrapper(ref):
     return out
 
 
+def make_pyramid(ref):
+    out = {}
+    sm = ref.supply.SupplyMaskToTransform()
+    for name, cfg in G.PYRAMID_CASES.items():
+        p = G.pyramid_inputs(cfg)
+        for k, lvl in enumerate(sm(p["alpha"]), 1):
+            out[f"{name}/mask{k}"] = _np(lvl)
+        # decoder side: models/AutoEncoderRGB_Journal.py:212-215
+        recon = p["raw"] * 255
+        recon = torch.round(recon)
+        recon = recon / 255
+        out[name + "/recon"] = _np(recon)
+        for k, lvl in enumerate(sm(recon), 1):
+            out[f"{name}/md{k}"] = _np(lvl)
+        out[name + "/crc"] = np.array(G.checksum(p["alpha"], p["raw"]), dtype=np.int64)
+    return out
+
+
 def make_rounding(ref):
     p = G.rounding_inputs()
     rgb = ref.model("rgb")
@@ -116,7 +134,7 @@ def main():
     import sys
     only = set(sys.argv[1:])
     makers = (("attention.npz", make_attention), ("gdn.npz", make_gdn), ("rounding.npz", make_rounding),
-              ("wrapper.npz", make_wrapper))
+              ("wrapper.npz", make_wrapper), ("pyramid.npz", make_pyramid))
     for fname, data in ((f, mk(ref)) for f, mk in makers if not only or f in only):
         path = os.path.join(OUT_DIR, fname)
         np.savez_compressed(path, **data)

@@ -29,7 +29,7 @@ def lib(pkg):
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
-    return {k: np.load(os.path.join(GOLDEN, k + ".npz")) for k in ("attention", "gdn", "rounding", "wrapper")}
+    return {k: np.load(os.path.join(GOLDEN, k + ".npz")) for k in ("attention", "gdn", "rounding", "wrapper", "pyramid")}
 
 
 @pytest.fixture(scope="session")

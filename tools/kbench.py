@@ -158,6 +158,47 @@ def bench_round(args, dev, flush):
               f"{byts / med / 1e6 / PEAKS['hbm_gbs'] * 100:5.1f}% HBM", flush=True)
 
 
+def bench_pyramid(args, dev, flush):
+    """alpha pyramid (+ mask quantisation) at the BASELINE config-2 shape vs the reference's op sequence in torch"""
+    a = torch.rand(16, 1, 512, 768, device=dev)
+    pool = torch.nn.AvgPool2d(3, stride=2, padding=1)
+
+    def eager():
+        r = torch.round(a * 255) / 255
+        out, m = [], r
+        for _ in range(6):
+            m = pool(m)
+            out.append(m)
+        return r, out
+    def graphed(fn, reps=10):
+        """device time of one call: `reps` calls captured into one CUDA graph (these ops are shorter than the host
+        takes to issue them, so event timing of eager calls would measure Python)"""
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for _ in range(reps):
+                    keep = fn()
+        med, best = timeit(gr.replay, args.iters, flush)
+        return med / reps, best / reps
+    med, best = graphed(lambda: pkg.alpha_pyramid(a, 6, quant_levels=255))
+    med_e, best_e = graphed(eager)
+    r0, l0 = pkg.alpha_pyramid(a, 6, quant_levels=255)
+    r1, l1 = eager()
+    r2 = torch.round(a.cpu() * 255) / 255
+    l2, m = [], r2
+    for _ in range(6):
+        m = pool(m)
+        l2.append(m)
+    same_cpu = torch.equal(r0.cpu(), r2) and all(torch.equal(x.cpu(), y) for x, y in zip(l0, l2))
+    diff_gpu = max((x - y).abs().max().item() for x, y in zip(l0, l1))
+    nbytes = a.numel() * 4 * 2 + sum(x.numel() for x in l0) * 4
+    print(f"alpha pyramid 16x1x512x768 (quantise + 6 levels), device time from a CUDA graph of 10 calls: 2 launches "
+          f"{med * 1e3:6.1f} us ({nbytes / med / 1e6:6.0f} GB/s);  torch eager op sequence (9 launches) {med_e * 1e3:6.1f} us;  "
+          f"bit-identical with torch CPU: {same_cpu};  max |diff| vs torch CUDA: {diff_gpu:.1e}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="*", default=["gdn", "attn", "round"])
@@ -171,4 +212,4 @@ if __name__ == "__main__":
     dev = torch.device("cuda:0")
     flush = torch.zeros(128 * 1024 * 1024, device=dev)
     for w in args.what:
-        {"gdn": bench_gdn, "attn": bench_attn, "round": bench_round, "gate": bench_gate}[w](args, dev, flush)
+        {"gdn": bench_gdn, "attn": bench_attn, "round": bench_round, "gate": bench_gate, "pyramid": bench_pyramid}[w](args, dev, flush)
