@@ -26,6 +26,11 @@
 namespace b200 {
 namespace {
 
+// Register budget: the file is 4 x 16 K registers, one quarter per SM sub-partition, and a CTA's pool is what its launch
+// bound allocates: 5 warps per sub-partition x 32 x 96 = 15,360 of 16,384 (the next multiple of 8 above 96 does not fit).
+// setmaxnreg only moves registers inside that pool: 32 (control) + 2 x 96 (producer) + 2 x 128 (attention) per
+// sub-partition uses it up exactly.  A 21st "donor" warp does not help: it lands as a 6th warp on one sub-partition and
+// ptxas lowers the launch allocation to 80 (checked), shrinking the pool.
 constexpr int kWsWarps = 20;
 constexpr int kWsThreads = kWsWarps * 32;
 constexpr int kMmaWarp = 0, kWgtWarp = 1, kAllocWarp = 2;

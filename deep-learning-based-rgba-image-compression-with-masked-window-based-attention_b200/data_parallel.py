@@ -39,40 +39,48 @@ class GradientAllReduce:
         if cur:
             self.buckets.append(cur)
         self._flat: list[torch.Tensor | None] = [None] * len(self.buckets)
+        self._view_cache: list[list[torch.Tensor]] = [[] for _ in self.buckets]
 
     @property
     def bytes_per_step(self) -> int:
         return sum(p.numel() * p.element_size() for p in self.params)
 
+    def _views(self, i: int):
+        """flat buffer of bucket i and one view per parameter (shaped like it)"""
+        bucket = self.buckets[i]
+        n = sum(p.numel() for p in bucket)
+        if self._flat[i] is None or self._flat[i].numel() != n:
+            flat = torch.empty(n, dtype=bucket[0].dtype, device=bucket[0].device)
+            views, off = [], 0
+            for p in bucket:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._flat[i] = flat
+            self._view_cache[i] = views
+        return self._flat[i], self._view_cache[i]
+
     def __call__(self) -> None:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         works = []
         for i, bucket in enumerate(self.buckets):
-            n = sum(p.numel() for p in bucket)
-            if self._flat[i] is None or self._flat[i].numel() != n:
-                self._flat[i] = torch.empty(n, dtype=bucket[0].dtype, device=bucket[0].device)
-            flat, off = self._flat[i], 0
-            for p in bucket:
-                seg = flat[off:off + p.numel()]
+            flat, views = self._views(i)
+            have = [(v, p.grad) for v, p in zip(views, bucket) if p.grad is not None]
+            for v, p in zip(views, bucket):
                 if p.grad is None:
-                    seg.zero_()          # a rank that did not touch p still takes part in the reduction
-                else:
-                    seg.copy_(p.grad.reshape(-1))
-                off += p.numel()
+                    v.zero_()            # a rank that did not touch p still takes part in the reduction
+            if have:                     # one multi-tensor copy instead of a launch per parameter
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
             works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                          if world > 1 else None)
         for i, bucket in enumerate(self.buckets):
             if works[i] is not None:
                 works[i].wait()
-            flat, off = self._flat[i], 0
+            flat, views = self._views(i)
             if world > 1:
                 flat.mul_(1.0 / world)
             if self.clip_value is not None:
                 flat.clamp_(-self.clip_value, self.clip_value)
-            for p in bucket:
-                seg = flat[off:off + p.numel()].view_as(p)
+            for v, p in zip(views, bucket):
                 if p.grad is None:
-                    p.grad = seg.clone()
-                else:
-                    p.grad.copy_(seg)
-                off += p.numel()
+                    p.grad = v.clone()
+            torch._foreach_copy_([p.grad for p in bucket], views)
