@@ -119,6 +119,34 @@ alpha_pyramid3_kernel(const float* __restrict__ src, float* __restrict__ recon, 
     }
 }
 
+// Isolated-pixel clean-up of the decoded mask (reference trainRGB.py:98-111 = trainmask.py:133-146 `constraint`), with the
+// clamp + quantisation that precedes it at its call site (trainRGB.py:285-287) folded in when quant > 0:
+//   m = round(clamp(m, 0, 1) * quant) / quant ;  s = sum of the 8 neighbours (zero padding)
+//   out = 1 if (m == 0 and s == 8);  0 if (m > 0 and s == 0);  m otherwise
+// The reference does it with a convolution, two boolean masks and two masked assignments (host-synchronising
+// index_put); both masks are taken from the tensor BEFORE either assignment, so it is a pure 3 x 3 stencil.
+__global__ void __launch_bounds__(256)
+mask_constraint_kernel(const float* __restrict__ m, float* __restrict__ out, int H, int W, float quant, int64_t total) {
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int x = int(idx % W), y = int((idx / W) % H);
+    const float* plane = m + (idx - int64_t(y) * W - x);
+    auto at = [&](int yy, int xx) -> float {
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
+        float v = __ldg(plane + int64_t(yy) * W + xx);
+        if (quant > 0.f) v = __fdiv_rn(rintf(__fmul_rn(fminf(fmaxf(v, 0.f), 1.f), quant)), quant);
+        return v;
+    };
+    float s = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+            if (dy != 0 || dx != 0) s += at(y + dy, x + dx);
+    const float c = at(y, x);
+    out[idx] = (c == 0.f && s == 8.f) ? 1.f : ((c > 0.f && s == 0.f) ? 0.f : c);
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -166,6 +194,18 @@ int alpha_pyramid_forward(const float* alpha, float* recon, float* levels, int B
         out = l3 + int64_t(B) * h3 * w3;
     }
     return MWA_OK;
+}
+
+int mask_constraint_forward(const float* mask, float* out, int B, int H, int W, int quant_levels, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || quant_levels < 0) return MWA_ERR_INVALID;
+    if (B == 0) return MWA_OK;
+    if (!mask || !out || mask == out) return MWA_ERR_INVALID;          // a stencil cannot run in place
+    const int64_t total = int64_t(B) * H * W;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffll) return MWA_ERR_UNSUPPORTED;
+    mask_constraint_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask, out, H, W, float(quant_levels), total);
+    return check_launch("mask_constraint_forward");
 }
 
 }  // extern "C"

@@ -51,6 +51,27 @@ def alpha_pyramid(alpha: torch.Tensor, nlevels: int = 6, quant_levels: int = 0):
     return (recon if recon is not None else alpha), levels
 
 
+def constraint(tensor: torch.Tensor, quant_levels: int = 0) -> torch.Tensor:
+    """Isolated-pixel clean-up of the decoded mask (reference trainRGB.py:98-111): a zero whose 8 neighbours sum to 8
+    becomes 1, a positive value whose neighbours sum to 0 becomes 0.  Like the reference it updates `tensor` in place and
+    returns it; one launch and no host synchronisation instead of conv2d + two boolean-mask assignments.
+    quant_levels > 0 folds in the `round(clamp(t, 0, 1) * q) / q` the scripts run just before (trainRGB.py:285-286)."""
+    lib = _abi.load()
+    _abi.require_cuda_f32(tensor, "constraint input")
+    if tensor.dim() != 4:
+        raise RuntimeError(f"constraint expects (B, C, H, W), got {tuple(tensor.shape)}")
+    B, C, H, W = tensor.shape
+    src = tensor.detach().contiguous()
+    out = torch.empty_like(src)
+    if src.numel():
+        with torch.cuda.device(tensor.device):
+            _abi.check(lib.mask_constraint_forward(src.data_ptr(), out.data_ptr(), B * C, H, W, int(quant_levels),
+                                                   _abi.stream_handle()), "mask_constraint_forward")
+    with torch.no_grad():
+        tensor.copy_(out)
+    return tensor
+
+
 class SupplyMaskToTransform(nn.Module):
     """Same constructor and return value as the reference (:7-18); only the 3 x 3 kernel it is built with is supported."""
 

@@ -215,6 +215,13 @@ MWA_API int64_t alpha_pyramid_level_offset(int B, int H, int W, int level);
 MWA_API int alpha_pyramid_forward(const float* alpha, float* recon, float* levels, int B, int H, int W, int nlevels,
                                   int quant_levels, void* stream);
 
+/* Isolated-pixel clean-up of the decoded mask   replaces  trainRGB.py:98-111 / trainmask.py:133-146 (`constraint`) and,
+ * with quant_levels > 0, the clamp + quantisation in front of it at its call site (trainRGB.py:285-287):
+ *   m = round(clamp(m, 0, 1) * q) / q;  s = sum of the 8 neighbours (zero padding);
+ *   out = 1 if (m == 0 && s == 8), 0 if (m > 0 && s == 0), m otherwise.      mask, out: (B, H, W) fp32, out != mask.
+ * One launch, no host synchronisation (the reference's boolean-mask assignments synchronise twice). */
+MWA_API int mask_constraint_forward(const float* mask, float* out, int B, int H, int W, int quant_levels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ Win_noShift_Attention = Masked_Attention.Win_noShift_Attention
 gate_residual = Masked_Attention.gate_residual
 SupplyMaskToTransform = SupplyMask.SupplyMaskToTransform
 alpha_pyramid = SupplyMask.alpha_pyramid
+constraint = SupplyMask.constraint
 ste_round = quant.ste_round
 quantize_offset = quant.quantize_offset
 lrp_add = quant.lrp_add

@@ -123,6 +123,20 @@ PYRAMID_CASES = {
 }
 
 
+def constraint_inputs(cfg):
+    """binary masks with isolated holes / specks (also on the border), and a soft k/255 variant + the raw decoder output
+    (values outside [0, 1]) that trainRGB.py:285-286 clamps and quantises first"""
+    g = _gen(cfg["seed"] + 7)
+    B, H, W = cfg["B"], cfg["H"], cfg["W"]
+    binary = (torch.rand(B, 1, H, W, generator=g) < 0.5).float()
+    binary[:, :, : H // 2, : W // 2] = 1.0
+    binary[:, :, H // 2:, W // 2:] = 0.0
+    holes = torch.rand(B, 1, H, W, generator=g) < 0.05
+    binary = torch.where(holes, 1.0 - binary, binary)
+    raw = binary + 0.3 * torch.randn(B, 1, H, W, generator=g) * (torch.rand(B, 1, H, W, generator=g) < 0.3)
+    return dict(binary=binary, raw=raw)
+
+
 def pyramid_inputs(cfg):
     """alpha: k/255 values with all-zero and all-one regions (what the dataset feeds); raw: un-quantised values in
     [0, 1] (what the mask decoder emits before models/AutoEncoderRGB_Journal.py:212-214 rounds them)"""

@@ -26,6 +26,17 @@ class _RefModules:
         self.wrapper = importlib.import_module("layers.Masked_Attention")
         self.supply = importlib.import_module("layers.SupplyMask")
 
+    def script(self, which: str = "trainRGB"):
+        """the training / evaluation script as a module (its argparse runs in main() only); its module-level `device`
+        is the hard-coded 'cuda:0' (trainRGB.py:31) -- set to 'cpu' so that `constraint` runs in this container"""
+        argv, sys.argv = sys.argv, [which]
+        try:
+            mod = importlib.import_module(which)
+        finally:
+            sys.argv = argv
+        mod.device = "cpu"
+        return mod
+
     def model(self, which: str):
         """'rgb' -> models.AutoEncoderRGB_Journal, 'mask' -> models.AutoEncoderMask_Journal."""
         name = {"rgb": "models.AutoEncoderRGB_Journal", "mask": "models.AutoEncoderMask_Journal"}[which]

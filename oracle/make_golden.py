@@ -111,6 +111,14 @@ def make_pyramid(ref):
         for k, lvl in enumerate(sm(recon), 1):
             out[f"{name}/md{k}"] = _np(lvl)
         out[name + "/crc"] = np.array(G.checksum(p["alpha"], p["raw"]), dtype=np.int64)
+        # constraint (trainRGB.py:98-111) on a binary mask, and the evaluation chain of trainRGB.py:285-287 on raw values
+        script = ref.script("trainRGB")
+        c = G.constraint_inputs(cfg)
+        out[name + "/constraint_binary"] = _np(script.constraint(c["binary"].clone()))
+        m = torch.clamp(c["raw"], 0, 1)
+        m = torch.round(m * 255) / 255
+        out[name + "/constraint_chain"] = _np(script.constraint(m))
+        out[name + "/crc_c"] = np.array(G.checksum(c["binary"], c["raw"]), dtype=np.int64)
     return out
 
 

@@ -283,6 +283,19 @@ def alpha_pyramid(alpha, levels: int = 6):
     return out
 
 
+def constraint(t):
+    """isolated-pixel clean-up of the decoded mask (trainRGB.py:98-111 = trainmask.py:133-146): both masks are taken from
+    the tensor before either assignment; returns a new tensor"""
+    kernel = torch.ones(1, 1, 3, 3, dtype=t.dtype)
+    kernel[0, 0, 1, 1] = 0
+    B, C, H, W = t.shape
+    nsum = torch.nn.functional.conv2d(t.reshape(B * C, 1, H, W), kernel, padding=1).reshape(B, C, H, W)
+    out = t.clone()
+    out[(t == 0) & (nsum == 8)] = 1
+    out[(t > 0) & (nsum == 0)] = 0
+    return out
+
+
 def flops_per_window(C: int, ws: int) -> int:
     N = ws * ws
     return 8 * N * C * C + 4 * N * N * C

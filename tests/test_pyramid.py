@@ -84,3 +84,45 @@ def test_pyramid_feeds_attention_like_the_reference_wiring(pkg, cuda_dev):
     want = R.alpha_pyramid(alpha)
     for lvl, ws, s in ((1, 8, 4), (2, 4, 2)):
         assert torch.equal(R.window_keep(masks[lvl].cpu(), ws, s), R.window_keep(want[lvl], ws, s))
+
+
+# ------------------------------------------------------------------------------------------------ constraint
+@pytest.mark.parametrize("name", list(G.PYRAMID_CASES))
+def test_oracle_constraint_matches_reference(golden, name):
+    c = G.constraint_inputs(G.PYRAMID_CASES[name])
+    g = golden["pyramid"]
+    assert int(g[name + "/crc_c"]) == G.checksum(c["binary"], c["raw"])
+    assert torch.equal(R.constraint(c["binary"]), _t(g[name + "/constraint_binary"]))
+    assert not torch.equal(R.constraint(c["binary"]), c["binary"]) or c["binary"].numel() < 64   # the cases do fire
+    m = R.quantize_levels(torch.clamp(c["raw"], 0, 1), 255)
+    assert torch.equal(R.constraint(m), _t(g[name + "/constraint_chain"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(G.PYRAMID_CASES))
+def test_cuda_constraint_bit_exact_vs_golden(pkg, cuda_dev, golden, name):
+    c = G.constraint_inputs(G.PYRAMID_CASES[name])
+    g = golden["pyramid"]
+    t = c["binary"].to(cuda_dev)
+    r = pkg.constraint(t)
+    assert r is t                                          # in place, like the reference
+    assert torch.equal(t.cpu(), _t(g[name + "/constraint_binary"]))
+    chain = pkg.constraint(c["raw"].to(cuda_dev), quant_levels=255)      # clamp + quantise + clean-up in one launch
+    assert torch.equal(chain.cpu(), _t(g[name + "/constraint_chain"]))
+
+
+@pytest.mark.gpu
+def test_cuda_constraint_full_size_properties(pkg, cuda_dev):
+    """BASELINE size (16, 1, 512, 768): idempotent on its own output for binary masks without adjacent defects, and equal
+    to the oracle"""
+    g = torch.Generator().manual_seed(3)
+    m = (torch.rand(16, 1, 512, 768, generator=g) < 0.5).float()
+    want = R.constraint(m)
+    got = pkg.constraint(m.to(cuda_dev).clone())
+    assert torch.equal(got.cpu(), want)
+    solid = torch.ones(2, 1, 64, 64)
+    solid[:, :, 10, 10] = 0
+    solid[:, :, 0, 5] = 0                                   # border pixel: only 5 neighbours -> stays
+    out = pkg.constraint(solid.to(cuda_dev).clone()).cpu()
+    assert out[0, 0, 10, 10] == 1 and out[0, 0, 0, 5] == 0
+    assert torch.equal(pkg.constraint(out.to(cuda_dev).clone()).cpu(), out)
