@@ -378,6 +378,66 @@ __host__ __device__ inline int64_t bwd_core_smem_floats(int C, int heads, int ws
     return 2 * N * (3 * d + 1) + N * (d + 1) + 2 * N * (N + 1) + heads * tbl + 8;
 }
 
+// ---- register-tiled products for the 8 x 8-window case (N = 64), 256 threads.  The plain loops below issue two shared
+//      loads per FMA and are LDS-bound; these tiles issue 0.5 (N x N outputs, 4 x 4 per thread) / 0.58 (N x D outputs,
+//      4 x D/8 per thread on half of the CTA, so two independent products run side by side).
+// out(i, j) = sum_c A[i][c] * B[j][c], i, j < 64: thread (ti, tj) owns rows ti + 16 a, columns tj + 16 b (rows of B at a
+// stride of 3D+1 or D+1 floats fall into distinct banks; A is a broadcast)
+template <int D, class Epi>
+__device__ __forceinline__ void tile_nn64(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int tid,
+                                          Epi epi) {
+    const int tj = tid & 15, ti = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D; ++c) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = A[(ti + 16 * a) * lda + c];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = B[(tj + 16 * b) * ldb + c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) epi(ti + 16 * a, tj + 16 * b, acc[a][b]);
+}
+// out(r, c) = sum_n P(r, n) * G[n][c]  (kTrans = false)   or   sum_n P(n, r) * G[n][c]  (kTrans = true),  r < 64, c < D;
+// P has a row stride of 65 floats.  t = thread index inside a 128-thread half: rows rg + 16 a, columns cg + 8 cc.
+template <int D, bool kTrans, class Epi>
+__device__ __forceinline__ void tile_nd64(const float* __restrict__ P, const float* __restrict__ G, int ldg, int t, Epi epi) {
+    constexpr int CT = D / 8, LDS_ = 65;
+    const int cg = t & 7, rg = t >> 3;
+    float acc[4][CT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) acc[a][cc] = 0.f;
+#pragma unroll 4
+    for (int n = 0; n < 64; ++n) {
+        float pv[4], gv[CT];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) pv[a] = kTrans ? P[n * LDS_ + rg + 16 * a] : P[(rg + 16 * a) * LDS_ + n];
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) gv[cc] = G[n * ldg + cg + 8 * cc];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int cc = 0; cc < CT; ++cc) acc[a][cc] = fmaf(pv[a], gv[cc], acc[a][cc]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) epi(rg + 16 * a, cg + 8 * cc, acc[a][cc]);
+}
+
 __global__ void __launch_bounds__(256)
 mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__ dao_tok, const uint8_t* __restrict__ blk,
                     const float* __restrict__ ext_mask, const uint8_t* __restrict__ flags, float* __restrict__ ao_tok,
@@ -396,17 +456,22 @@ mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__
     const float scale = reinterpret_cast<const float*>(blk + L.header)[0];
     const float* bias = reinterpret_cast<const float*>(blk + L.bias);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fast = (N == 64 && (d == 24 || d == 32)) ? d : 0;        // register-tiled products (tile_nn64 / tile_nd64)
     for (int i = tid; i < heads * TBL; i += kT) tacc[i] = 0.f;
     __syncthreads();
-    for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+    // work unit = (window, head): 8 x finer than a window, so that a few hundred windows still balance over the CTAs
+    for (int64_t unit = blockIdx.x; unit < int64_t(nwin) * heads; unit += gridDim.x) {
+        const int win = static_cast<int>(unit / heads), h = static_cast<int>(unit % heads);
         const int wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
         const int64_t tok0 = int64_t(win) * N;
         if (flags != nullptr && !flags[win]) {
-            for (int e = tid; e < N * C; e += kT) ao_tok[tok0 * C + e] = 0.f;
-            for (int e = tid; e < N * 3 * C; e += kT) dqkv_tok[tok0 * 3 * C + e] = 0.f;
+            if (h == 0) {
+                for (int e = tid; e < N * C; e += kT) ao_tok[tok0 * C + e] = 0.f;
+                for (int e = tid; e < N * 3 * C; e += kT) dqkv_tok[tok0 * 3 * C + e] = 0.f;
+            }
             continue;
         }
-        for (int h = 0; h < heads; ++h) {
+        {
             for (int e = tid; e < N * 3 * d; e += kT) {
                 const int n = e / (3 * d), j = e % (3 * d);
                 const float v = __ldg(qkv_tok + (tok0 + n) * 3 * C + (j / d) * C + h * d + (j % d));
@@ -415,20 +480,26 @@ mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__
             for (int e = tid; e < N * d; e += kT) R2[(e / d) * ld2 + e % d] = __ldg(dao_tok + (tok0 + e / d) * C + h * d + e % d);
             __syncthreads();
             const float* bh = bias + int64_t(h) * N * N;
-            for (int e = tid; e < N * N; e += kT) {
-                const int i = e / N, j = e % N;
-                const float* q = R3 + i * ldh;
-                const float* k = R3 + j * ldh + d;
-                float acc = 0.f;
-                for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
-                acc += __ldg(bh + e);
+            auto logit = [&](int i, int j, float acc) {
+                acc += __ldg(bh + i * N + j);
                 if (g.tokens) {
                     if (g.mask_nw > 0) acc += __ldg(ext_mask + (int64_t(win % g.mask_nw) * N + i) * N + j);
                 } else if (g.shift > 0 && g.region(wy, wx, i) != g.region(wy, wx, j)) {
                     acc += kNegMaskB;
                 }
                 R4[i * lds + j] = acc;
-            }
+            };
+            if (fast == 24) tile_nn64<24>(R3, ldh, R3 + d, ldh, tid, logit);
+            else if (fast == 32) tile_nn64<32>(R3, ldh, R3 + d, ldh, tid, logit);
+            else
+                for (int e = tid; e < N * N; e += kT) {
+                    const int i = e / N, j = e % N;
+                    const float* q = R3 + i * ldh;
+                    const float* k = R3 + j * ldh + d;
+                    float acc = 0.f;
+                    for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
+                    logit(i, j, acc);
+                }
             __syncthreads();
             for (int i = warp; i < N; i += kT / 32) {
                 float* row = R4 + i * lds;
@@ -448,23 +519,38 @@ mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__
                 for (int j = lane; j < N; j += 32) row[j] *= inv;
             }
             __syncthreads();
+            auto put_ao = [&](int i, int c, float v) { ao_tok[(tok0 + i) * C + h * d + c] = v; };
+            auto put_dv = [&](int i, int c, float v) { R6[i * ldh + 2 * d + c] = v; };
+            if (fast) {                 // warps 0-3: AO = P v, warps 4-7: dv = P^T dAO (independent, both read P)
+                if (tid < 128) {
+                    if (fast == 24) tile_nd64<24, false>(R4, R3 + 2 * d, ldh, tid, put_ao);
+                    else tile_nd64<32, false>(R4, R3 + 2 * d, ldh, tid, put_ao);
+                } else {
+                    if (fast == 24) tile_nd64<24, true>(R4, R2, ld2, tid - 128, put_dv);
+                    else tile_nd64<32, true>(R4, R2, ld2, tid - 128, put_dv);
+                }
+            } else
             for (int e = tid; e < N * d; e += kT) {
                 const int i = e / d, c = e % d;
                 const float* p = R4 + i * lds;
                 float acc = 0.f;
                 for (int j = 0; j < N; ++j) acc = fmaf(p[j], R3[j * ldh + 2 * d + c], acc);
-                ao_tok[(tok0 + i) * C + h * d + c] = acc;
+                put_ao(i, c, acc);
                 float dv = 0.f;
                 for (int n = 0; n < N; ++n) dv = fmaf(R4[n * lds + i], R2[n * ld2 + c], dv);
-                R6[i * ldh + 2 * d + c] = dv;
+                put_dv(i, c, dv);
             }
+            auto put_dp = [&](int i, int j, float v) { R5[i * lds + j] = v; };
+            if (fast == 24) tile_nn64<24>(R2, ld2, R3 + 2 * d, ldh, tid, put_dp);
+            else if (fast == 32) tile_nn64<32>(R2, ld2, R3 + 2 * d, ldh, tid, put_dp);
+            else
             for (int e = tid; e < N * N; e += kT) {
                 const int i = e / N, j = e % N;
                 const float* da = R2 + i * ld2;
                 const float* v = R3 + j * ldh + 2 * d;
                 float acc = 0.f;
                 for (int c = 0; c < d; ++c) acc = fmaf(da[c], v[c], acc);
-                R5[i * lds + j] = acc;
+                put_dp(i, j, acc);
             }
             __syncthreads();
             for (int i = warp; i < N; i += kT / 32) {
@@ -475,6 +561,17 @@ mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__
                 for (int j = lane; j < N; j += 32) R5[i * lds + j] = R4[i * lds + j] * (R5[i * lds + j] - dot);
             }
             __syncthreads();
+            auto put_dq = [&](int i, int c, float v) { R6[i * ldh + c] = v * scale; };
+            auto put_dk = [&](int i, int c, float v) { R6[i * ldh + d + c] = v; };
+            if (fast) {                 // warps 0-3: dq = dS k, warps 4-7: dk = dS^T q'
+                if (tid < 128) {
+                    if (fast == 24) tile_nd64<24, false>(R5, R3 + d, ldh, tid, put_dq);
+                    else tile_nd64<32, false>(R5, R3 + d, ldh, tid, put_dq);
+                } else {
+                    if (fast == 24) tile_nd64<24, true>(R5, R3, ldh, tid - 128, put_dk);
+                    else tile_nd64<32, true>(R5, R3, ldh, tid - 128, put_dk);
+                }
+            } else
             for (int e = tid; e < N * d; e += kT) {
                 const int i = e / d, c = e % d;
                 float dq = 0.f, dk = 0.f;
@@ -482,8 +579,8 @@ mwa_bwd_core_kernel(const float* __restrict__ qkv_tok, const float* __restrict__
                     dq = fmaf(R5[i * lds + j], R3[j * ldh + d + c], dq);
                     dk = fmaf(R5[j * lds + i], R3[j * ldh + c], dk);
                 }
-                R6[i * ldh + c] = dq * scale;
-                R6[i * ldh + d + c] = dk;
+                put_dq(i, c, dq);
+                put_dk(i, c, dk);
             }
             for (int idx = tid; idx < TBL; idx += kT) {
                 const int dy = idx / (2 * ws - 1) - (ws - 1), dx = idx % (2 * ws - 1) - (ws - 1);
@@ -593,7 +690,8 @@ int mwa_bwd_core(const float* qkv_tok, const float* dao_tok, const void* params,
                  "mwa_bwd_core(attr)");
     const int per_sm = smem > 0 ? static_cast<int>((220 * 1024) / smem) : 1;
     const int64_t cap = int64_t(kNumSMs) * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
-    const int grid = static_cast<int>(nwin < cap ? nwin : cap);
+    const int64_t units = nwin * heads;
+    const int grid = static_cast<int>(units < cap ? units : cap);
     mwa_bwd_core_kernel<<<grid, 256, smem, st>>>(qkv_tok, dao_tok, static_cast<const uint8_t*>(params), mask, keep_flags,
                                                  ao_tok, dqkv_tok, grad_table, g, heads, static_cast<int>(nwin));
     return check_launch("mwa_bwd_core");
