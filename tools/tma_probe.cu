@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__
         }
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && mode != 2) {                                     // mode 2: loads only (the gather alone)
             int x0, y0, c0, b;
             coords(j, x0, y0, c0, b);
             if (mode == 0) tma_store4(&out_map, buf, x0, y0, c0, b);
@@ -99,6 +99,44 @@ __global__ void __launch_bounds__(128) tma_window_kernel(const __grid_constant__
         }
     }
     if (tid == 0) bulk_wait_group<0>();
+}
+
+// Same gather (loads only), but NW warps of ONE CTA per SM each run their own ring: does the per-SM rate scale with the
+// number of issuing warps inside a CTA the way it does with the number of CTAs?
+template <int CB, int STAGES, int NW>
+__global__ void __launch_bounds__(NW * 32) tma_gather_warps_kernel(const __grid_constant__ CUtensorMap in_map, int nwx, int nwy,
+                                                                   int nwin, int C, int shift) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[NW][STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(smem) + warp * STAGES * CB * 64;
+    constexpr uint32_t kBoxBytes = CB * 64 * 4;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < NW; ++w)
+            for (int s = 0; s < STAGES; ++s) mbar_init(&full[w][s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int chunks = C / CB;
+    int my = 0;
+    for (int w = blockIdx.x; w < nwin; w += gridDim.x) ++my;
+    const int total_cta = my * chunks;
+    const int total = (total_cta - warp + NW - 1) / NW;                 // jobs warp, warp + NW, ...
+    auto issue = [&](int jw) {
+        const int job = warp + jw * NW;
+        const int win = blockIdx.x + (job / chunks) * gridDim.x;
+        const int b = win / (nwx * nwy), r = win % (nwx * nwy);
+        mbar_expect(&full[warp][jw % STAGES], kBoxBytes);
+        tma_load4(stage + (jw % STAGES) * CB * 64, &in_map, (r % nwx) * 8 + shift, (r / nwx) * 8 + shift, (job % chunks) * CB, b,
+                  &full[warp][jw % STAGES]);
+    };
+    if (lane == 0)
+        for (int j = 0; j < STAGES - 1 && j < total; ++j) issue(j);
+    for (int j = 0; j < total; ++j) {
+        if (lane == 0 && j + STAGES - 1 < total) issue(j + STAGES - 1);
+        mbar_wait(&full[warp][j % STAGES], (j / STAGES) & 1);
+        __syncwarp();
+    }
 }
 
 int main() {
@@ -127,6 +165,71 @@ int main() {
     const int nwx = W / 8, nwy = H / 8, nwin = B * nwx * nwy;
     std::vector<float> hy(n);
     bool all_ok = true;
+    // deeper pipelines, loads only: what the gather alone can reach (8 stages of [16 ch][8][8] = 32 KB)
+    {
+        CUtensorMap in_map, out_map;
+        if (!make_map(x, 16, &in_map) || !make_map(y, 16, &out_map)) return 1;
+        // more CTAs per SM (4 stages each): does the per-SM rate scale with the number of independent issue streams?
+        for (int shift : {0, 4}) for (int grid : {296, 592, 1184}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemsetAsync(flush, rep, 512u << 20));
+                cudaEventRecord(e0);
+                const int smem = 4 * 16 * 64 * 4;
+                cudaFuncSetAttribute(tma_window_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                tma_window_kernel<16, 4><<<grid, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, 2);
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("TMA window gather only  box [16 ch][8][8]  shift %d   4 stages  grid %4d (%d CTAs per SM): %.3f ms  %.0f GB/s (read)\n",
+                   shift, grid, grid / 148, best, 1.0 * n * 4 / best / 1e6);
+        }
+        for (int shift : {0, 4}) for (int nw : {1, 2, 4, 8}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemsetAsync(flush, rep, 512u << 20));
+                cudaEventRecord(e0);
+                const int smem = nw * 4 * 16 * 64 * 4;
+#define LAUNCH_W(NW_)                                                                                                   \
+    cudaFuncSetAttribute(tma_gather_warps_kernel<16, 4, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+    tma_gather_warps_kernel<16, 4, NW_><<<148, NW_ * 32, smem>>>(in_map, nwx, nwy, nwin, C, shift);
+                if (nw == 1) { LAUNCH_W(1) } else if (nw == 2) { LAUNCH_W(2) } else if (nw == 4) { LAUNCH_W(4) } else { LAUNCH_W(8) }
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("TMA window gather only  box [16 ch][8][8]  shift %d   ONE CTA per SM, %d issuing warps x 4 stages: %.3f ms  %.0f GB/s "
+                   "(read) = %.0f cycles per 128-token tile at 1.9 GHz\n", shift, nw, best, 1.0 * n * 4 / best / 1e6,
+                   best * 1e-3 * 1.9e9 / (6144.0 / 2 / 148));
+        }
+        for (int shift : {0, 4}) for (int stages : {4, 8, 12}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemsetAsync(flush, rep, 512u << 20));
+                cudaEventRecord(e0);
+                const int smem = stages * 16 * 64 * 4;
+                if (stages == 4) {
+                    cudaFuncSetAttribute(tma_window_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<16, 4><<<148, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, 2);
+                } else if (stages == 8) {
+                    cudaFuncSetAttribute(tma_window_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<16, 8><<<148, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, 2);
+                } else {
+                    cudaFuncSetAttribute(tma_window_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    tma_window_kernel<16, 12><<<148, 128, smem>>>(in_map, out_map, nwx, nwy, nwin, C, shift, 2);
+                }
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("TMA window gather only  box [16 ch][8][8]  shift %d  %2d stages  grid 148: %.3f ms  %.0f GB/s (read)  = %.0f cycles "
+                   "per 128-token tile at 1.9 GHz\n", shift, stages, best, 1.0 * n * 4 / best / 1e6, best * 1e-3 * 1.9e9 / (6144.0 / 2 / 148));
+        }
+    }
     for (int cb : {16, 32, 64}) {
         CUtensorMap in_map, out_map;
         if (!make_map(x, cb, &in_map) || !make_map(y, cb, &out_map)) return 1;
