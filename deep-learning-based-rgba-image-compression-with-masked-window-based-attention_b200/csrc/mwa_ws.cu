@@ -21,7 +21,35 @@
 // Registers are re-balanced with setmaxnreg (issuer / feeder 32, PE 96, A 128).
 // TMEM: two D_qkv buffers + the projection accumulator.  Shared memory: X, Q/K/V, 1-2 O buffers, weight ring.
 // Operand precision: fp16 x fp16 -> fp32 accumulate; softmax, bias, residual in fp32.
+#include <cstring>
+#include <cuda.h>          // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "mwa_tc_shared.cuh"
+
+// tuning knobs (defaults = the measured best; tools/build_variants.py builds side-by-side variants)
+#ifndef MWA_WS_LB
+#define MWA_WS_LB 4
+#endif
+#ifndef MWA_WS_TMA_DEBUG
+#define MWA_WS_TMA_DEBUG 0      // 1: stage but do not issue the reduce-adds (bring-up aid)
+#endif
+// 8 x 8 windows: epilogue through cp.reduce.async.bulk.tensor (TMA reduce-add of [16 ch][8][8] boxes staged in shared
+// memory) instead of red.global.  Correct (the GPU suite passes with it) but measured SLOWER: 0.464 vs 0.425 ms for 6144
+// windows -- the reduce-add of 32-byte rows at a 16-byte offset runs at ~7 B/clk per SM (13.6 k cycles per tile against
+// 9.6 k for the LSU reductions) and its L2 traffic slows the gather of the next tile (14.5 k -> 19.9 k cycles).  Kept
+// behind this switch, default off, as the scaffolding (tensor map, staging ring, rotating issuer warps) of the TMA gather.
+#ifndef MWA_WS_TMA_OUT
+#define MWA_WS_TMA_OUT 0
+#endif
+#ifndef MWA_WS_SLOTS
+#define MWA_WS_SLOTS (MWA_WS_TMA_OUT ? 2 : 3)   // 2 slabs in flight measured as fast as 3 (0.425 vs 0.425 ms) and free 18 KB
+#endif
+#ifndef MWA_WS_OBUFS_MAX
+#define MWA_WS_OBUFS_MAX 2
+#endif
+#ifndef MWA_WS_MASK_PREFETCH
+#define MWA_WS_MASK_PREFETCH 0
+#endif
+
 
 namespace b200 {
 namespace {
@@ -41,7 +69,7 @@ constexpr int kRegsCtl = 32, kRegsPe = 96, kRegsAt = 128;
 
 template <class CF>
 struct WsMap {
-    static constexpr int kSlots = 3;                                      // QKV weight slabs in flight
+    static constexpr int kSlots = MWA_WS_SLOTS;                           // QKV weight slabs in flight
     static constexpr uint32_t kDqStride = (CF::NQKV + 31) / 32 * 32;      // TMEM columns per D_qkv buffer
     static constexpr int kDqBufs = (2 * kDqStride + CF::C <= 512) ? 2 : 1;
     static constexpr uint32_t tDq = 0;
@@ -54,11 +82,18 @@ struct WsMap {
     static constexpr uint32_t oV = oK + 16384;
     static constexpr uint32_t oO = oV + 16384;                            // kOBufs x [128 x 64]
     static constexpr uint32_t kFixed = CF::KB * 16384 + 3 * 16384 + kSlots * CF::kQkvSlabBytes + CF::kProjSlabBytes;
-    static constexpr uint32_t kSmall = ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16 + CF::NG * CF::NQKV * 4 + CF::C * 4 + 512;
-    static constexpr int kOBufs = (kFixed + 2 * 16384 + kSmall <= 227 * 1024) ? 2 : 1;
+    static constexpr uint32_t kSmall = ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16 + CF::NG * CF::NQKV * 4 + CF::C * 4 + 512 +
+                                       ((CF::WS == 8 && MWA_WS_TMA_OUT != 0) ? 3 * 8192 : 0);
+    static constexpr int kOBufs = (MWA_WS_OBUFS_MAX >= 3 && kFixed + 3 * 16384 + kSmall <= 227 * 1024) ? 3
+                                  : (kFixed + 2 * 16384 + kSmall <= 227 * 1024) ? 2 : 1;
     static constexpr uint32_t oRing = oO + kOBufs * 16384;
     static constexpr uint32_t oRingP = oRing + kSlots * CF::kQkvSlabBytes;
-    static constexpr uint32_t oTbl = oRingP + CF::kProjSlabBytes;         // fp32 [HEADS][TBL]
+    // epilogue staging for the TMA reduce-add: kStageBufs x [2 windows][16 ch][8][8] fp32 (box order of the tensor map)
+    static constexpr bool kTmaOut = (CF::WS == 8) && (MWA_WS_TMA_OUT != 0);
+    static constexpr int kStageBufs = 3;
+    static constexpr uint32_t kStageBytes = 2 * 16 * 64 * 4;
+    static constexpr uint32_t oStage = oRingP + CF::kProjSlabBytes;
+    static constexpr uint32_t oTbl = oStage + (kTmaOut ? kStageBufs * kStageBytes : 0);   // fp32 [HEADS][TBL]
     static constexpr uint32_t oBqkv = oTbl + ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16;   // fp32 [NG][NQKV]
     static constexpr uint32_t oBproj = oBqkv + CF::NG * CF::NQKV * 4;
     static constexpr uint32_t oBars = (oBproj + CF::C * 4 + 15) / 16 * 16;
@@ -68,17 +103,9 @@ struct WsMap {
     // barrier indices
     static constexpr int bXFull = 0, bXEmpty = 1, bPjFull = 2, bPjEmpty = 3, bPFull = 4, bPEmpty = 5;
     static constexpr int bWFull = 6, bWEmpty = bWFull + kSlots;
-    static constexpr int bDqFull = bWEmpty + kSlots, bDqEmpty = bDqFull + 2, bOFull = bDqEmpty + 2, bOEmpty = bOFull + 2;
-    static_assert(bOEmpty + 2 <= 32, "barrier slots");
+    static constexpr int bDqFull = bWEmpty + kSlots, bDqEmpty = bDqFull + 2, bOFull = bDqEmpty + 2, bOEmpty = bOFull + 3;
+    static_assert(bOEmpty + 3 <= 32, "barrier slots");
 };
-
-// tuning knobs (defaults = the measured best; tools/build_variants.py builds side-by-side variants)
-#ifndef MWA_WS_LB
-#define MWA_WS_LB 4
-#endif
-#ifndef MWA_WS_MASK_PREFETCH
-#define MWA_WS_MASK_PREFETCH 0
-#endif
 
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -112,6 +139,9 @@ __device__ __forceinline__ float rcp_approx(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
     float v;
@@ -343,7 +373,7 @@ template <class CF, bool kTiming>
 __global__ void __launch_bounds__(kWsThreads, 1)
 mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
               const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
-              Geom geo, unsigned long long* __restrict__ timing) {
+              Geom geo, unsigned long long* __restrict__ timing, const __grid_constant__ CUtensorMap out_map) {
     using MP = WsMap<CF>;
     constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
     constexpr int LOOK = MP::kDqBufs;                   // QKV groups issued ahead of the projection stream
@@ -374,6 +404,8 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + MP::bDqFull + i, 1);
             mbar_init(bars + MP::bDqEmpty + i, kAtThreads);
+        }
+        for (int i = 0; i < 3; ++i) {
             mbar_init(bars + MP::bOFull + i, kAtThreads);
             mbar_init(bars + MP::bOEmpty + i, 1);
         }
@@ -622,6 +654,87 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             tc_fence_after_sync();
             tick(12);                                                            // 12: wait projection complete
             constexpr int EG = 4;                            // chunks per TMEM round trip
+            if constexpr (MP::kTmaOut) {
+                // ---- TMA epilogue: projection + bias -> fp32 staging boxes [window][16 ch][8][8] -> reduce-add onto
+                //      `out` inside the L2 (cp.reduce.async.bulk.tensor): no global request touches the LSU, the
+                //      accumulator is released after ~3 k cycles of shared-memory stores instead of ~10 k of reductions.
+                //      A window that hangs over the right / bottom border (cyclic shift): the tensor map clips the
+                //      out-of-bound part of its box; the tokens that wrap round to the left / top edge (a few per cent)
+                //      go through red.global as before -- negative box coordinates are an illegal instruction for the
+                //      reduce (probed), so the wrapped copies cannot be issued as shifted boxes.
+                //      Chunk e of the kernel (12 per tile) uses staging buffer e % 3; its two boxes are issued by lane 0 of
+                //      producer warps (2e) & 7 and (2e + 1) & 7 (several issuing warps: the TMA rate scales with them,
+                //      tools/tma_probe.cu), which also wait for their own reads before the buffer comes round again.
+                constexpr int NCK = C / 16;
+                int bwin[2] = {0, 0};
+                bool bvalid[2] = {false, false};
+                if (lane == 0) {
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int lidx = tile * CF::WPT + w;
+                        bvalid[w] = lidx < count;
+                        bwin[w] = list[bvalid[w] ? lidx : count - 1];
+                    }
+                }
+                const uint32_t my_off = wslot * (MP::kStageBytes / 2) + (half * 8) * 256 + tok * 4;
+                bool wraps = false;                          // this token lies beyond the right / bottom image border
+                {
+                    const int lidx = tile * CF::WPT + wslot;
+                    if (lidx < count) {
+                        int b_, wy_, wx_;
+                        window_coords(geo, list[lidx], b_, wy_, wx_);
+                        wraps = (wx_ * WS + tok % WS + geo.shift >= geo.W) || (wy_ * WS + tok / WS + geo.shift >= geo.H);
+                    }
+                }
+                float* owrap = orow - int64_t(half * CPH * 8) * hw + int64_t(half * 8) * hw;     // channel half * 8 of chunk 0
+#pragma unroll
+                for (int k0 = 0; k0 < NCK; k0 += EG) {
+                    uint32_t acc[EG][8];
+#pragma unroll
+                    for (int i = 0; i < EG; ++i) tmem_ld_x8(tm + MP::tP + lane_addr + (k0 + i) * 16 + half * 8, acc[i]);
+                    tmem_wait_ld();
+                    if (k0 + EG >= NCK) {                    // last TMEM read of the tile: hand the accumulator back
+                        tc_fence_before_sync();
+                        mbar_arrive(bars + MP::bPjEmpty);
+                    }
+#pragma unroll
+                    for (int i = 0; i < EG; ++i) {
+                        const int k = k0 + i;
+                        const uint32_t e = uint32_t(it) * NCK + k;
+                        const uint32_t sbuf = sb + MP::oStage + (e % MP::kStageBufs) * MP::kStageBytes;
+                        if (!wraps) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                st_shared_f32(sbuf + my_off + j * 256,
+                                              __uint_as_float(acc[i][j]) + s_bproj[k * 16 + half * 8 + j]);
+                        } else if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                red_add_f32(owrap + int64_t(k * 16 + j) * hw,
+                                            __uint_as_float(acc[i][j]) + s_bproj[k * 16 + half * 8 + j]);
+                        }
+                        fence_proxy_async_smem();
+                        // the buffer chunk e + 1 will use was read by the boxes of chunk e - 2: their issuers wait here
+                        if (lane == 0 && e >= 2 && (pw == int((2 * (e - 2)) & 7) || pw == int((2 * (e - 2) + 1) & 7)))
+                            bulk_wait_group_read<0>();
+                        named_sync(3, kPeThreads);
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+                            if (MWA_WS_TMA_DEBUG != 1 && lane == 0 && pw == int((2 * e + w) & 7) && bvalid[w]) {
+                                int b_, wy_, wx_;
+                                window_coords(geo, bwin[w], b_, wy_, wx_);
+                                const int x0 = wx_ * WS + geo.shift, y0 = wy_ * WS + geo.shift;
+                                const void* src = smem + MP::oStage + (e % MP::kStageBufs) * MP::kStageBytes +
+                                                  w * (MP::kStageBytes / 2);
+                                tma_reduce_add_4d(&out_map, src, x0, y0, k * 16, b_);
+                                bulk_commit_group();
+                            }
+                        }
+                    }
+                }
+                tick(13);
+                continue;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < CPH; c0 += EG) {
                 uint32_t acc[EG][8];
@@ -643,6 +756,9 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             tc_fence_before_sync();
             mbar_arrive(bars + MP::bPjEmpty);
             tick(13);                                                            // 13: epilogue
+        }
+        if constexpr (MP::kTmaOut) {
+            if (lane == 0) bulk_wait_group<0>();             // this warp's reduce-adds have left shared memory and landed
         }
     } else {
         // =========================================================================================== attention warps
@@ -780,6 +896,29 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
 
 unsigned long long* g_ws_timing = nullptr;
 
+// 4-D tiled tensor map over the NCHW fp32 output, box = [16 ch][8][8] (one 16-channel slice of an 8 x 8 window)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_out_map(float* out, int B, int C, int H, int W, CUtensorMap* map) {
+    static EncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MWA_TRY_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "mwa_forward(tensor map)");
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return MWA_ERR_UNSUPPORTED;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[4] = {cuuint64_t(W), cuuint64_t(H), cuuint64_t(C), cuuint64_t(B)};
+    const cuuint64_t strides[3] = {cuuint64_t(W) * 4, cuuint64_t(H) * W * 4, cuuint64_t(C) * H * W * 4};
+    const cuuint32_t box[4] = {8, 8, 16, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MWA_OK : MWA_ERR_UNSUPPORTED;
+}
+
 template <class CF>
 int launch_ws(const float* x, const float* alpha, float* out, const void* params, int B, int H, int W, int shift,
               int32_t* kept_count, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
@@ -813,6 +952,12 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         rc = check_launch("mwa_forward(residual copy)");
         if (rc != MWA_OK) return rc;
     }
+    CUtensorMap out_map;
+    memset(&out_map, 0, sizeof(out_map));
+    if constexpr (WsMap<CF>::kTmaOut) {
+        rc = make_out_map(out, B, CF::C, H, W, &out_map);
+        if (rc != MWA_OK) return rc;
+    }
     const int smem = WsMap<CF>::oTotal;
     const int max_tiles = (nwin + CF::WPT - 1) / CF::WPT;
     const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
@@ -820,12 +965,12 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, true><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                g_ws_timing);
+                                                                g_ws_timing, out_map);
     } else {
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, false><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                 nullptr);
+                                                                 nullptr, out_map);
     }
     rc = check_launch("mwa_forward(tcgen05 ws)");
     if (rc != MWA_OK) return rc;
