@@ -59,10 +59,26 @@ rowwise_kernel(const float* __restrict__ a, const float* __restrict__ b, float* 
     }
 }
 
+__device__ __forceinline__ float to_level(float v, float levels) { return __fdiv_rn(rintf(__fmul_rn(v, levels)), levels); }
+// VEC = 4: 128-bit streaming loads / stores (n % 4 == 0, 16-byte aligned); VEC = 1: any n
+template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 levels_kernel(const float* __restrict__ m, float* __restrict__ out, int64_t n, float levels) {
-    for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kThreads)
-        out[i] = __fdiv_rn(rintf(__fmul_rn(m[i], levels)), levels);
+    const int64_t stride = int64_t(gridDim.x) * kThreads;
+    if constexpr (VEC == 4) {
+        const float4* m4 = reinterpret_cast<const float4*>(m);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n / 4; i += stride) {
+            float4 v = __ldcs(m4 + i);
+            v.x = to_level(v.x, levels);
+            v.y = to_level(v.y, levels);
+            v.z = to_level(v.z, levels);
+            v.w = to_level(v.w, levels);
+            __stcs(o4 + i, v);
+        }
+    } else {
+        for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < n; i += stride) out[i] = to_level(m[i], levels);
+    }
 }
 
 inline int grid_for(int64_t work_items) {
@@ -127,7 +143,10 @@ int quantize_levels_forward(const float* m, float* out, int64_t n, float levels,
     if (n < 0 || !(levels > 0.f)) return MWA_ERR_INVALID;
     if (n == 0) return MWA_OK;
     if (!m || !out) return MWA_ERR_INVALID;
-    levels_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(m, out, n, levels);
+    if (n % 4 == 0 && aligned16(m) && aligned16(out))
+        levels_kernel<4><<<grid_for(n / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(m, out, n, levels);
+    else
+        levels_kernel<1><<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(m, out, n, levels);
     return check_launch("quantize_levels_forward");
 }
 
