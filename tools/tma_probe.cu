@@ -139,6 +139,24 @@ __global__ void __launch_bounds__(NW * 32) tma_gather_warps_kernel(const __grid_
     }
 }
 
+// Are NEGATIVE box coordinates legal for a tiled LOAD (they are an illegal instruction for the reduce-add store)?  One box at
+// (x0, y0) = (-4, -4): the out-of-bound part must arrive as zeros -- what a wrapped window of the cyclic shift needs.
+__global__ void tma_negative_load_kernel(const __grid_constant__ CUtensorMap in_map, float* dbg, int x0, int y0) {
+    __shared__ __align__(128) float box[16 * 64];
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect(&bar, sizeof(box));
+        tma_load4(box, &in_map, x0, y0, 0, 0, &bar);
+    }
+    mbar_wait(&bar, 0);
+    for (int e = threadIdx.x; e < 16 * 64; e += blockDim.x) dbg[e] = box[e];
+}
+
 int main() {
     const int B = 16, C = 192, H = 128, W = 192;
     const size_t n = (size_t)B * C * H * W;
@@ -269,6 +287,29 @@ int main() {
             if (bad) all_ok = false;
             printf("TMA window %s  box [%2d ch][8][8]  shift %d  grid %3d: %.3f ms  %.0f GB/s (read+write)  %s\n",
                    mode == 0 ? "copy  " : "reduce", cb, shift, grid, best, 2.0 * n * 4 / best / 1e6, bad ? "MISMATCH" : "ok");
+        }
+    }
+    {   // negative coordinates on the load path (run last: a fault here ends the process)
+        CUtensorMap in_map;
+        if (!make_map(x, 16, &in_map)) return 1;
+        float* dbg;
+        CK(cudaMalloc(&dbg, 16 * 64 * 4));
+        for (int neg : {0, 1}) {
+            const int x0 = neg ? -4 : W - 4, y0 = neg ? -4 : H - 4;
+            tma_negative_load_kernel<<<1, 128>>>(in_map, dbg, x0, y0);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("TMA load at (%d, %d): %s\n", x0, y0, cudaGetErrorString(e)); all_ok = false; break; }
+            std::vector<float> hb(16 * 64);
+            CK(cudaMemcpy(hb.data(), dbg, hb.size() * 4, cudaMemcpyDeviceToHost));
+            size_t bad = 0;
+            for (int c = 0; c < 16; ++c) for (int yy = 0; yy < 8; ++yy) for (int xx = 0; xx < 8; ++xx) {
+                const int gx = x0 + xx, gy = y0 + yy;
+                const float want = (gx < 0 || gy < 0 || gx >= W || gy >= H) ? 0.f : hx[((size_t)c * H + gy) * W + gx];
+                if (hb[c * 64 + yy * 8 + xx] != want) ++bad;
+            }
+            printf("TMA load of one box at (%d, %d): %s (out-of-bound part zero-filled, %zu mismatches)\n", x0, y0,
+                   bad ? "MISMATCH" : "ok", bad);
+            if (bad) all_ok = false;
         }
     }
     printf(all_ok ? "PROBE PASSED\n" : "PROBE FAILED\n");
