@@ -40,8 +40,19 @@
 #ifndef MWA_WS_TMA_OUT
 #define MWA_WS_TMA_OUT 0
 #endif
+// 8 x 8 windows: gather x with cp.async.bulk.tensor boxes [16 ch][8][8] issued by the two idle control warps (one ring of
+// three 4 KB slots per window slot of the tile); the producer warps read the staged fp32 values from shared memory
+// instead of gathering them from global memory through the LSU.  Windows that wrap round the image border keep the LSU
+// path (whole tile, so that the choice is warp-uniform in the producer warps).  Correct (GPU suite green with it) and the
+// MEDIAN CTA gets faster (cycles per tile 35.3 k -> 33-34.4 k dense, -8 % with half of the windows dropped), but the CTAs that own
+// the border windows (every fourth CTA, a third of its tiles on the LSU path) run 36-39 k cycles per tile and set the
+// kernel time: 0.359 vs 0.374 ms at 50 % kept, 0.466 vs 0.425 ms with every window kept.  Default off until the wrapped
+// windows go through the TMA as well (negative box coordinates are legal and zero-filled on loads: tools/tma_probe.cu).
+#ifndef MWA_WS_TMA_IN
+#define MWA_WS_TMA_IN 0
+#endif
 #ifndef MWA_WS_SLOTS
-#define MWA_WS_SLOTS (MWA_WS_TMA_OUT ? 2 : 3)   // 2 slabs in flight measured as fast as 3 (0.425 vs 0.425 ms) and free 18 KB
+#define MWA_WS_SLOTS ((MWA_WS_TMA_OUT || MWA_WS_TMA_IN) ? 2 : 3)   // 2 slabs in flight measured as fast as 3 (0.425 vs 0.425 ms) and free 18 KB
 #endif
 #ifndef MWA_WS_OBUFS_MAX
 #define MWA_WS_OBUFS_MAX 2
@@ -83,7 +94,7 @@ struct WsMap {
     static constexpr uint32_t oO = oV + 16384;                            // kOBufs x [128 x 64]
     static constexpr uint32_t kFixed = CF::KB * 16384 + 3 * 16384 + kSlots * CF::kQkvSlabBytes + CF::kProjSlabBytes;
     static constexpr uint32_t kSmall = ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16 + CF::NG * CF::NQKV * 4 + CF::C * 4 + 512 +
-                                       ((CF::WS == 8 && MWA_WS_TMA_OUT != 0) ? 3 * 8192 : 0);
+                                       ((CF::WS == 8 && (MWA_WS_TMA_OUT != 0 || MWA_WS_TMA_IN != 0)) ? 3 * 8192 : 0);
     static constexpr int kOBufs = (MWA_WS_OBUFS_MAX >= 3 && kFixed + 3 * 16384 + kSmall <= 227 * 1024) ? 3
                                   : (kFixed + 2 * 16384 + kSmall <= 227 * 1024) ? 2 : 1;
     static constexpr uint32_t oRing = oO + kOBufs * 16384;
@@ -93,18 +104,21 @@ struct WsMap {
     static constexpr int kStageBufs = 3;
     static constexpr uint32_t kStageBytes = 2 * 16 * 64 * 4;
     static constexpr uint32_t oStage = oRingP + CF::kProjSlabBytes;
-    static constexpr uint32_t oTbl = oStage + (kTmaOut ? kStageBufs * kStageBytes : 0);   // fp32 [HEADS][TBL]
+    static constexpr bool kTmaIn = (CF::WS == 8) && (MWA_WS_TMA_IN != 0);      // staging = 3 slots x [2 windows] x 4 KB boxes
+    static_assert(!(kTmaOut && kTmaIn), "one user of the staging ring at a time");
+    static constexpr uint32_t oTbl = oStage + ((kTmaOut || kTmaIn) ? kStageBufs * kStageBytes : 0);   // fp32 [HEADS][TBL]
     static constexpr uint32_t oBqkv = oTbl + ((CF::HEADS * CF::TBL * 4 + 15) / 16) * 16;   // fp32 [NG][NQKV]
     static constexpr uint32_t oBproj = oBqkv + CF::NG * CF::NQKV * 4;
     static constexpr uint32_t oBars = (oBproj + CF::C * 4 + 15) / 16 * 16;
-    static constexpr uint32_t oTmem = oBars + 32 * 8;
+    static constexpr uint32_t oTmem = oBars + 40 * 8;
     static constexpr uint32_t oTotal = oTmem + 16;
     static_assert(oTotal <= 227 * 1024, "shared memory budget");
     // barrier indices
     static constexpr int bXFull = 0, bXEmpty = 1, bPjFull = 2, bPjEmpty = 3, bPFull = 4, bPEmpty = 5;
     static constexpr int bWFull = 6, bWEmpty = bWFull + kSlots;
     static constexpr int bDqFull = bWEmpty + kSlots, bDqEmpty = bDqFull + 2, bOFull = bDqEmpty + 2, bOEmpty = bOFull + 3;
-    static_assert(bOEmpty + 3 <= 32, "barrier slots");
+    static constexpr int bSFull = bOEmpty + 3, bSEmpty = bSFull + 6;       // staging ring of the TMA gather: [window][slot]
+    static_assert(bSEmpty + 6 <= 40, "barrier slots");
 };
 
 template <int N>
@@ -373,7 +387,8 @@ template <class CF, bool kTiming>
 __global__ void __launch_bounds__(kWsThreads, 1)
 mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ blk,
               const uint8_t* __restrict__ tcp, const int32_t* __restrict__ list, const int32_t* __restrict__ count_p,
-              Geom geo, unsigned long long* __restrict__ timing, const __grid_constant__ CUtensorMap out_map) {
+              Geom geo, unsigned long long* __restrict__ timing, const __grid_constant__ CUtensorMap out_map,
+              const __grid_constant__ CUtensorMap x_map) {
     using MP = WsMap<CF>;
     constexpr int C = CF::C, WS = CF::WS, NTOK = CF::NTOK, DPAD = CF::DPAD, HPG = CF::HPG, NG = CF::NG;
     constexpr int LOOK = MP::kDqBufs;                   // QKV groups issued ahead of the projection stream
@@ -408,6 +423,10 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         for (int i = 0; i < 3; ++i) {
             mbar_init(bars + MP::bOFull + i, kAtThreads);
             mbar_init(bars + MP::bOEmpty + i, 1);
+        }
+        for (int i = 0; i < 6; ++i) {
+            mbar_init(bars + MP::bSFull + i, 1);
+            mbar_init(bars + MP::bSEmpty + i, 128);      // the 128 producer threads of a window slot (both channel halves)
         }
         fence_mbar_init();
     }
@@ -560,6 +579,38 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 }
             }
         }
+        if constexpr (MP::kTmaIn) {
+            if (warp == 2 || warp == 3) {
+                // ---- TMA gather issuer of window slot w: boxes of tile i in the order the producer warps consume them
+                //      (chunk j of channel half 0, chunk j of half 1, ...), three boxes in flight
+                const int w = warp - 2;
+                uint32_t n = 0;
+                for (int i = 0; i < my_tiles; ++i) {
+                    // a tile is staged only if BOTH of its windows exist and neither wraps round the image border (the
+                    // choice must be warp-uniform in the producer warps, whose lanes cover both windows)
+                    const int lidx0 = (blockIdx.x + i * gridDim.x) * CF::WPT;
+                    if (lidx0 + 1 >= count) continue;
+                    int b_, wy_, wx_, bo_, wyo_, wxo_;
+                    window_coords(geo, list[lidx0 + w], b_, wy_, wx_);
+                    window_coords(geo, list[lidx0 + 1 - w], bo_, wyo_, wxo_);
+                    const int x0 = wx_ * WS + geo.shift, y0 = wy_ * WS + geo.shift;
+                    if (x0 + WS > geo.W || y0 + WS > geo.H || wxo_ * WS + geo.shift + WS > geo.W ||
+                        wyo_ * WS + geo.shift + WS > geo.H)
+                        continue;                                           // LSU path for the whole tile
+                    for (int j = 0; j < C / 16; ++j, ++n) {
+                        const int k = (j & 1) * (C / 32) + (j >> 1);
+                        const uint32_t slot = n % 3;
+                        if (n >= 3) mbar_wait(bars + MP::bSEmpty + w * 3 + slot, ((n / 3) - 1) & 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(bars + MP::bSFull + w * 3 + slot, 4096);
+                            tma_load_4d(smem + MP::oStage + (slot * 2 + w) * 4096, &x_map, x0, y0, k * 16, b_,
+                                        bars + MP::bSFull + w * 3 + slot);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
     } else if (warp < kAtWarp0) {
         // =========================================================================================== x producer + epilogue
         reg_dec<kRegsPe>();
@@ -589,11 +640,56 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         //                With dropped neighbours these half-sector stores are slow, hence the switch.  (An L2
         //                evict-last hint on these stores changed nothing measurable and would leave persisting lines
         //                behind for the next kernel, so they are plain stores.)
+        uint32_t stage_n = 0;                                // boxes of this thread's window slot issued so far (kTmaIn)
         auto load_x = [&](int tile) {
             bool valid;
             const int64_t off = row_base(tile, valid) + int64_t(half * CPH * 8) * hw;
             const float* p = x + off;
             float* po = out + off;
+            if constexpr (MP::kTmaIn) {
+                bool staged = tile * CF::WPT + 1 < count;
+                if (staged) {
+#pragma unroll
+                    for (int w2 = 0; w2 < 2; ++w2) {
+                        int b_, wy_, wx_;
+                        window_coords(geo, list[tile * CF::WPT + w2], b_, wy_, wx_);
+                        staged = staged && (wx_ * WS + geo.shift + WS <= geo.W) && (wy_ * WS + geo.shift + WS <= geo.H);
+                    }
+                }
+                if (staged) {
+                    // this thread's 96 channels arrive as six [16 ch][64 tok] boxes (every second box of the window's
+                    // stream: the other channel half's boxes are interleaved with them)
+                    // (every thread of the window observes EVERY box of the stream, also the other half's: a parity wait
+                    //  may lag the barrier by at most one phase)
+#pragma unroll
+                    for (int jj = 0; jj < CPH; ++jj) {
+                        const uint32_t nb = stage_n + jj, slot = nb % 3;
+                        mbar_wait(bars + MP::bSFull + wslot * 3 + slot, (nb / 3) & 1);
+                        if ((jj & 1) != half) {
+                            mbar_arrive(bars + MP::bSEmpty + wslot * 3 + slot);
+                            continue;
+                        }
+                        const int i = jj >> 1;
+                        const uint32_t base = sb + MP::oStage + (slot * 2 + wslot) * 4096 + tok * 4;
+                        float v[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) v[c] = ld_shared_f32(base + c * 256);
+                        mbar_arrive(bars + MP::bSEmpty + wslot * 3 + slot);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            if (prestore) *po = v[c];
+                            po += hw;
+                        }
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp) {
+                            pk[2 * i][jp] = pack_f16x2(v[2 * jp], v[2 * jp + 1]);
+                            pk[2 * i + 1][jp] = pack_f16x2(v[8 + 2 * jp], v[8 + 2 * jp + 1]);
+                        }
+                    }
+                    stage_n += C / 16;
+                    return;
+                }
+            }
 #pragma unroll
             for (int c0 = 0; c0 < CPH; c0 += LB) {
                 float v[LB][8];
@@ -952,10 +1048,15 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         rc = check_launch("mwa_forward(residual copy)");
         if (rc != MWA_OK) return rc;
     }
-    CUtensorMap out_map;
+    CUtensorMap out_map, x_map;
     memset(&out_map, 0, sizeof(out_map));
+    memset(&x_map, 0, sizeof(x_map));
     if constexpr (WsMap<CF>::kTmaOut) {
         rc = make_out_map(out, B, CF::C, H, W, &out_map);
+        if (rc != MWA_OK) return rc;
+    }
+    if constexpr (WsMap<CF>::kTmaIn) {
+        rc = make_out_map(const_cast<float*>(x), B, CF::C, H, W, &x_map);
         if (rc != MWA_OK) return rc;
     }
     const int smem = WsMap<CF>::oTotal;
@@ -965,12 +1066,12 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, true><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                g_ws_timing, out_map);
+                                                                g_ws_timing, out_map, x_map);
     } else {
         MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_ws_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                      "mwa_forward(ws attr)");
         mwa_ws_kernel<CF, false><<<grid, kWsThreads, smem, st>>>(x, out, blk, blk + L.img_wqkv, list, count, geo,
-                                                                 nullptr, out_map);
+                                                                 nullptr, out_map, x_map);
     }
     rc = check_launch("mwa_forward(tcgen05 ws)");
     if (rc != MWA_OK) return rc;
