@@ -380,12 +380,12 @@ def main():
         else "fallback (B200_PROFILING.md)"
 
     # DRAM traffic from the committed ncu --set full captures of this command (dram__bytes_read.sum + dram__bytes_write.sum):
-    # GDN: profiles/r01_gdn_tc_ncu_raw_v2.csv, the three shapes, x2 for IGDN, in GB per step like the algorithmic 6.34 GB
-    # behind `achieved`; attention: profiles/r01_attn_ws_ncu_raw.csv, main kernel of one 8x8 launch (3798 kept windows:
+    # GDN: profiles/r01_gdn_tc_ncu_raw_final.csv (first capture: ..._v2.csv), the three shapes, x2 for IGDN, in GB per step like the algorithmic 6.34 GB
+    # behind `achieved`; attention: profiles/r01_attn_ws_ncu_raw_final.csv, main kernel of one 8x8 launch (3798 kept windows:
     # 0.374 GB algorithmic for the kept windows; the reductions re-fetch `out` lines that left L2)
     roofs[1]["traffic"] = 2 * (1.209517 + 1.149031 + 0.302230 + 0.243435 + 0.075690 + 0.019050)
     roofs[1]["traffic_unit"] = "GB per step (6 launches), ncu capture under profiles/"
-    roofs[0]["traffic"] = 0.448074 + 0.160595
+    roofs[0]["traffic"] = 0.450246 + 0.167950
     roofs[0]["traffic_unit"] = "GB per launch (main kernel), ncu capture under profiles/"
     if dominant is roofs[1]:
         roofline["traffic"] = roofs[1]["traffic"]

@@ -40,22 +40,24 @@
 #ifndef MWA_WS_TMA_OUT
 #define MWA_WS_TMA_OUT 0
 #endif
-// 8 x 8 windows: gather x with cp.async.bulk.tensor boxes [16 ch][8][8] issued by the two idle control warps (one ring of
-// three 4 KB slots per window slot of the tile); the producer warps read the staged fp32 values from shared memory
-// instead of gathering them from global memory through the LSU.  Windows that wrap round the image border keep the LSU
-// path (whole tile, so that the choice is warp-uniform in the producer warps).  Correct (GPU suite green with it) and the
-// MEDIAN CTA gets faster (cycles per tile 35.3 k -> 33-34.4 k dense, -8 % with half of the windows dropped), but the CTAs that own
-// the border windows (every fourth CTA, a third of its tiles on the LSU path) run 36-39 k cycles per tile and set the
-// kernel time: 0.359 vs 0.374 ms at 50 % kept, 0.466 vs 0.425 ms with every window kept.  Default off until the wrapped
-// windows go through the TMA as well (negative box coordinates are legal and zero-filled on loads: tools/tma_probe.cu).
+// 8 x 8 windows: gather x with cp.async.bulk.tensor boxes [16 ch][8][8] issued by the two otherwise idle control warps (one
+// ring of three 4 KB slots per window slot of the tile, paid for by the third weight slab); the producer warps read the
+// staged fp32 values from shared memory instead of gathering them from global memory through the LSU.  Tiles with a window
+// on the wrapped image border keep the LSU gather (whole tile: the choice must be warp-uniform in the producer warps).
+// Measured A/B on one box (tools/build_variants.py): 0.415 vs 0.435 ms for 6144 kept windows, 0.353 vs 0.378 ms at 50 %
+// kept, attention share of the bench step 0.912 vs 0.961 ms; +4 % only at 25 % kept.  Needs MWA_WS_SKEW (border tiles spread
+// over the CTAs): without it every fourth CTA owns all border tiles and sets the kernel time (0.466 ms).
 #ifndef MWA_WS_TMA_IN
-#define MWA_WS_TMA_IN 0
+#define MWA_WS_TMA_IN 1
 #endif
 #ifndef MWA_WS_SLOTS
 #define MWA_WS_SLOTS ((MWA_WS_TMA_OUT || MWA_WS_TMA_IN) ? 2 : 3)   // 2 slabs in flight measured as fast as 3 (0.425 vs 0.425 ms) and free 18 KB
 #endif
 #ifndef MWA_WS_OBUFS_MAX
 #define MWA_WS_OBUFS_MAX 2
+#endif
+#ifndef MWA_WS_SKEW
+#define MWA_WS_SKEW 1u          // 0: tile t -> CTA t % grid (every round the same)
 #endif
 #ifndef MWA_WS_MASK_PREFETCH
 #define MWA_WS_MASK_PREFETCH 0
@@ -460,7 +462,13 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     const int num_tiles = (count + CF::WPT - 1) / CF::WPT;
     const int64_t hw = int64_t(geo.H) * geo.W;
     int my_tiles = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) ++my_tiles;
+    // tile of this CTA in round `it`: the rounds are skewed by one CTA each, so that the tiles with a window on the wrapped
+    // image border (every 12th tile of a 24-window row: they would all land on every fourth CTA) spread over all CTAs
+    auto tile_of = [&](int it) -> int { return it * int(gridDim.x) + int((blockIdx.x + unsigned(it) * MWA_WS_SKEW) % gridDim.x); };
+    {
+        const int full = num_tiles / int(gridDim.x), rem = num_tiles - full * int(gridDim.x);
+        my_tiles = full + ((int((blockIdx.x + unsigned(full) * MWA_WS_SKEW) % gridDim.x) < rem) ? 1 : 0);
+    }
     const int total = my_tiles * NG;                       // head groups this CTA processes
     const uint8_t* wimg = tcp + TcParams<CF>::img;
 
@@ -588,7 +596,7 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 for (int i = 0; i < my_tiles; ++i) {
                     // a tile is staged only if BOTH of its windows exist and neither wraps round the image border (the
                     // choice must be warp-uniform in the producer warps, whose lanes cover both windows)
-                    const int lidx0 = (blockIdx.x + i * gridDim.x) * CF::WPT;
+                    const int lidx0 = tile_of(i) * CF::WPT;
                     if (lidx0 + 1 >= count) continue;
                     int b_, wy_, wx_, bo_, wyo_, wxo_;
                     window_coords(geo, list[lidx0 + w], b_, wy_, wx_);
@@ -729,17 +737,17 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         if (my_tiles > 0) {
             load_x(blockIdx.x);
             store_x();
-            if (my_tiles > 1) load_x(blockIdx.x + gridDim.x);
+            if (my_tiles > 1) load_x(tile_of(1));
         }
         tick(8);                                                                 // 8: PE prologue
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
+            const int tile = tile_of(it);
             if (it + 1 < my_tiles) {
                 mbar_wait(bars + MP::bXEmpty, it & 1);       // QKV MMAs of tile `it` have consumed X
                 tick(9);                                                         // 9: wait X free
                 store_x();
                 tick(10);                                                        // 10: store X
-                if (it + 2 < my_tiles) load_x(tile + 2 * gridDim.x);
+                if (it + 2 < my_tiles) load_x(tile_of(it + 2));
                 tick(11);                                                        // 11: load x (tile + 2)
             }
             // ---- epilogue of tile `it`: out (= x, stored by this very thread when it loaded the tile) += proj + bias;
@@ -892,14 +900,14 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         };
         if (my_tiles > 0) fetch_wins(blockIdx.x);
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
+            const int tile = tile_of(it);
             // SW-MSA region mask bits of this warp's rows (:194-216); zero unless the window touches the wrapped border
             uint32_t rowmask[TPW][2];
             uint32_t mask_any = 0;
             int win_cur[TPW];
 #pragma unroll
             for (int i = 0; i < TPW; ++i) win_cur[i] = win_next[i];
-            if (MWA_WS_MASK_PREFETCH && it + 1 < my_tiles) fetch_wins(tile + gridDim.x);
+            if (MWA_WS_MASK_PREFETCH && it + 1 < my_tiles) fetch_wins(tile_of(it + 1));
 #pragma unroll
             for (int i = 0; i < TPW; ++i) {
                 rowmask[i][0] = rowmask[i][1] = 0u;
