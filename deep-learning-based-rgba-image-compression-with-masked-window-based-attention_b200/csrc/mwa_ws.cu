@@ -1000,11 +1000,12 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
 
 unsigned long long* g_ws_timing = nullptr;
 
-// 4-D tiled tensor map over the NCHW fp32 output, box = [16 ch][8][8] (one 16-channel slice of an 8 x 8 window)
+// 4-D tiled tensor map over an NCHW fp32 tensor (x for the gather, out for the experimental reduce-add epilogue),
+// box = [16 ch][8][8]: one 16-channel slice of an 8 x 8 window
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_out_map(float* out, int B, int C, int H, int W, CUtensorMap* map) {
+int make_window_box_map(float* out, int B, int C, int H, int W, CUtensorMap* map) {
     static EncodeTiledFn encode = nullptr;
     if (encode == nullptr) {
         void* fn = nullptr;
@@ -1060,11 +1061,11 @@ int launch_ws(const float* x, const float* alpha, float* out, const void* params
     memset(&out_map, 0, sizeof(out_map));
     memset(&x_map, 0, sizeof(x_map));
     if constexpr (WsMap<CF>::kTmaOut) {
-        rc = make_out_map(out, B, CF::C, H, W, &out_map);
+        rc = make_window_box_map(out, B, CF::C, H, W, &out_map);
         if (rc != MWA_OK) return rc;
     }
     if constexpr (WsMap<CF>::kTmaIn) {
-        rc = make_out_map(const_cast<float*>(x), B, CF::C, H, W, &x_map);
+        rc = make_window_box_map(const_cast<float*>(x), B, CF::C, H, W, &x_map);
         if (rc != MWA_OK) return rc;
     }
     const int smem = WsMap<CF>::oTotal;
