@@ -287,9 +287,9 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     return check_launch("mwa_prepare(images)");
 }
 
-void mwa_debug_set_timing_buffer(void* device_u64x32) {
-    mwa_tc_set_timing_buffer(device_u64x32);
-    mwa_ws_set_timing_buffer(device_u64x32);
+void mwa_debug_set_timing_buffer(void* device_u64x4096) {
+    mwa_tc_set_timing_buffer(device_u64x4096);
+    mwa_ws_set_timing_buffer(device_u64x4096);
 }
 
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {

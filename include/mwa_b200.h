@@ -120,7 +120,7 @@ MWA_API int64_t mwa_workspace_bytes(int B, int H, int W, int ws);
 /* development aid: device buffer of 4096 uint64 that the tcgen05 attention kernels fill with clock64() totals
  * ([0,32): per-stage totals of CTA 0; [64,320): cycles per CTA; [320,576): tiles per CTA).  NULL switches it off
  * (the default). */
-MWA_API void mwa_debug_set_timing_buffer(void* device_u64x32);
+MWA_API void mwa_debug_set_timing_buffer(void* device_u64x4096);
 MWA_API int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
                 int heads, int ws, int shift, int channels_last, int algo, int32_t* kept_count, void* workspace,
                 int64_t workspace_bytes, void* stream);
