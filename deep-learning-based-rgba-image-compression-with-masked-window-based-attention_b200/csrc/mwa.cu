@@ -23,6 +23,15 @@ int mwa_forward_ws(const float* x, const float* alpha, float* out, const void* p
 bool mwa_ws_supported(int C, int heads, int ws, int channels_last);
 void mwa_ws_set_timing_buffer(void* p);
 
+int mwa_forward_sp(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                   int heads, int ws, int shift, int32_t* kept_count, void* workspace, int64_t workspace_bytes,
+                   cudaStream_t st);                                                                          // mwa_sp.cu
+bool mwa_sp_supported(int C, int heads, int ws, int H, int W, int channels_last);
+int64_t mwa_sp_workspace_bytes(int64_t nwin);
+void mwa_sp_set_timing_buffer(void* p);
+void mwa_sp_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
+                           const float* table, int C, int heads, int ws, float scale, uint8_t* blk, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -284,17 +293,23 @@ int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* proj_w, con
     int rc = check_launch("mwa_prepare");
     if (rc != MWA_OK) return rc;
     mwa_tc_prepare_images(qkv_w, qkv_b, proj_w, proj_b, C, heads, ws, scale, blk, st);
-    return check_launch("mwa_prepare(images)");
+    rc = check_launch("mwa_prepare(images)");
+    if (rc != MWA_OK) return rc;
+    mwa_sp_prepare_images(qkv_w, qkv_b, proj_w, proj_b, bias_table, C, heads, ws, scale, blk, st);
+    return check_launch("mwa_prepare(split-precision images)");
 }
 
 void mwa_debug_set_timing_buffer(void* device_u64x4096) {
     mwa_tc_set_timing_buffer(device_u64x4096);
     mwa_ws_set_timing_buffer(device_u64x4096);
+    mwa_sp_set_timing_buffer(device_u64x4096);
 }
 
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
     if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;
-    return mwa_tc_workspace_bytes(int64_t(B) * (H / ws) * (W / ws));
+    const int64_t nwin = int64_t(B) * (H / ws) * (W / ws);
+    const int64_t a = mwa_tc_workspace_bytes(nwin), b = mwa_sp_workspace_bytes(nwin);
+    return a > b ? a : b;
 }
 
 int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
@@ -308,7 +323,12 @@ int mwa_forward(const float* x, const float* alpha, float* out, const void* para
     if (B == 0) return MWA_OK;                              // empty batch: x / out may be null
     if (!x || !out || !params) return MWA_ERR_INVALID;
     const bool tc_ok = mwa_tc_supported(C, heads, ws, H, W, shift, channels_last);
-    if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || (algo == MWA_ALGO_AUTO && tc_ok)) {
+    // split-precision tcgen05 kernel (meets the fp32 contract on every element): the default wherever it covers the shape
+    if ((algo == MWA_ALGO_AUTO || algo == MWA_ALGO_TCGEN05) && mwa_sp_supported(C, heads, ws, H, W, channels_last)) {
+        if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
+        return mwa_forward_sp(x, alpha, out, params, B, C, H, W, heads, ws, shift, kept_count, workspace, workspace_bytes, st);
+    }
+    if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || algo == MWA_ALGO_TCGEN05_FP16 || (algo == MWA_ALGO_AUTO && tc_ok)) {
         if (!tc_ok) return MWA_ERR_UNSUPPORTED;
         if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
         // warp-specialised pipeline where it covers the layout, else the phase-serial v1 kernel

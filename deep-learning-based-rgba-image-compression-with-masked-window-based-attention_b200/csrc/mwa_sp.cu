@@ -1,0 +1,934 @@
+// Fused masked window attention forward in SPLIT PRECISION (fp32-faithful results on the tensor cores), sm_100a only.
+// Reference semantics: layers/masked_win_attention.py:169-251 (block) and :96-131 (window attention), whose arithmetic
+// is fp32 end to end.  A single fp16 pass per contraction (csrc/mwa_ws.cu) misses the 1e-3 rel / 1e-4 abs contract on
+// ~0.1 % of the outputs; tools/precision_study.py shows which operand roundings cost what.  Here every operand on the
+// value path (x, Wv, V, P, O, Wproj) is carried as fp16 hi + lo and contracted in three passes
+// (hi*hi + lo*hi + hi*lo, fp32 accumulation), the logit path (q, k) stays single fp16: rms error 8e-6, worst
+// err / tolerance 0.4 at the north-star protocol (N(0,1) inputs, random init) against 1.1-1.2 for plain fp16.
+//
+// EVERY contraction runs on tcgen05 with accumulators in TMEM, and one thread owns one token (= TMEM lane) from the
+// QKV drain to the projection epilogue, so nothing but Q / K / V goes through shared memory:
+//
+//   tile = 128 tokens = 2 kept 8x8 windows (rows 0-63 window slot 0, 64-127 slot 1), one head at a time:
+//   QKV(h)   D_qkv[128 x 3d]  = X_hi Wh_hi^T  (+ X_lo Wv_hi^T + X_hi Wv_lo^T on the v columns); X_lo is a TMEM operand
+//   drain    thread = token: q (+bias, pre-scaled by scale*log2e), k -> fp16 [Q | K] rows; v -> fp16 hi / lo [key][w0 d | w1 d]
+//   S(h)     [128 x 64] = [Q_w0; 0] K_w0^T + [0; Q_w1] K_w1^T   (zero-block trick: no junk columns, 64 TMEM columns)
+//   softmax  thread = row: + relative-position bias (+ SW-MSA region mask), exp2, row sum; P -> fp16 hi / lo written
+//            back over S in TMEM (A operand of P V)
+//   PV(h)    O[128 x 2d] = P V  (V is the MN-major B operand; a row's own window is one d-wide half), 3 passes
+//   norm     thread = row: O / rowsum -> fp16 hi / lo in TMEM (A operand of the projection)
+//   proj(h)  D_out[128 x 192] += O_h Wproj_h^T, 3 passes, accumulated over the heads in TMEM
+//   residual D_out is INITIALISED with x itself (X_hi I + X_lo I, 16-column identity MMAs, exact to 2^-22), so the
+//            epilogue is a plain store of D_out + bias: no second read of x, no reduction, no pre-copy of the tensor.
+//
+// Roles (20 warps, setmaxnreg): 0 MMA issuer | 1 weight feeder (two rings of bulk copies) | 2-3 TMA gather issuers
+// (one per window slot, [16 ch][8][8] boxes of x) | 4-11 x converter + epilogue (fp32 boxes -> X_hi in shared memory,
+// X_lo kept in registers until the previous tile's last QKV MMA has retired, then stored to TMEM; epilogue interleaved
+// with the conversion of the next tile) | 12-15 softmax + normalisation | 16-19 QKV drain.
+// Dropped windows are copied through by a separate small kernel (only the dropped ones).
+#include <cstring>
+#include <cuda.h>          // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include "mwa_tc_shared.cuh"
+
+// bring-up switches (tools/build_variants.py)
+#ifndef MWA_SP_NO_TMA
+#define MWA_SP_NO_TMA 0          // 1: every window through the LSU gather
+#endif
+#ifndef MWA_SP_FUSE_BLOCKING
+#define MWA_SP_FUSE_BLOCKING 0   // 1: one epilogue step per box, blocking box waits (no polling)
+#endif
+#ifndef MWA_SP_EPI_NOSTORE
+#define MWA_SP_EPI_NOSTORE 0     // 1: (debug) epilogue without its global stores
+#endif
+#ifndef MWA_SP_NO_FUSE
+#define MWA_SP_NO_FUSE 0         // 1: epilogue first, then the conversion of the next tile (no interleaving)
+#endif
+
+namespace b200 {
+namespace {
+
+constexpr int kSpWarps = 20;
+constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpMma = 0, kSpFeed = 1, kSpTma0 = 2;
+constexpr int kSpPe0 = 4, kSpNumPe = 8, kSpSm0 = 12, kSpDr0 = 16;
+// register pool of the CTA = 20 warps x 96 (launch bound); per SM sub-partition 48 + 2 x 104 + 144 + 80 = 480 = 5 x 96
+constexpr int kSpRegsCtl = 48, kSpRegsPe = 104, kSpRegsSm = 144, kSpRegsDr = 80;
+constexpr float kNegMaskL2 = kNegMask * kLog2e;
+
+template <int HEADS_>
+struct SpCfg {
+    static constexpr int C = 192, WS = 8, NTOK = 64, HEADS = HEADS_, D = C / HEADS;
+    static_assert(D == 24 || D == 32, "head dim 24 / 32");
+    static constexpr int KB = 3, KSTEPS = 12;
+    static constexpr int NQH = (3 * D + 15) / 16 * 16;       // QKV MMA N per head (q | k | v | pad)
+    static constexpr int VOFF = 2 * D;                       // first v column
+    static constexpr int NVC = NQH - VOFF;                   // N of the correction passes (v columns + pad) = 32
+    static constexpr int ON = 2 * D;                         // P V output columns: [window slot 0 d | slot 1 d]
+    static constexpr int TBL = 225;
+    static constexpr bool kSepOA = (HEADS == 8);             // projection A operand in its own TMEM columns
+    static_assert(NVC == 32 && VOFF % 8 == 0, "v correction geometry");
+    // weight chunks (one bulk copy each)
+    static constexpr uint32_t kWqHi = NQH * 128, kWqChunk = kWqHi + NVC * 128, kWqStride = 16384;
+    static constexpr uint32_t kWpChunk = 96 * 128;
+    // TMEM columns
+    static constexpr uint32_t tDq = 0, tPj = NQH, tS = tPj + C, tO = tS + 64, tOA = kSepOA ? tO + ON : tO, tXl = 416;
+    static_assert(tOA + 32 <= tXl && tO + ON <= tXl, "TMEM budget");
+    // shared memory map
+    static constexpr uint32_t oXh = 0;                       // 2 x (KB x [128 x 64] fp16)
+    static constexpr uint32_t oQK = 2 * 49152;               // [W0 64 rows][Z 64 zero rows][W1 64 rows] x 128 B: q | k
+    static constexpr uint32_t oVh = oQK + 24576, oVl = oVh + 8192;
+    static constexpr uint32_t oWq = oVl + 8192;              // 2 slots
+    static constexpr uint32_t oWp = oWq + 2 * kWqChunk;      // 2 slots
+    static constexpr uint32_t oStage = oWp + 2 * kWpChunk;   // 3 slots x 2 windows x 4 KB
+    static constexpr uint32_t oI16 = oStage + 24576;
+    static constexpr uint32_t oTbl = oI16 + 2048;
+    static constexpr uint32_t oBq = (oTbl + HEADS * TBL * 4 + 15) / 16 * 16;
+    static constexpr uint32_t oBpf = oBq + C * 4;
+    static constexpr uint32_t oBars = oBpf + C * 4;
+    static constexpr uint32_t oTmem = oBars + 64 * 8;
+    static constexpr uint32_t oTotal = oTmem + 16;
+    static_assert(oTotal <= 227 * 1024, "shared memory budget");
+    static_assert(kWqChunk % 1024 == 0 && oWq % 1024 == 0 && oWp % 1024 == 0 && oI16 % 1024 == 0, "operand alignment");
+    // barriers
+    static constexpr int bXhFull = 0, bXhEmpty = 2, bXlFull = 4, bXlEmpty = 5, bWqFull = 6, bWqEmpty = 8, bWpFull = 10,
+                         bWpEmpty = 12, bDqFull = 14, bDqEmpty = 15, bQkReady = 16, bVReady = 17, bQkFree = 18, bVFree = 19,
+                         bSFull = 20, bPReady = 21, bOFull = 22, bOAReady = 23, bOAFree = 24, bPjFull = 25, bPjEmpty = 26,
+                         bStFull = 27, bStEmpty = 33, bEnd = 39;
+    static_assert(bEnd <= 64, "barrier slots");
+};
+
+// layout of the split-precision section of the parameter block (offsets from MwaParamLayout::img_sp)
+template <class CF>
+struct SpParams {
+    static constexpr int64_t wq = 0;                                                   // [HEADS][KB] x kWqStride
+    static constexpr int64_t wp = wq + int64_t(CF::HEADS) * CF::KB * CF::kWqStride;    // [HEADS][2] x kWpChunk
+    static constexpr int64_t bq = wp + int64_t(CF::HEADS) * 2 * CF::kWpChunk;          // fp32 [C]  q bias * scale * log2e
+    static constexpr int64_t bpf = bq + CF::C * 4;                                     // fp32 [C]  proj.bias + Wproj b_v
+    static constexpr int64_t tbl = bpf + CF::C * 4;                                    // fp32 [HEADS][TBL] * log2e
+    static constexpr int64_t i16 = tbl + (int64_t(CF::HEADS) * CF::TBL * 4 + 1023) / 1024 * 1024;
+    static constexpr int64_t total = i16 + 2048;
+};
+
+__device__ __forceinline__ uint16_t f16_bits(float v) { return __half_as_ushort(__float2half_rn(v)); }
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+template <class CF>
+__global__ void mwa_sp_prepare_kernel(const float* __restrict__ qkv_w, const float* __restrict__ qkv_b,
+                                      const float* __restrict__ proj_w, const float* __restrict__ proj_b,
+                                      const float* __restrict__ table, float scale, uint8_t* __restrict__ out) {
+    constexpr int C = CF::C, D = CF::D, H = CF::HEADS;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const float qs = scale * kLog2e;
+    for (int e = tid; e < H * CF::KB * 3 * D * 64; e += nth) {
+        const int h = e / (CF::KB * 3 * D * 64), kb = (e / (3 * D * 64)) % CF::KB, n = (e / 64) % (3 * D), kk = e % 64;
+        const int part = n / D, c = n % D;
+        float w = qkv_w[int64_t(part * C + h * D + c) * C + kb * 64 + kk];
+        if (part == 0) w *= qs;
+        uint8_t* chunk = out + SpParams<CF>::wq + int64_t(h * CF::KB + kb) * CF::kWqStride;
+        const float hi = f16_round(w);
+        *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, kk)) = f16_bits(w);
+        if (n >= CF::VOFF) *reinterpret_cast<uint16_t*>(chunk + CF::kWqHi + sw128_offset(n - CF::VOFF, kk)) = f16_bits(w - hi);
+    }
+    for (int e = tid; e < H * 2 * 96 * D; e += nth) {
+        const int h = e / (2 * 96 * D), nh = (e / (96 * D)) % 2, n = (e / D) % 96, kk = e % D;
+        const float w = proj_w[int64_t(nh * 96 + n) * C + h * D + kk];
+        uint8_t* chunk = out + SpParams<CF>::wp + int64_t(h * 2 + nh) * CF::kWpChunk;
+        const float hi = f16_round(w);
+        *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, kk)) = f16_bits(w);
+        *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, 32 + kk)) = f16_bits(w - hi);
+    }
+    for (int c = tid; c < C; c += nth) {
+        reinterpret_cast<float*>(out + SpParams<CF>::bq)[c] = qkv_b ? qkv_b[c] * qs : 0.f;
+        float v = proj_b[c];
+        if (qkv_b != nullptr)
+            for (int k = 0; k < C; ++k) v = fmaf(proj_w[int64_t(c) * C + k], qkv_b[2 * C + k], v);
+        reinterpret_cast<float*>(out + SpParams<CF>::bpf)[c] = v;
+    }
+    for (int e = tid; e < H * CF::TBL; e += nth)
+        reinterpret_cast<float*>(out + SpParams<CF>::tbl)[e] = table[(e % CF::TBL) * H + e / CF::TBL] * kLog2e;
+    for (int n = tid; n < 16; n += nth)
+        *reinterpret_cast<uint16_t*>(out + SpParams<CF>::i16 + sw128_offset(n, n)) = f16_bits(1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ scan / compaction
+struct SpWs {             // workspace layout: counts (kept, dropped), keep flags, kept list, dropped list
+    int64_t count, flags, list, dlist, total;
+    __host__ __device__ explicit SpWs(int64_t nwin) {
+        count = 0;
+        flags = 16;
+        list = align_up(flags + nwin, 16);
+        dlist = align_up(list + 4 * (nwin + 16), 16);
+        total = align_up(dlist + 4 * (nwin + 16), 256);
+    }
+};
+
+// single block: ordered lists of kept and of dropped windows (flags == nullptr: every window kept)
+__global__ void __launch_bounds__(1024)
+mwa_sp_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __restrict__ list, int32_t* __restrict__ dlist,
+                      int32_t* __restrict__ count) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (nwin + 1023) / 1024;
+    const int beg = min(tid * per, nwin), end = min(beg + per, nwin);
+    int n = 0;
+    for (int i = beg; i < end; ++i) n += flags ? flags[i] : 1;
+    part[tid] = n;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int pos = part[tid] - n, dpos = beg - pos;
+    for (int i = beg; i < end; ++i) {
+        if (!flags || flags[i]) list[pos++] = i;
+        else dlist[dpos++] = i;
+    }
+    if (tid == 1023) {
+        count[0] = part[1023];
+        count[1] = nwin - part[1023];
+    }
+}
+
+// out = x on the dropped windows (the block is the identity there, layers/masked_win_attention.py:249 adds zeros).
+// One warp per (window, 48-channel part): a warp iteration moves 2 channels x 8 rows x 8 px as float4s.
+__global__ void __launch_bounds__(256)
+mwa_sp_copy_dropped_kernel(const float* __restrict__ x, float* __restrict__ out, Geom g, int C,
+                           const int32_t* __restrict__ dlist, const int32_t* __restrict__ count) {
+    constexpr int WS = 8, PARTS = 4;
+    const int n = count[1];
+    const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int64_t hw = int64_t(g.H) * g.W;
+    const int cpp = C / PARTS;
+    const bool vec = (g.shift % 4 == 0) && (g.W % 4 == 0);
+    for (int i = gw; i < n * PARTS; i += nw) {
+        int b, wy, wx;
+        window_coords(g, dlist[i / PARTS], b, wy, wx);
+        const int c0 = (i % PARTS) * cpp;
+        if (vec) {
+            const int ty = (lane & 15) >> 1, tx = (lane & 1) * 4;
+            int py = wy * WS + ty + g.shift, px = wx * WS + tx + g.shift;
+            if (py >= g.H) py -= g.H;
+            if (px >= g.W) px -= g.W;
+            const int64_t off = (int64_t(b) * C + c0 + (lane >> 4)) * hw + int64_t(py) * g.W + px;
+            constexpr int U = 8;
+            for (int c = 0; c < cpp; c += 2 * U) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (c + 2 * u < cpp) v[u] = __ldcs(reinterpret_cast<const float4*>(x + off + int64_t(c + 2 * u) * hw));
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (c + 2 * u < cpp) __stcs(reinterpret_cast<float4*>(out + off + int64_t(c + 2 * u) * hw), v[u]);
+            }
+        } else {
+            for (int t = lane; t < 64; t += 32) {
+                int py, px;
+                token_pixel<WS>(g, wy, wx, t, py, px);
+                const int64_t off = (int64_t(b) * C + c0) * hw + int64_t(py) * g.W + px;
+                for (int c = 0; c < cpp; ++c) out[off + c * hw] = __ldg(x + off + c * hw);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small helpers
+template <int N>
+__device__ __forceinline__ void sp_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void sp_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ float sp_ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// fp16 hi / lo split of two values: hi = rn(v), lo = rn(v - hi), packed (first value in the low half)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_f16x2(a - hf.x, b - hf.y);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+template <class CF, bool kTiming>
+__global__ void __launch_bounds__(kSpThreads, 1)
+mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ sp,
+              const int32_t* __restrict__ list, const int32_t* __restrict__ count_p, Geom geo,
+              unsigned long long* __restrict__ timing, const __grid_constant__ CUtensorMap x_map) {
+    constexpr int C = CF::C, WS = CF::WS, D = CF::D, H = CF::HEADS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sb = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF::oBars);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + CF::oTmem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup
+    if (tid == 0) {
+        if (sb & 1023u) __trap();
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bars + CF::bXhFull + i, kSpNumPe * 32);
+            mbar_init(bars + CF::bXhEmpty + i, 1);
+            mbar_init(bars + CF::bWqFull + i, 1);
+            mbar_init(bars + CF::bWqEmpty + i, 1);
+            mbar_init(bars + CF::bWpFull + i, 1);
+            mbar_init(bars + CF::bWpEmpty + i, 1);
+        }
+        mbar_init(bars + CF::bXlFull, kSpNumPe * 32);
+        mbar_init(bars + CF::bXlEmpty, 1);
+        mbar_init(bars + CF::bDqFull, 1);
+        mbar_init(bars + CF::bDqEmpty, 128);
+        mbar_init(bars + CF::bQkReady, 128);
+        mbar_init(bars + CF::bVReady, 128);
+        mbar_init(bars + CF::bQkFree, 1);
+        mbar_init(bars + CF::bVFree, 1);
+        mbar_init(bars + CF::bSFull, 1);
+        mbar_init(bars + CF::bPReady, 128);
+        mbar_init(bars + CF::bOFull, 1);
+        mbar_init(bars + CF::bOAReady, 128);
+        mbar_init(bars + CF::bOAFree, 1);
+        mbar_init(bars + CF::bPjFull, 1);
+        mbar_init(bars + CF::bPjEmpty, kSpNumPe * 32);
+        for (int i = 0; i < 6; ++i) {
+            mbar_init(bars + CF::bStFull + i, 1);
+            mbar_init(bars + CF::bStEmpty + i, 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kSpFeed) tmem_alloc<512>(tmem_ptr);
+    {
+        const float* gt = reinterpret_cast<const float*>(sp + SpParams<CF>::tbl);
+        float* st = reinterpret_cast<float*>(smem + CF::oTbl);
+        for (int i = tid; i < H * CF::TBL; i += kSpThreads) st[i] = gt[i];
+        const float* gb = reinterpret_cast<const float*>(sp + SpParams<CF>::bq);       // bq and bpf are adjacent
+        float* sbq = reinterpret_cast<float*>(smem + CF::oBq);
+        for (int i = tid; i < 2 * C; i += kSpThreads) sbq[i] = gb[i];
+        const uint4* gi = reinterpret_cast<const uint4*>(sp + SpParams<CF>::i16);
+        for (int i = tid; i < 2048 / 16; i += kSpThreads) reinterpret_cast<uint4*>(smem + CF::oI16)[i] = gi[i];
+        // Q | K rows incl. the zero block and the pad chunks, V rows: must read as zeros wherever nothing is written
+        for (int i = tid; i < (CF::oWq - CF::oQK) / 16; i += kSpThreads)
+            reinterpret_cast<uint4*>(smem + CF::oQK)[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = *tmem_ptr;
+
+    const int count = *count_p;
+    const int num_tiles = (count + 1) / 2;
+    const int64_t hw = int64_t(geo.H) * geo.W;
+    auto tile_of = [&](int it) -> int { return it * int(gridDim.x) + int((blockIdx.x + unsigned(it)) % gridDim.x); };
+    int my_tiles;
+    {
+        const int full = num_tiles / int(gridDim.x), rem = num_tiles - full * int(gridDim.x);
+        my_tiles = full + ((int((blockIdx.x + unsigned(full)) % gridDim.x) < rem) ? 1 : 0);
+    }
+    const int total = my_tiles * H;                       // heads this CTA processes (global head index G = it * H + h)
+    const long long t_cta0 = (kTiming && timing != nullptr) ? clock64() : 0;
+
+    if (warp < 4) {
+        // =========================================================================================== control warps
+        sp_reg_dec<kSpRegsCtl>();
+        if (warp == kSpMma && lane == 0) {
+            constexpr uint32_t id_q = umma_idesc(kFmtF16, kFmtF16, 128, CF::NQH), id_c = umma_idesc(kFmtF16, kFmtF16, 128, CF::NVC);
+            constexpr uint32_t id_s = umma_idesc(kFmtF16, kFmtF16, 128, 64);
+            constexpr uint32_t id_o = umma_idesc(kFmtF16, kFmtF16, 128, CF::ON) | kUmmaBMajorMN;
+            constexpr uint32_t id_p = umma_idesc(kFmtF16, kFmtF16, 128, 96), id_r = umma_idesc(kFmtF16, kFmtF16, 128, 16);
+            uint32_t nq = 0, np = 0;                       // weight chunks consumed from the two rings
+            int next_q = 0;                                // next head whose QKV MMAs are to be issued
+            auto issue_qkv = [&](int q) {
+                const int it = q / H, h = q - it * H, xb = it & 1;
+                if (h == 0) {
+                    mbar_wait(bars + CF::bXhFull + xb, (it >> 1) & 1);
+                    mbar_wait(bars + CF::bXlFull, it & 1);
+                }
+                if (q > 0) mbar_wait(bars + CF::bDqEmpty, (q - 1) & 1);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kb = 0; kb < CF::KB; ++kb) {
+                    const uint32_t slot = nq & 1;
+                    mbar_wait(bars + CF::bWqFull + slot, (nq >> 1) & 1);
+                    tc_fence_after_sync();
+                    const uint64_t a0 = umma_desc_k_sw128(sb + CF::oXh + xb * 49152 + kb * 16384);
+                    const uint32_t wbase = sb + CF::oWq + slot * CF::kWqChunk;
+                    const uint64_t b0 = umma_desc_k_sw128(wbase), bv = umma_desc_k_sw128(wbase + CF::VOFF * 128),
+                                   bl = umma_desc_k_sw128(wbase + CF::kWqHi);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, (kb | ks) != 0);
+                        umma_f16_ts(tm + CF::tDq + CF::VOFF, tm + CF::tXl + (kb * 4 + ks) * 8, bv + ks * 2, id_c, 1);
+                        umma_f16_ss(tm + CF::tDq + CF::VOFF, a0 + ks * 2, bl + ks * 2, id_c, 1);
+                    }
+                    umma_commit(bars + CF::bWqEmpty + slot);
+                    ++nq;
+                }
+                umma_commit(bars + CF::bDqFull);
+                if (h == H - 1) {
+                    umma_commit(bars + CF::bXhEmpty + xb);
+                    umma_commit(bars + CF::bXlEmpty);
+                }
+            };
+            auto issue_pv = [&](int G) {
+                mbar_wait(bars + CF::bVReady, G & 1);
+                mbar_wait(bars + CF::bPReady, G & 1);
+                tc_fence_after_sync();
+                const uint64_t vh = umma_desc_k_sw128(sb + CF::oVh), vl = umma_desc_k_sw128(sb + CF::oVl);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {           // 16 keys per step = 2048 bytes of the [key][128 B] buffers
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, vh + ks * 128, id_o, ks != 0);
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + 32 + ks * 8, vh + ks * 128, id_o, 1);
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, vl + ks * 128, id_o, 1);
+                }
+                umma_commit(bars + CF::bOFull);
+                umma_commit(bars + CF::bVFree);
+            };
+            auto issue_proj = [&](int G) {
+                const int it = G / H, h = G - it * H, xb = it & 1;
+                mbar_wait(bars + CF::bOAReady, G & 1);
+                if (h == 0) {
+                    // the accumulator starts as the residual x itself: D[:, 16j .. 16j+15] = X_hi(j) I + X_lo(j) I
+                    if (it > 0) mbar_wait(bars + CF::bPjEmpty, (it - 1) & 1);
+                    tc_fence_after_sync();
+                    const uint64_t bi = umma_desc_k_sw128(sb + CF::oI16);
+#pragma unroll
+                    for (int ks = 0; ks < CF::KSTEPS; ++ks) {
+                        const uint64_t a = umma_desc_k_sw128(sb + CF::oXh + xb * 49152 + (ks >> 2) * 16384) + (ks & 3) * 2;
+                        umma_f16_ss(tm + CF::tPj + ks * 16, a, bi, id_r, 0);
+                        umma_f16_ts(tm + CF::tPj + ks * 16, tm + CF::tXl + ks * 8, bi, id_r, 1);
+                    }
+                }
+                tc_fence_after_sync();
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {
+                    const uint32_t slot = np & 1;
+                    mbar_wait(bars + CF::bWpFull + slot, (np >> 1) & 1);
+                    tc_fence_after_sync();
+                    const uint64_t b0 = umma_desc_k_sw128(sb + CF::oWp + slot * CF::kWpChunk);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + ks * 2, id_p, 1);
+                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + 16 + ks * 8, b0 + ks * 2, id_p, 1);
+                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + 4 + ks * 2, id_p, 1);
+                    }
+                    umma_commit(bars + CF::bWpEmpty + slot);
+                    ++np;
+                }
+                umma_commit(bars + CF::bOAFree);
+                if (h == H - 1) umma_commit(bars + CF::bPjFull);
+            };
+            for (int G = 0; G < total; ++G) {
+                if (next_q <= G) issue_qkv(next_q++);
+                // ---- S(G) = [Q_w0; 0] K_w0^T + [0; Q_w1] K_w1^T
+                mbar_wait(bars + CF::bQkReady, G & 1);
+                tc_fence_after_sync();
+                {
+                    const uint32_t w0 = sb + CF::oQK, z = w0 + 8192, w1 = w0 + 16384;
+                    const uint64_t a0 = umma_desc_k_sw128(w0), az = umma_desc_k_sw128(z);
+                    const uint64_t k0 = umma_desc_k_sw128(w0 + 64), k1 = umma_desc_k_sw128(w1 + 64);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        umma_f16_ss(tm + CF::tS, a0 + ks * 2, k0 + ks * 2, id_s, ks != 0);
+                        umma_f16_ss(tm + CF::tS, az + ks * 2, k1 + ks * 2, id_s, 1);
+                    }
+                    umma_commit(bars + CF::bSFull);
+                    umma_commit(bars + CF::bQkFree);
+                }
+                if (next_q < total) issue_qkv(next_q++);     // QKV(G + 1) fills the tensor pipe during softmax(G)
+                if constexpr (CF::kSepOA) {
+                    issue_pv(G);
+                    if (G > 0) issue_proj(G - 1);
+                } else {
+                    if (G > 0) issue_proj(G - 1);            // reads the projection operand before P V overwrites it
+                    issue_pv(G);
+                }
+            }
+            if (total > 0) issue_proj(total - 1);
+        } else if (warp == kSpFeed && lane == 0) {
+            // weight feeder: two rings of bulk copies, each in exactly the order the issuer consumes it
+            const uint8_t* gq = sp + SpParams<CF>::wq;
+            const uint8_t* gp = sp + SpParams<CF>::wp;
+            const uint32_t nQ = uint32_t(total) * CF::KB, nP = uint32_t(total) * 2;
+            uint32_t iq = 0, ip = 0;
+            while (iq < nQ || ip < nP) {
+                if (iq < nQ) {
+                    const uint32_t slot = iq & 1;
+                    if (iq < 2 || mbar_test_wait(bars + CF::bWqEmpty + slot, ((iq >> 1) - 1) & 1)) {
+                        const uint32_t h = (iq / CF::KB) % H, kb = iq % CF::KB;
+                        mbar_arrive_expect_tx(bars + CF::bWqFull + slot, CF::kWqChunk);
+                        bulk_g2s(smem + CF::oWq + slot * CF::kWqChunk, gq + int64_t(h * CF::KB + kb) * CF::kWqStride,
+                                 CF::kWqChunk, bars + CF::bWqFull + slot);
+                        ++iq;
+                    }
+                }
+                if (ip < nP) {
+                    const uint32_t slot = ip & 1;
+                    if (ip < 2 || mbar_test_wait(bars + CF::bWpEmpty + slot, ((ip >> 1) - 1) & 1)) {
+                        const uint32_t h = (ip >> 1) % H, nh = ip & 1;
+                        mbar_arrive_expect_tx(bars + CF::bWpFull + slot, CF::kWpChunk);
+                        bulk_g2s(smem + CF::oWp + slot * CF::kWpChunk, gp + int64_t(h * 2 + nh) * CF::kWpChunk, CF::kWpChunk,
+                                 bars + CF::bWpFull + slot);
+                        ++ip;
+                    }
+                }
+            }
+        } else if (warp >= kSpTma0) {
+            // TMA gather issuer of window slot w: 12 boxes [16 ch][8][8] per window, channel halves interleaved in the
+            // order the converter warps consume them; windows that wrap round the image border are left to the LSU path
+            const int w = warp - kSpTma0;
+            uint32_t n = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int lidx = tile_of(i) * 2 + w;
+                if (lidx >= count) continue;
+                int b_, wy_, wx_;
+                window_coords(geo, list[lidx], b_, wy_, wx_);
+                const int x0 = wx_ * WS + geo.shift, y0 = wy_ * WS + geo.shift;
+                if (MWA_SP_NO_TMA || x0 + WS > geo.W || y0 + WS > geo.H) continue;
+                for (int j = 0; j < 12; ++j, ++n) {
+                    const int k = (j & 1) * 6 + (j >> 1);
+                    const uint32_t slot = n % 3;
+                    if (n >= 3) mbar_wait(bars + CF::bStEmpty + w * 3 + slot, ((n / 3) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(bars + CF::bStFull + w * 3 + slot, 4096);
+                        tma_load_4d(smem + CF::oStage + (slot * 2 + w) * 4096, &x_map, x0, y0, k * 16, b_,
+                                    bars + CF::bStFull + w * 3 + slot);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < kSpSm0) {
+        // =========================================================================================== x converter + epilogue
+        sp_reg_inc<kSpRegsPe>();
+        const int pw = warp - kSpPe0, q = pw & 3, half = pw >> 2;
+        const int r = q * 32 + lane, wslot = r >> 6, tok = r & 63;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float* s_bpf = reinterpret_cast<const float*>(smem + CF::oBpf);
+        uint32_t lo[6][8];                                   // fp16 lo parts of this thread's 96 channels of the NEXT tile
+        uint32_t stage_n = 0;                                // boxes of this thread's window slot consumed so far
+        // per-tile window info of this thread's token
+        struct Win {
+            bool valid, staged;
+            int64_t base;                                    // NCHW element offset of (b, c = 0, py, px)
+        };
+        auto win_of = [&](int tile) -> Win {
+            Win wi;
+            const int lidx = tile * 2 + wslot;
+            wi.valid = lidx < count;
+            int b, wy, wx, py, px;
+            window_coords(geo, list[wi.valid ? lidx : (count - 1)], b, wy, wx);
+            wi.staged = !MWA_SP_NO_TMA && wi.valid && (wx * WS + geo.shift + WS <= geo.W) && (wy * WS + geo.shift + WS <= geo.H);
+            token_pixel<WS>(geo, wy, wx, tok, py, px);
+            wi.base = int64_t(b) * C * hw + int64_t(py) * geo.W + px;
+            return wi;
+        };
+        // box jj (0..11) of the window's stream: channels k*16 .. k*16+15 with k = (jj & 1) * 6 + (jj >> 1); this thread
+        // converts the boxes of its own half.  EVERY thread of the window observes every box (a parity wait may lag an
+        // mbarrier by one phase only).
+        auto gather_box = [&](const Win& wi, int jj, int xb) {
+            float v[16];
+            uint64_t* release = nullptr;                     // staging slot to hand back once its values have been consumed
+            if (wi.staged) {
+                const uint32_t nb = stage_n + jj, slot = nb % 3;
+                mbar_wait(bars + CF::bStFull + wslot * 3 + slot, (nb / 3) & 1);
+                if ((jj & 1) != half) {
+                    mbar_arrive(bars + CF::bStEmpty + wslot * 3 + slot);
+                    return;
+                }
+                const uint32_t base = sb + CF::oStage + (slot * 2 + wslot) * 4096 + tok * 4;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = sp_ld_shared_f32(base + c * 256);
+                release = bars + CF::bStEmpty + wslot * 3 + slot;
+            } else {
+                if ((jj & 1) != half) return;
+                const float* p = x + wi.base + int64_t((half * 6 + (jj >> 1)) * 16) * hw;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = wi.valid ? __ldg(p + c * hw) : 0.f;
+            }
+            const int i = jj >> 1, k = half * 6 + i;
+            uint32_t hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[i][j]);
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int ci = 2 * k + c2;                   // 8-channel chunk index 0..23
+                const uint32_t addr = sb + CF::oXh + xb * 49152 + (ci >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 +
+                                      (((ci & 7) ^ (r & 7)) << 4);
+                st_shared_v4(addr, hi[4 * c2], hi[4 * c2 + 1], hi[4 * c2 + 2], hi[4 * c2 + 3]);
+            }
+            // The slot is released only AFTER the loaded values have been used: an mbarrier arrive does not wait for
+            // ld.shared instructions still queued in the LSU (behind the epilogue's global stores they can be hundreds of
+            // cycles late), and the TMA would overwrite the box under them.  Seen on the hardware as stale tail channels.
+            if (release != nullptr) mbar_arrive(release);
+        };
+        auto box_ready = [&](const Win& wi, int jj) -> bool {
+            if (!wi.staged) return true;
+            const uint32_t nb = stage_n + jj, slot = nb % 3;
+            return __all_sync(0xffffffffu, mbar_test_wait(bars + CF::bStFull + wslot * 3 + slot, (nb / 3) & 1));
+        };
+        auto publish_lo = [&](int it_next) {                 // X_lo of tile it_next -> TMEM (columns = channel pairs)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) tmem_st_x8(tm + CF::tXl + lane_addr + (half * 6 + i) * 8, lo[i]);
+            tmem_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(bars + CF::bXlFull);
+            (void)it_next;
+        };
+        if (my_tiles > 0) {
+            const Win w0 = win_of(tile_of(0));
+#pragma unroll
+            for (int jj = 0; jj < 12; ++jj) gather_box(w0, jj, 0);
+            if (w0.staged) stage_n += 12;
+            fence_proxy_async_smem();
+            mbar_arrive(bars + CF::bXhFull + 0);
+            publish_lo(0);
+        }
+        // iteration `it` runs while tile `it` is computed: epilogue of tile it - 1 interleaved with the conversion of
+        // tile it + 1.  The box index is a compile-time constant (the lo parts live in registers), the epilogue step is
+        // not: one epilogue step per box, plus as many as fit while a box has not landed yet.
+        for (int it = 0; it <= my_tiles; ++it) {
+            const bool do_epi = it >= 1, do_gather = it + 1 < my_tiles;
+            if (!do_epi && !do_gather) continue;
+            Win wn{false, false, 0}, wp{false, false, 0};
+            const int xb = (it + 1) & 1;
+            if (do_gather) {
+                wn = win_of(tile_of(it + 1));
+                if (it >= 1) mbar_wait(bars + CF::bXhEmpty + xb, ((it - 1) >> 1) & 1);
+            }
+            float* orow = out;
+            int estep = 12;
+            if (do_epi) {
+                wp = win_of(tile_of(it - 1));
+                orow = out + wp.base + int64_t(half * 96) * hw;
+                mbar_wait(bars + CF::bPjFull, (it - 1) & 1);
+                tc_fence_after_sync();
+                estep = 0;
+            }
+            auto epi_step = [&]() {
+                uint32_t acc[8];
+                tmem_ld_x8(tm + CF::tPj + lane_addr + half * 96 + estep * 8, acc);
+                tmem_wait_ld();
+                if (estep == 11) {                           // last TMEM read of the tile: hand the accumulator back
+                    tc_fence_before_sync();
+                    mbar_arrive(bars + CF::bPjEmpty);
+                }
+                if (wp.valid && !MWA_SP_EPI_NOSTORE) {
+                    float* o = orow + int64_t(estep * 8) * hw;
+                    const float* bp = s_bpf + half * 96 + estep * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[int64_t(j) * hw] = __uint_as_float(acc[j]) + bp[j];
+                }
+                ++estep;
+            };
+            if (do_gather) {
+#pragma unroll
+                for (int jj = 0; jj < 12; ++jj) {
+                    do {
+                        if (estep < 12) epi_step();
+                    } while (!MWA_SP_FUSE_BLOCKING && estep < 12 && (MWA_SP_NO_FUSE || !box_ready(wn, jj)));
+                    gather_box(wn, jj, xb);
+                }
+            }
+            while (estep < 12) epi_step();
+            if (do_gather) {
+                if (wn.staged) stage_n += 12;
+                fence_proxy_async_smem();
+                mbar_arrive(bars + CF::bXhFull + xb);
+                mbar_wait(bars + CF::bXlEmpty, it & 1);      // the correction MMAs of tile `it` have read X_lo
+                tc_fence_after_sync();
+                publish_lo(it + 1);
+            }
+        }
+    } else if (warp < kSpDr0) {
+        // =========================================================================================== softmax + normalisation
+        sp_reg_inc<kSpRegsSm>();
+        const int sw = warp - kSpSm0, r = sw * 32 + lane, wslot = r >> 6, tok = r & 63;
+        const int yi = tok >> 3, xi = tok & 7;
+        const uint32_t lane_addr = static_cast<uint32_t>(sw * 32) << 16;
+        const uint32_t tbl0 = sb + CF::oTbl + 4 * ((yi + WS - 1) * (2 * WS - 1) + xi + WS - 1);
+        for (int it = 0; it < my_tiles; ++it) {
+            // SW-MSA region mask bits of this row (:194-216); zero unless the window touches the wrapped border
+            uint32_t mb0 = 0, mb1 = 0;
+            bool has_mask = false;
+            if (geo.shift > 0) {
+                const int lidx = tile_of(it) * 2 + wslot;
+                int b_, wy, wx;
+                window_coords(geo, list[lidx < count ? lidx : count - 1], b_, wy, wx);
+                has_mask = (wy == geo.nwy - 1) || (wx == geo.nwx - 1);
+                if (has_mask) {
+                    const int ys0 = wy * WS, xs0 = wx * WS;
+                    const int by = (ys0 + yi >= geo.H - WS) + (ys0 + yi >= geo.H - geo.shift);
+                    const int bx = (xs0 + xi >= geo.W - WS) + (xs0 + xi >= geo.W - geo.shift);
+                    uint32_t dy = 0, dx = 0;
+#pragma unroll
+                    for (int j = 0; j < WS; ++j) {
+                        dy |= uint32_t(((ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift)) != by) << j;
+                        dx |= uint32_t(((xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift)) != bx) << j;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        mb0 |= (((dy >> (j >> 3)) | (dx >> (j & 7))) & 1u) << j;
+                        mb1 |= (((dy >> (4 + (j >> 3))) | (dx >> (j & 7))) & 1u) << j;
+                    }
+                }
+            }
+            for (int h = 0; h < H; ++h) {
+                const int G = it * H + h;
+                mbar_wait(bars + CF::bSFull, G & 1);
+                tc_fence_after_sync();
+                float s[64];
+                {
+                    uint32_t raw[32];
+                    tmem_ld_x32(tm + CF::tS + lane_addr, raw);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
+                    tmem_ld_x32(tm + CF::tS + lane_addr + 32, raw);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
+                }
+                // relative-position bias (layers/masked_win_attention.py:109-112), table pre-multiplied by log2(e)
+                const uint32_t tb = tbl0 + h * (CF::TBL * 4);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) s[j] += sp_ld_shared_f32(tb - 4 * ((j >> 3) * (2 * WS - 1) + (j & 7)));
+                if (has_mask) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((mb0 >> j) & 1u) s[j] += kNegMaskL2;
+                        if ((mb1 >> j) & 1u) s[32 + j] += kNegMaskL2;
+                    }
+                }
+                float m = s[0];
+#pragma unroll
+                for (int j = 1; j < 63; j += 2) m = max3(m, s[j], s[j + 1]);
+                m = fmaxf(m, s[63]);
+                float sum = 0.f;
+                uint32_t ph[32], pl[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float p0 = ex2(s[2 * j] - m), p1 = ex2(s[2 * j + 1] - m);
+                    sum += p0 + p1;
+                    split_f16x2(p0, p1, ph[j], pl[j]);
+                }
+                tmem_st_x32(tm + CF::tS + lane_addr, ph);
+                tmem_st_x32(tm + CF::tS + lane_addr + 32, pl);
+                tmem_wait_st();
+                tc_fence_before_sync();
+                mbar_arrive(bars + CF::bPReady);
+                const float inv = 1.0f / sum;
+                // ---- O / rowsum -> fp16 hi / lo, the projection's A operand
+                mbar_wait(bars + CF::bOFull, G & 1);
+                tc_fence_after_sync();
+                uint32_t oraw[D];
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tO + lane_addr + wslot * D + c * 8, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) oraw[c * 8 + j] = t8[j];
+                }
+                tmem_wait_ld();
+                if (CF::kSepOA && G > 0) mbar_wait(bars + CF::bOAFree, (G - 1) & 1);
+                uint32_t oh[16], ol[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (2 * j < D) split_f16x2(__uint_as_float(oraw[2 * j]) * inv, __uint_as_float(oraw[2 * j + 1]) * inv, oh[j], ol[j]);
+                    else oh[j] = ol[j] = 0u;
+                }
+                tmem_st_x16(tm + CF::tOA + lane_addr, oh);
+                tmem_st_x16(tm + CF::tOA + lane_addr + 16, ol);
+                tmem_wait_st();
+                tc_fence_before_sync();
+                mbar_arrive(bars + CF::bOAReady);
+            }
+        }
+    } else {
+        // =========================================================================================== QKV drain
+        sp_reg_dec<kSpRegsDr>();
+        const int dw = warp - kSpDr0, r = dw * 32 + lane, wslot = r >> 6, tok = r & 63;
+        const uint32_t lane_addr = static_cast<uint32_t>(dw * 32) << 16;
+        const uint32_t rowoff = (tok >> 3) * 1024 + (tok & 7) * 128, sx = tok & 7;
+        const uint32_t qk_row = sb + CF::oQK + wslot * 16384 + rowoff;
+        const float* s_bq = reinterpret_cast<const float*>(smem + CF::oBq);
+        for (int G = 0; G < total; ++G) {
+            const int h = G % H;
+            mbar_wait(bars + CF::bDqFull, G & 1);
+            tc_fence_after_sync();
+            uint32_t raw[2 * D];                               // q | k columns
+#pragma unroll
+            for (int c = 0; c < 2 * D / 8; ++c) {
+                uint32_t t8[8];
+                tmem_ld_x8(tm + CF::tDq + lane_addr + c * 8, t8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) raw[c * 8 + j] = t8[j];
+            }
+            tmem_wait_ld();
+            if (G > 0) mbar_wait(bars + CF::bQkFree, (G - 1) & 1);
+#pragma unroll
+            for (int ch = 0; ch < D / 8; ++ch) {               // q (+ bias) -> chunks 0.., k -> chunks 4..
+                uint32_t pq[4], pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = ch * 8 + 2 * j;
+                    pq[j] = pack_f16x2(__uint_as_float(raw[c]) + s_bq[h * D + c], __uint_as_float(raw[c + 1]) + s_bq[h * D + c + 1]);
+                    pk[j] = pack_f16x2(__uint_as_float(raw[D + c]), __uint_as_float(raw[D + c + 1]));
+                }
+                st_shared_v4(qk_row + ((uint32_t(ch) ^ sx) << 4), pq[0], pq[1], pq[2], pq[3]);
+                st_shared_v4(qk_row + ((uint32_t(4 + ch) ^ sx) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bars + CF::bQkReady);
+            uint32_t rv[D];                                    // v columns
+#pragma unroll
+            for (int c = 0; c < D / 8; ++c) {
+                uint32_t t8[8];
+                tmem_ld_x8(tm + CF::tDq + lane_addr + 2 * D + c * 8, t8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rv[c * 8 + j] = t8[j];
+            }
+            tmem_wait_ld();
+            tc_fence_before_sync();
+            mbar_arrive(bars + CF::bDqEmpty);                  // the accumulator may be overwritten by QKV(G + 1)
+            if (G > 0) mbar_wait(bars + CF::bVFree, (G - 1) & 1);
+#pragma unroll
+            for (int ch = 0; ch < D / 8; ++ch) {               // v -> hi / lo rows [key][slot 0 d | slot 1 d]
+                uint32_t vh[4], vl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = ch * 8 + 2 * j;
+                    split_f16x2(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]), vh[j], vl[j]);
+                }
+                const uint32_t off = rowoff + ((uint32_t(wslot * (D / 8) + ch) ^ sx) << 4);
+                st_shared_v4(sb + CF::oVh + off, vh[0], vh[1], vh[2], vh[3]);
+                st_shared_v4(sb + CF::oVl + off, vl[0], vl[1], vl[2], vl[3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bars + CF::bVReady);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kSpFeed) tmem_dealloc<512>(tm);
+    if constexpr (kTiming) {      // per-CTA totals: [64 + cta] cycles, [64 + 256 + cta] tiles (buffer of 4096 u64)
+        if (timing != nullptr && tid == 0) {
+            timing[64 + blockIdx.x] = static_cast<unsigned long long>(clock64() - t_cta0);
+            timing[64 + 256 + blockIdx.x] = my_tiles;
+        }
+    }
+}
+
+unsigned long long* g_sp_timing = nullptr;
+
+typedef CUresult (*SpEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// 4-D tiled tensor map over the NCHW fp32 input, box = [16 ch][8][8]: one 16-channel slice of an 8 x 8 window
+int sp_window_box_map(const float* x, int B, int C, int H, int W, CUtensorMap* map) {
+    static SpEncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MWA_TRY_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "mwa_forward(tensor map)");
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return MWA_ERR_UNSUPPORTED;
+        encode = reinterpret_cast<SpEncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[4] = {cuuint64_t(W), cuuint64_t(H), cuuint64_t(C), cuuint64_t(B)};
+    const cuuint64_t strides[3] = {cuuint64_t(W) * 4, cuuint64_t(H) * W * 4, cuuint64_t(C) * H * W * 4};
+    const cuuint32_t box[4] = {8, 8, 16, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MWA_OK : MWA_ERR_UNSUPPORTED;
+}
+
+template <class CF>
+int launch_sp(const float* x, const float* alpha, float* out, const uint8_t* sp, int B, int H, int W, int shift,
+              int32_t* kept_count, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    const Geom geo{B, H, W, shift, W / CF::WS, H / CF::WS, 0};
+    const int64_t nwin64 = int64_t(B) * geo.nwx * geo.nwy;
+    if (nwin64 > 0x3fffffffll) return MWA_ERR_UNSUPPORTED;
+    const int nwin = static_cast<int>(nwin64);
+    const SpWs ws(nwin);
+    if (!workspace || workspace_bytes < ws.total) return MWA_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return MWA_ERR_ALIGNMENT;
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    int32_t* count = reinterpret_cast<int32_t*>(wsp + ws.count);
+    uint8_t* flags = wsp + ws.flags;
+    int32_t* list = reinterpret_cast<int32_t*>(wsp + ws.list);
+    int32_t* dlist = reinterpret_cast<int32_t*>(wsp + ws.dlist);
+    int rc;
+    if (alpha != nullptr) {
+        mwa_scan_kernel<CF::WS, 1><<<(nwin + 7) / 8, 256, 0, st>>>(x, alpha, out, geo, CF::C, nwin, flags, 0);
+        rc = check_launch("mwa_forward(scan)");
+        if (rc != MWA_OK) return rc;
+    }
+    mwa_sp_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, dlist, count);
+    rc = check_launch("mwa_forward(compact)");
+    if (rc != MWA_OK) return rc;
+    if (alpha != nullptr && out != x) {
+        mwa_sp_copy_dropped_kernel<<<kNumSMs * 4, 256, 0, st>>>(x, out, geo, CF::C, dlist, count);
+        rc = check_launch("mwa_forward(copy dropped)");
+        if (rc != MWA_OK) return rc;
+    }
+    CUtensorMap x_map;
+    memset(&x_map, 0, sizeof(x_map));
+    rc = sp_window_box_map(x, B, CF::C, H, W, &x_map);
+    if (rc != MWA_OK) return rc;
+    const int smem = CF::oTotal;
+    const int max_tiles = (nwin + 1) / 2;
+    const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+    if (g_sp_timing != nullptr) {
+        MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_sp_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                     "mwa_forward(sp attr)");
+        mwa_sp_kernel<CF, true><<<grid, kSpThreads, smem, st>>>(x, out, sp, list, count, geo, g_sp_timing, x_map);
+    } else {
+        MWA_TRY_CUDA(cudaFuncSetAttribute(mwa_sp_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                     "mwa_forward(sp attr)");
+        mwa_sp_kernel<CF, false><<<grid, kSpThreads, smem, st>>>(x, out, sp, list, count, geo, nullptr, x_map);
+    }
+    rc = check_launch("mwa_forward(tcgen05 split precision)");
+    if (rc != MWA_OK) return rc;
+    if (kept_count)
+        MWA_TRY_CUDA(cudaMemcpyAsync(kept_count, count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st), "mwa_forward(kept_count)");
+    return MWA_OK;
+}
+
+}  // namespace
+
+bool mwa_sp_supported(int C, int heads, int ws, int H, int W, int channels_last) {
+    if (channels_last) return false;
+    return C == 192 && ws == 8 && (heads == 8 || heads == 6) && H % 8 == 0 && W % 8 == 0 && W % 4 == 0;
+}
+int64_t mwa_sp_workspace_bytes(int64_t nwin) { return SpWs(nwin).total; }
+void mwa_sp_set_timing_buffer(void* p) { g_sp_timing = static_cast<unsigned long long*>(p); }
+
+void mwa_sp_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
+                           const float* table, int C, int heads, int ws, float scale, uint8_t* blk, cudaStream_t st) {
+    const int64_t bytes = mwa_sp_section_bytes(C, heads, ws);
+    if (bytes == 0) return;
+    const MwaParamLayout L(C, heads, ws);
+    uint8_t* dst = blk + L.img_sp;
+    zero16_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), bytes / 16);
+    if (heads == 8) mwa_sp_prepare_kernel<SpCfg<8>><<<kNumSMs, 256, 0, st>>>(qkv_w, qkv_b, proj_w, proj_b, table, scale, dst);
+    else mwa_sp_prepare_kernel<SpCfg<6>><<<kNumSMs, 256, 0, st>>>(qkv_w, qkv_b, proj_w, proj_b, table, scale, dst);
+}
+
+int mwa_forward_sp(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                   int heads, int ws, int shift, int32_t* kept_count, void* workspace, int64_t workspace_bytes,
+                   cudaStream_t st) {
+    const MwaParamLayout L(C, heads, ws);
+    const uint8_t* sp = static_cast<const uint8_t*>(params) + L.img_sp;
+    if (heads == 8) return launch_sp<SpCfg<8>>(x, alpha, out, sp, B, H, W, shift, kept_count, workspace, workspace_bytes, st);
+    if (heads == 6) return launch_sp<SpCfg<6>>(x, alpha, out, sp, B, H, W, shift, kept_count, workspace, workspace_bytes, st);
+    return MWA_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200

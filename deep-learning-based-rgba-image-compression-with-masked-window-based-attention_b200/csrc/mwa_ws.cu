@@ -682,7 +682,6 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                         float v[16];
 #pragma unroll
                         for (int c = 0; c < 16; ++c) v[c] = ld_shared_f32(base + c * 256);
-                        mbar_arrive(bars + MP::bSEmpty + wslot * 3 + slot);
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
                             if (prestore) *po = v[c];
@@ -692,6 +691,24 @@ mwa_ws_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                         for (int jp = 0; jp < 4; ++jp) {
                             pk[2 * i][jp] = pack_f16x2(v[2 * jp], v[2 * jp + 1]);
                             pk[2 * i + 1][jp] = pack_f16x2(v[8 + 2 * jp], v[8 + 2 * jp + 1]);
+                        }
+                        // Release the slot only after the loaded values have ARRIVED: an mbarrier arrive does not wait for
+                        // ld.shared instructions still queued in the LSU (behind global stores they can be hundreds of cycles
+                        // late; found with csrc/mwa_sp.cu in round 2, where the TMA overwrote boxes under their readers).
+                        // The arrive is predicated on a value computed from all 16 loads (cvt.satfinite never produces the
+                        // all-ones pattern, so the minimum of the packed words never equals it and the predicate is always
+                        // true -- but the hardware has to wait for the data).
+                        {
+                            uint32_t all = 0xffffffffu;
+#pragma unroll
+                            for (int jp = 0; jp < 4; ++jp) all = min(all, min(pk[2 * i][jp], pk[2 * i + 1][jp]));
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+                                "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(
+                                    smem_u32(bars + MP::bSEmpty + wslot * 3 + slot)),
+                                "r"(all)
+                                : "memory");
                         }
                     }
                     stage_n += C / 16;

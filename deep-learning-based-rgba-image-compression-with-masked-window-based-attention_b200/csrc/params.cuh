@@ -46,6 +46,16 @@ __host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
     return ng * (kb * nqkv * 128 + int64_t(C) * 128) + ng * nqkv * 4 + int64_t(C) * 4;
 }
 
+// size of the split-precision section (csrc/mwa_sp.cu, layout: SpParams<> there): per head the fp16 hi (+ lo for the v
+// rows) K-major SW128 slabs of Wq|Wk|Wv per 64-channel K block in ring-slot sized chunks, per head and output half the
+// [hi | lo] slab of Wproj, the scaled q bias, the projection bias with the v bias folded in, the relative-position
+// table times log2(e) and a 16 x 16 identity operand.  0 when the geometry is not covered.
+__host__ __device__ inline int64_t mwa_sp_section_bytes(int C, int heads, int ws) {
+    if (!(C == 192 && ws == 8 && (heads == 8 || heads == 6))) return 0;
+    const int64_t tbl = (2 * ws - 1) * (2 * ws - 1);
+    return int64_t(heads) * 3 * 16384 + int64_t(heads) * 2 * 12288 + 2 * int64_t(C) * 4 + align_up(heads * tbl * 4, 1024) + 2048;
+}
+
 struct MwaParamLayout {
     int C, heads, ws, N, d, dpad, kblocks;
     int64_t header;     // float[4]: scale, -, -, -
@@ -57,6 +67,7 @@ struct MwaParamLayout {
     int64_t img_wqkv;   // tcgen05 section (layout: TcParams<> in mwa_tc.cu): per head group the fp16 K-major SW128
                         // B-operand slabs of Wq|Wk|Wv (rows head-padded to 16/32, q rows pre-scaled) and of Wproj,
                         // followed by the qkv bias in the same padded order
+    int64_t img_sp;     // split-precision section (layout: SpParams<> in mwa_sp.cu)
     int64_t total;
     __host__ __device__ MwaParamLayout(int C_, int heads_, int ws_)
         : C(C_), heads(heads_), ws(ws_), N(ws_ * ws_), d(C_ / heads_), dpad(int(align_up(C_ / heads_, 16))),
@@ -69,6 +80,7 @@ struct MwaParamLayout {
         bproj = o;     o = align_up(o + 4ll * C, 1024);
         bias = o;      o = align_up(o + 4ll * heads * N * N, 1024);
         img_wqkv = o;  o = align_up(o + mwa_tc_section_bytes(C, heads), 1024);
+        img_sp = o;    o = align_up(o + mwa_sp_section_bytes(C, heads, ws), 1024);
         total = o;
     }
 };

@@ -40,9 +40,12 @@ enum {
     MWA_ERR_CUDA = -5          /* a CUDA runtime call failed (launch error) */
 };
 
-/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel;
- * TCGEN05_V1 forces the phase-serial first-generation attention kernel (kept for A/B measurements) */
-enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2, MWA_ALGO_TCGEN05_V1 = 3 };
+/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel.  For the shapes the
+ * split-precision kernel covers (C = 192, 8 x 8 windows, 6 or 8 heads, NCHW) AUTO and TCGEN05 run it: fp16 hi + lo
+ * operands, three MMA passes, every output within the reference's fp32 tolerance.  TCGEN05_FP16 forces the round-1
+ * single-pass fp16 kernel (faster, ~1e-4 absolute error: opt-in only); TCGEN05_V1 the phase-serial first-generation
+ * kernel (kept for A/B measurements). */
+enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2, MWA_ALGO_TCGEN05_V1 = 3, MWA_ALGO_TCGEN05_FP16 = 4 };
 
 MWA_API int mwa_b200_abi_version(void);
 MWA_API const char* mwa_b200_status_string(int status);
