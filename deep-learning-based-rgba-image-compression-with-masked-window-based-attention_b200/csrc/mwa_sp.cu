@@ -47,12 +47,12 @@
 namespace b200 {
 namespace {
 
-constexpr int kSpWarps = 20;
+constexpr int kSpWarps = 24;
 constexpr int kSpThreads = kSpWarps * 32;
 constexpr int kSpMma = 0, kSpFeed = 1, kSpTma0 = 2;
-constexpr int kSpPe0 = 4, kSpNumPe = 8, kSpSm0 = 12, kSpDr0 = 16;
-// register pool of the CTA = 20 warps x 96 (launch bound); per SM sub-partition 48 + 2 x 104 + 144 + 80 = 480 = 5 x 96
-constexpr int kSpRegsCtl = 48, kSpRegsPe = 104, kSpRegsSm = 144, kSpRegsDr = 80;
+constexpr int kSpPe0 = 4, kSpNumPe = 8, kSpSm0 = 12, kSpNumSm = 8, kSpDr0 = 20;
+// register pool of the CTA = 24 warps x 80 (launch bound); per SM sub-partition 40 + 2 x 96 + 2 x 88 + 72 = 480 = 6 x 80
+constexpr int kSpRegsCtl = 40, kSpRegsPe = 96, kSpRegsSm = 88, kSpRegsDr = 72;
 constexpr float kNegMaskL2 = kNegMask * kLog2e;
 
 template <int HEADS_>
@@ -60,48 +60,56 @@ struct SpCfg {
     static constexpr int C = 192, WS = 8, NTOK = 64, HEADS = HEADS_, D = C / HEADS;
     static_assert(D == 24 || D == 32, "head dim 24 / 32");
     static constexpr int KB = 3, KSTEPS = 12;
-    static constexpr int NQH = (3 * D + 15) / 16 * 16;       // QKV MMA N per head (q | k | v | pad)
-    static constexpr int VOFF = 2 * D;                       // first v column
-    static constexpr int NVC = NQH - VOFF;                   // N of the correction passes (v columns + pad) = 32
-    static constexpr int ON = 2 * D;                         // P V output columns: [window slot 0 d | slot 1 d]
+    // QKV weight chunk of a (head, 64-channel K block), one bulk copy, rows of 128 B (K-major SW128), no padding rows:
+    //   d = 24:  [q 24][k 24][v lo 24][v hi 24] = 96 rows.  ONE MMA with N = 96 over x_hi yields q, k, x_hi Wv_lo^T and
+    //            x_hi Wv_hi^T in 96 accumulator columns; the x_lo Wv_hi^T pass (A from TMEM, N = 32 from row 72: the 8
+    //            rows past the chunk are whatever follows in shared memory and only feed columns 96-103, never read)
+    //            accumulates onto columns 72-103; the drain adds the two v parts.
+    //   d = 32:  [q 32][k 32][v hi 32][v lo 32] = 128 rows.  N = 96 over x_hi, then two N = 32 passes onto columns 64-95
+    //            (x_lo Wv_hi^T from TMEM, x_hi Wv_lo^T): 128 accumulator columns do not fit the TMEM budget.
+    static constexpr bool kMergedLo = (D == 24);
+    static constexpr int NQH = 96;                           // N of the main QKV MMA
+    static constexpr int DQW = kMergedLo ? 104 : 96;         // accumulator columns of D_qkv
+    static constexpr int kVhiRow = kMergedLo ? 72 : 64;      // first v hi row of the chunk = first column of the TMEM pass
+    static constexpr int kVloRow = kMergedLo ? 48 : 96;      // first v lo row
     static constexpr int TBL = 225;
-    static constexpr bool kSepOA = (HEADS == 8);             // projection A operand in its own TMEM columns
-    static_assert(NVC == 32 && VOFF % 8 == 0, "v correction geometry");
-    // weight chunks (one bulk copy each)
-    static constexpr uint32_t kWqHi = NQH * 128, kWqChunk = kWqHi + NVC * 128, kWqStride = 16384;
+    static constexpr int ON = 2 * D;                         // P V output columns: [window slot 0 d | slot 1 d]
+    static constexpr uint32_t kWqChunk = 4 * D * 128;
     static constexpr uint32_t kWpChunk = 96 * 128;
-    // TMEM columns
-    static constexpr uint32_t tDq = 0, tPj = NQH, tS = tPj + C, tO = tS + 64, tOA = kSepOA ? tO + ON : tO, tXl = 416;
-    static_assert(tOA + 32 <= tXl && tO + ON <= tXl, "TMEM budget");
+    static constexpr int kWqSlots = (HEADS == 8) ? 3 : 2;    // a whole head's QKV weights in flight where they fit
+    // TMEM columns (the projection's A operand overwrites O in place)
+    static constexpr uint32_t tDq = 0, tPj = DQW, tS = tPj + C, tO = tS + 64, tOA = tO, tXl = 416;
+    static_assert(tO + ON <= tXl, "TMEM budget");
     // shared memory map
     static constexpr uint32_t oXh = 0;                       // 2 x (KB x [128 x 64] fp16)
-    static constexpr uint32_t oQK = 2 * 49152;               // [W0 64 rows][Z 64 zero rows][W1 64 rows] x 128 B: q | k
-    static constexpr uint32_t oVh = oQK + 24576, oVl = oVh + 8192;
-    static constexpr uint32_t oWq = oVl + 8192;              // 2 slots
-    static constexpr uint32_t oWp = oWq + 2 * kWqChunk;      // 2 slots
+    static constexpr uint32_t oQK = 2 * 49152;               // [128 rows] x 128 B: q (64 B) | k (64 B) of the head
+    static constexpr uint32_t oVh = oQK + 16384, oVl = oVh + 8192;
+    static constexpr uint32_t oWq = oVl + 8192;              // kWqSlots slots
+    static constexpr uint32_t oWp = oWq + kWqSlots * kWqChunk;   // 2 slots
     static constexpr uint32_t oStage = oWp + 2 * kWpChunk;   // 3 slots x 2 windows x 4 KB
     static constexpr uint32_t oI16 = oStage + 24576;
     static constexpr uint32_t oTbl = oI16 + 2048;
     static constexpr uint32_t oBq = (oTbl + HEADS * TBL * 4 + 15) / 16 * 16;
     static constexpr uint32_t oBpf = oBq + C * 4;
-    static constexpr uint32_t oBars = oBpf + C * 4;
+    static constexpr uint32_t oXch = oBpf + C * 4;            // fp32 [max | sum][column half][128 rows]: softmax warp pairs
+    static constexpr uint32_t oBars = oXch + 2048;
     static constexpr uint32_t oTmem = oBars + 64 * 8;
     static constexpr uint32_t oTotal = oTmem + 16;
     static_assert(oTotal <= 227 * 1024, "shared memory budget");
     static_assert(kWqChunk % 1024 == 0 && oWq % 1024 == 0 && oWp % 1024 == 0 && oI16 % 1024 == 0, "operand alignment");
     // barriers
-    static constexpr int bXhFull = 0, bXhEmpty = 2, bXlFull = 4, bXlEmpty = 5, bWqFull = 6, bWqEmpty = 8, bWpFull = 10,
-                         bWpEmpty = 12, bDqFull = 14, bDqEmpty = 15, bQkReady = 16, bVReady = 17, bQkFree = 18, bVFree = 19,
-                         bSFull = 20, bPReady = 21, bOFull = 22, bOAReady = 23, bOAFree = 24, bPjFull = 25, bPjEmpty = 26,
-                         bStFull = 27, bStEmpty = 33, bEnd = 39;
+    static constexpr int bXhFull = 0, bXhEmpty = 2, bXlFull = 4, bXlEmpty = 5, bWqFull = 6, bWqEmpty = 9, bWpFull = 12,
+                         bWpEmpty = 14, bDqFull = 16, bDqEmpty = 17, bQkReady = 18, bVReady = 19, bQkFree = 20, bVFree = 21,
+                         bSFull = 22, bPReady = 23, bOFull = 24, bOAReady = 25, bPjFull = 26, bPjEmpty = 27,
+                         bStFull = 28, bStEmpty = 34, bEnd = 40;
     static_assert(bEnd <= 64, "barrier slots");
 };
 
 // layout of the split-precision section of the parameter block (offsets from MwaParamLayout::img_sp)
 template <class CF>
 struct SpParams {
-    static constexpr int64_t wq = 0;                                                   // [HEADS][KB] x kWqStride
-    static constexpr int64_t wp = wq + int64_t(CF::HEADS) * CF::KB * CF::kWqStride;    // [HEADS][2] x kWpChunk
+    static constexpr int64_t wq = 0;                                                   // [HEADS][KB] x kWqChunk
+    static constexpr int64_t wp = wq + int64_t(CF::HEADS) * CF::KB * CF::kWqChunk;     // [HEADS][2] x kWpChunk
     static constexpr int64_t bq = wp + int64_t(CF::HEADS) * 2 * CF::kWpChunk;          // fp32 [C]  q bias * scale * log2e
     static constexpr int64_t bpf = bq + CF::C * 4;                                     // fp32 [C]  proj.bias + Wproj b_v
     static constexpr int64_t tbl = bpf + CF::C * 4;                                    // fp32 [HEADS][TBL] * log2e
@@ -124,10 +132,14 @@ __global__ void mwa_sp_prepare_kernel(const float* __restrict__ qkv_w, const flo
         const int part = n / D, c = n % D;
         float w = qkv_w[int64_t(part * C + h * D + c) * C + kb * 64 + kk];
         if (part == 0) w *= qs;
-        uint8_t* chunk = out + SpParams<CF>::wq + int64_t(h * CF::KB + kb) * CF::kWqStride;
+        uint8_t* chunk = out + SpParams<CF>::wq + int64_t(h * CF::KB + kb) * CF::kWqChunk;
         const float hi = f16_round(w);
-        *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, kk)) = f16_bits(w);
-        if (n >= CF::VOFF) *reinterpret_cast<uint16_t*>(chunk + CF::kWqHi + sw128_offset(n - CF::VOFF, kk)) = f16_bits(w - hi);
+        if (part < 2) {
+            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, kk)) = f16_bits(w);
+        } else {
+            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(CF::kVhiRow + c, kk)) = f16_bits(w);
+            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(CF::kVloRow + c, kk)) = f16_bits(w - hi);
+        }
     }
     for (int e = tid; e < H * 2 * 96 * D; e += nth) {
         const int h = e / (2 * 96 * D), nh = (e / (96 * D)) % 2, n = (e / D) % 96, kk = e % D;
@@ -238,9 +250,15 @@ template <int N>
 __device__ __forceinline__ void sp_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void sp_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void sp_st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sp_named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ float sp_ld_shared_f32(uint32_t addr) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
 // fp16 hi / lo split of two values: hi = rn(v), lo = rn(v - hi), packed (first value in the low half)
@@ -274,10 +292,12 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         for (int i = 0; i < 2; ++i) {
             mbar_init(bars + CF::bXhFull + i, kSpNumPe * 32);
             mbar_init(bars + CF::bXhEmpty + i, 1);
-            mbar_init(bars + CF::bWqFull + i, 1);
-            mbar_init(bars + CF::bWqEmpty + i, 1);
             mbar_init(bars + CF::bWpFull + i, 1);
             mbar_init(bars + CF::bWpEmpty + i, 1);
+        }
+        for (int i = 0; i < CF::kWqSlots; ++i) {
+            mbar_init(bars + CF::bWqFull + i, 1);
+            mbar_init(bars + CF::bWqEmpty + i, 1);
         }
         mbar_init(bars + CF::bXlFull, kSpNumPe * 32);
         mbar_init(bars + CF::bXlEmpty, 1);
@@ -288,10 +308,9 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         mbar_init(bars + CF::bQkFree, 1);
         mbar_init(bars + CF::bVFree, 1);
         mbar_init(bars + CF::bSFull, 1);
-        mbar_init(bars + CF::bPReady, 128);
+        mbar_init(bars + CF::bPReady, kSpNumSm * 32);
         mbar_init(bars + CF::bOFull, 1);
-        mbar_init(bars + CF::bOAReady, 128);
-        mbar_init(bars + CF::bOAFree, 1);
+        mbar_init(bars + CF::bOAReady, kSpNumSm * 32);
         mbar_init(bars + CF::bPjFull, 1);
         mbar_init(bars + CF::bPjEmpty, kSpNumPe * 32);
         for (int i = 0; i < 6; ++i) {
@@ -331,15 +350,34 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     }
     const int total = my_tiles * H;                       // heads this CTA processes (global head index G = it * H + h)
     const long long t_cta0 = (kTiming && timing != nullptr) ? clock64() : 0;
+    // development aid (kTiming instantiation only): event trace of CTA 0, first lane of the first warp of each role:
+    // timing[1024 + role * 1024 + i] = stage << 48 | cycles since kernel start at the END of the stage (buffer: 8192 u64)
+    const bool do_time = kTiming && timing != nullptr && blockIdx.x == 0 && lane == 0 &&
+                         (warp == kSpMma || warp == kSpPe0 || warp == kSpSm0 || warp == kSpDr0);
+    int n_ev = 0;
+    auto tick = [&](int slot) {
+        if constexpr (kTiming) {
+            if (do_time && n_ev < 1024)
+                timing[1024 + (slot >> 3) * 1024 + n_ev++] =
+                    (static_cast<unsigned long long>(slot) << 48) | static_cast<unsigned long long>(clock64() - t_cta0);
+        }
+    };
 
     if (warp < 4) {
         // =========================================================================================== control warps
         sp_reg_dec<kSpRegsCtl>();
-        if (warp == kSpMma && lane == 0) {
-            constexpr uint32_t id_q = umma_idesc(kFmtF16, kFmtF16, 128, CF::NQH), id_c = umma_idesc(kFmtF16, kFmtF16, 128, CF::NVC);
+        if (warp == kSpMma && elect_one()) {
+            // One elected thread of a CONVERGED warp (not `lane == 0`: a divergent branch makes every tcgen05.mma cost ~45
+            // cycles of issue, tools/umma_rate_probe.cu) issues every MMA of the CTA.  Measured cost per MMA (M = 128,
+            // K = 16): A from shared memory max(N/2, 32 + N/4) cycles, A from TMEM N/2.
+            constexpr uint32_t id_q = umma_idesc(kFmtF16, kFmtF16, 128, CF::NQH), id_c = umma_idesc(kFmtF16, kFmtF16, 128, 32);
             constexpr uint32_t id_s = umma_idesc(kFmtF16, kFmtF16, 128, 64);
             constexpr uint32_t id_o = umma_idesc(kFmtF16, kFmtF16, 128, CF::ON) | kUmmaBMajorMN;
             constexpr uint32_t id_p = umma_idesc(kFmtF16, kFmtF16, 128, 96), id_r = umma_idesc(kFmtF16, kFmtF16, 128, 16);
+            const uint64_t d_x = umma_desc_k_sw128(sb + CF::oXh), d_wq = umma_desc_k_sw128(sb + CF::oWq),
+                           d_wp = umma_desc_k_sw128(sb + CF::oWp), d_qk = umma_desc_k_sw128(sb + CF::oQK),
+                           d_vh = umma_desc_k_sw128(sb + CF::oVh), d_vl = umma_desc_k_sw128(sb + CF::oVl),
+                           d_i = umma_desc_k_sw128(sb + CF::oI16);
             uint32_t nq = 0, np = 0;                       // weight chunks consumed from the two rings
             int next_q = 0;                                // next head whose QKV MMAs are to be issued
             auto issue_qkv = [&](int q) {
@@ -352,18 +390,17 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kb = 0; kb < CF::KB; ++kb) {
-                    const uint32_t slot = nq & 1;
-                    mbar_wait(bars + CF::bWqFull + slot, (nq >> 1) & 1);
+                    const uint32_t slot = nq % CF::kWqSlots;
+                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);
                     tc_fence_after_sync();
-                    const uint64_t a0 = umma_desc_k_sw128(sb + CF::oXh + xb * 49152 + kb * 16384);
-                    const uint32_t wbase = sb + CF::oWq + slot * CF::kWqChunk;
-                    const uint64_t b0 = umma_desc_k_sw128(wbase), bv = umma_desc_k_sw128(wbase + CF::VOFF * 128),
-                                   bl = umma_desc_k_sw128(wbase + CF::kWqHi);
+                    const uint64_t a0 = d_x + ((xb * 49152 + kb * 16384) >> 4);
+                    const uint64_t b0 = d_wq + ((slot * CF::kWqChunk) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, (kb | ks) != 0);
-                        umma_f16_ts(tm + CF::tDq + CF::VOFF, tm + CF::tXl + (kb * 4 + ks) * 8, bv + ks * 2, id_c, 1);
-                        umma_f16_ss(tm + CF::tDq + CF::VOFF, a0 + ks * 2, bl + ks * 2, id_c, 1);
+                        umma_f16_ts(tm + CF::tDq + CF::kVhiRow, tm + CF::tXl + (kb * 4 + ks) * 8, b0 + CF::kVhiRow * 8 + ks * 2, id_c, 1);
+                        if constexpr (!CF::kMergedLo)
+                            umma_f16_ss(tm + CF::tDq + CF::kVhiRow, a0 + ks * 2, b0 + CF::kVloRow * 8 + ks * 2, id_c, 1);
                     }
                     umma_commit(bars + CF::bWqEmpty + slot);
                     ++nq;
@@ -378,12 +415,11 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 mbar_wait(bars + CF::bVReady, G & 1);
                 mbar_wait(bars + CF::bPReady, G & 1);
                 tc_fence_after_sync();
-                const uint64_t vh = umma_desc_k_sw128(sb + CF::oVh), vl = umma_desc_k_sw128(sb + CF::oVl);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {           // 16 keys per step = 2048 bytes of the [key][128 B] buffers
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, vh + ks * 128, id_o, ks != 0);
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + 32 + ks * 8, vh + ks * 128, id_o, 1);
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, vl + ks * 128, id_o, 1);
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, d_vh + ks * 128, id_o, ks != 0);
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + 32 + ks * 8, d_vh + ks * 128, id_o, 1);
+                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, d_vl + ks * 128, id_o, 1);
                 }
                 umma_commit(bars + CF::bOFull);
                 umma_commit(bars + CF::bVFree);
@@ -395,12 +431,10 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     // the accumulator starts as the residual x itself: D[:, 16j .. 16j+15] = X_hi(j) I + X_lo(j) I
                     if (it > 0) mbar_wait(bars + CF::bPjEmpty, (it - 1) & 1);
                     tc_fence_after_sync();
-                    const uint64_t bi = umma_desc_k_sw128(sb + CF::oI16);
 #pragma unroll
                     for (int ks = 0; ks < CF::KSTEPS; ++ks) {
-                        const uint64_t a = umma_desc_k_sw128(sb + CF::oXh + xb * 49152 + (ks >> 2) * 16384) + (ks & 3) * 2;
-                        umma_f16_ss(tm + CF::tPj + ks * 16, a, bi, id_r, 0);
-                        umma_f16_ts(tm + CF::tPj + ks * 16, tm + CF::tXl + ks * 8, bi, id_r, 1);
+                        umma_f16_ss(tm + CF::tPj + ks * 16, d_x + ((xb * 49152 + (ks >> 2) * 16384) >> 4) + (ks & 3) * 2, d_i, id_r, 0);
+                        umma_f16_ts(tm + CF::tPj + ks * 16, tm + CF::tXl + ks * 8, d_i, id_r, 1);
                     }
                 }
                 tc_fence_after_sync();
@@ -409,7 +443,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     const uint32_t slot = np & 1;
                     mbar_wait(bars + CF::bWpFull + slot, (np >> 1) & 1);
                     tc_fence_after_sync();
-                    const uint64_t b0 = umma_desc_k_sw128(sb + CF::oWp + slot * CF::kWpChunk);
+                    const uint64_t b0 = d_wp + ((slot * CF::kWpChunk) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + ks * 2, id_p, 1);
@@ -419,37 +453,33 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     umma_commit(bars + CF::bWpEmpty + slot);
                     ++np;
                 }
-                umma_commit(bars + CF::bOAFree);
                 if (h == H - 1) umma_commit(bars + CF::bPjFull);
             };
             for (int G = 0; G < total; ++G) {
                 if (next_q <= G) issue_qkv(next_q++);
-                // ---- S(G) = [Q_w0; 0] K_w0^T + [0; Q_w1] K_w1^T
+                tick(0);                                                         // 0: (first) QKV issue
+                // ---- S(G): rows 0-63 (window slot 0) against the keys of slot 0, rows 64-127 against those of slot 1: two
+                //      MMAs per k step with the other half of the output lanes disabled -- no junk columns, 64 TMEM columns
                 mbar_wait(bars + CF::bQkReady, G & 1);
                 tc_fence_after_sync();
-                {
-                    const uint32_t w0 = sb + CF::oQK, z = w0 + 8192, w1 = w0 + 16384;
-                    const uint64_t a0 = umma_desc_k_sw128(w0), az = umma_desc_k_sw128(z);
-                    const uint64_t k0 = umma_desc_k_sw128(w0 + 64), k1 = umma_desc_k_sw128(w1 + 64);
+                tick(1);                                                         // 1: wait Q | K of the head
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        umma_f16_ss(tm + CF::tS, a0 + ks * 2, k0 + ks * 2, id_s, ks != 0);
-                        umma_f16_ss(tm + CF::tS, az + ks * 2, k1 + ks * 2, id_s, 1);
-                    }
-                    umma_commit(bars + CF::bSFull);
-                    umma_commit(bars + CF::bQkFree);
+                for (int ks = 0; ks < 2; ++ks) {
+                    umma_f16_ss_lanes(tm + CF::tS, d_qk + ks * 2, d_qk + 4 + ks * 2, id_s, ks != 0, 0u, 0u, ~0u, ~0u);
+                    umma_f16_ss_lanes(tm + CF::tS, d_qk + ks * 2, d_qk + 512 + 4 + ks * 2, id_s, ks != 0, ~0u, ~0u, 0u, 0u);
                 }
+                umma_commit(bars + CF::bSFull);
+                umma_commit(bars + CF::bQkFree);
+                tick(2);                                                         // 2: S issue
                 if (next_q < total) issue_qkv(next_q++);     // QKV(G + 1) fills the tensor pipe during softmax(G)
-                if constexpr (CF::kSepOA) {
-                    issue_pv(G);
-                    if (G > 0) issue_proj(G - 1);
-                } else {
-                    if (G > 0) issue_proj(G - 1);            // reads the projection operand before P V overwrites it
-                    issue_pv(G);
-                }
+                tick(3);                                                         // 3: QKV(G + 1) issue incl. its waits
+                if (G > 0) issue_proj(G - 1);                // reads the projection operand before P V(G) overwrites it
+                tick(5);                                                         // 5: wait O operand (+ accumulator) + proj issue
+                issue_pv(G);
+                tick(4);                                                         // 4: wait P, V + P V issue
             }
             if (total > 0) issue_proj(total - 1);
-        } else if (warp == kSpFeed && lane == 0) {
+        } else if (warp == kSpFeed && elect_one()) {
             // weight feeder: two rings of bulk copies, each in exactly the order the issuer consumes it
             const uint8_t* gq = sp + SpParams<CF>::wq;
             const uint8_t* gp = sp + SpParams<CF>::wp;
@@ -457,11 +487,11 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             uint32_t iq = 0, ip = 0;
             while (iq < nQ || ip < nP) {
                 if (iq < nQ) {
-                    const uint32_t slot = iq & 1;
-                    if (iq < 2 || mbar_test_wait(bars + CF::bWqEmpty + slot, ((iq >> 1) - 1) & 1)) {
+                    const uint32_t slot = iq % CF::kWqSlots;
+                    if (iq < uint32_t(CF::kWqSlots) || mbar_test_wait(bars + CF::bWqEmpty + slot, ((iq / CF::kWqSlots) - 1) & 1)) {
                         const uint32_t h = (iq / CF::KB) % H, kb = iq % CF::KB;
                         mbar_arrive_expect_tx(bars + CF::bWqFull + slot, CF::kWqChunk);
-                        bulk_g2s(smem + CF::oWq + slot * CF::kWqChunk, gq + int64_t(h * CF::KB + kb) * CF::kWqStride,
+                        bulk_g2s(smem + CF::oWq + slot * CF::kWqChunk, gq + int64_t(h * CF::KB + kb) * CF::kWqChunk,
                                  CF::kWqChunk, bars + CF::bWqFull + slot);
                         ++iq;
                     }
@@ -605,8 +635,10 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             if (do_epi) {
                 wp = win_of(tile_of(it - 1));
                 orow = out + wp.base + int64_t(half * 96) * hw;
+                tick(8);                                                         // 8: tile set-up + wait X_hi buffer free
                 mbar_wait(bars + CF::bPjFull, (it - 1) & 1);
                 tc_fence_after_sync();
+                tick(9);                                                         // 9: wait projection complete
                 estep = 0;
             }
             auto epi_step = [&]() {
@@ -616,6 +648,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 if (estep == 11) {                           // last TMEM read of the tile: hand the accumulator back
                     tc_fence_before_sync();
                     mbar_arrive(bars + CF::bPjEmpty);
+                    tick(13);                                                    // 13: (marker) accumulator released
                 }
                 if (wp.valid && !MWA_SP_EPI_NOSTORE) {
                     float* o = orow + int64_t(estep * 8) * hw;
@@ -635,25 +668,36 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 }
             }
             while (estep < 12) epi_step();
+            tick(10);                                                            // 10: epilogue + conversion interleaved
             if (do_gather) {
                 if (wn.staged) stage_n += 12;
                 fence_proxy_async_smem();
                 mbar_arrive(bars + CF::bXhFull + xb);
                 mbar_wait(bars + CF::bXlEmpty, it & 1);      // the correction MMAs of tile `it` have read X_lo
                 tc_fence_after_sync();
+                tick(11);                                                        // 11: wait X_lo free
                 publish_lo(it + 1);
+                tick(12);                                                        // 12: X_lo -> TMEM
             }
         }
     } else if (warp < kSpDr0) {
         // =========================================================================================== softmax + normalisation
+        // Two warps per 32-row lane quarter (both on the same SM sub-partition, as the TMEM lane rule demands): each takes
+        // 32 of the row's 64 logits and half of its d output columns; row max and row sum go through shared memory and a
+        // 64-thread named barrier.  One warp per quarter was latency-bound at ~2 k cycles per head (profiles/).
         sp_reg_inc<kSpRegsSm>();
-        const int sw = warp - kSpSm0, r = sw * 32 + lane, wslot = r >> 6, tok = r & 63;
+        const int sw = warp - kSpSm0, q = sw & 3, ch = sw >> 2;
+        const int r = q * 32 + lane, wslot = r >> 6, tok = r & 63;
         const int yi = tok >> 3, xi = tok & 7;
-        const uint32_t lane_addr = static_cast<uint32_t>(sw * 32) << 16;
-        const uint32_t tbl0 = sb + CF::oTbl + 4 * ((yi + WS - 1) * (2 * WS - 1) + xi + WS - 1);
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        // this lane's entry of the relative-position table for key 32 * ch (keys run down the table: - (yj * 15 + xj))
+        const uint32_t tbl0 = sb + CF::oTbl + 4 * ((yi + WS - 1 - 4 * ch) * (2 * WS - 1) + xi + WS - 1);
+        const uint32_t xmax_me = sb + CF::oXch + 4 * (ch * 128 + r), xmax_other = sb + CF::oXch + 4 * ((ch ^ 1) * 128 + r);
+        const uint32_t xsum_me = xmax_me + 1024, xsum_other = xmax_other + 1024;
+        constexpr int DH = D / 2, NP = D / 4;                // output columns / packed fp16 columns of this thread
         for (int it = 0; it < my_tiles; ++it) {
-            // SW-MSA region mask bits of this row (:194-216); zero unless the window touches the wrapped border
-            uint32_t mb0 = 0, mb1 = 0;
+            // SW-MSA region mask bits of this row's 32 keys (:194-216); zero unless the window touches the wrapped border
+            uint32_t mb = 0;
             bool has_mask = false;
             if (geo.shift > 0) {
                 const int lidx = tile_of(it) * 2 + wslot;
@@ -670,82 +714,94 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                         dy |= uint32_t(((ys0 + j >= geo.H - WS) + (ys0 + j >= geo.H - geo.shift)) != by) << j;
                         dx |= uint32_t(((xs0 + j >= geo.W - WS) + (xs0 + j >= geo.W - geo.shift)) != bx) << j;
                     }
+                    dy >>= 4 * ch;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        mb0 |= (((dy >> (j >> 3)) | (dx >> (j & 7))) & 1u) << j;
-                        mb1 |= (((dy >> (4 + (j >> 3))) | (dx >> (j & 7))) & 1u) << j;
-                    }
+                    for (int j = 0; j < 32; ++j) mb |= (((dy >> (j >> 3)) | (dx >> (j & 7))) & 1u) << j;
                 }
             }
             for (int h = 0; h < H; ++h) {
                 const int G = it * H + h;
                 mbar_wait(bars + CF::bSFull, G & 1);
                 tc_fence_after_sync();
-                float s[64];
+                tick(16);                                                        // 16: wait S
+                float s[32];
                 {
                     uint32_t raw[32];
-                    tmem_ld_x32(tm + CF::tS + lane_addr, raw);
+                    tmem_ld_x32(tm + CF::tS + lane_addr + ch * 32, raw);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(raw[j]);
-                    tmem_ld_x32(tm + CF::tS + lane_addr + 32, raw);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(raw[j]);
                 }
                 // relative-position bias (layers/masked_win_attention.py:109-112), table pre-multiplied by log2(e)
                 const uint32_t tb = tbl0 + h * (CF::TBL * 4);
 #pragma unroll
-                for (int j = 0; j < 64; ++j) s[j] += sp_ld_shared_f32(tb - 4 * ((j >> 3) * (2 * WS - 1) + (j & 7)));
+                for (int j = 0; j < 32; ++j) s[j] += sp_ld_shared_f32(tb - 4 * ((j >> 3) * (2 * WS - 1) + (j & 7)));
                 if (has_mask) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if ((mb0 >> j) & 1u) s[j] += kNegMaskL2;
-                        if ((mb1 >> j) & 1u) s[32 + j] += kNegMaskL2;
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if ((mb >> j) & 1u) s[j] += kNegMaskL2;
                 }
                 float m = s[0];
 #pragma unroll
-                for (int j = 1; j < 63; j += 2) m = max3(m, s[j], s[j + 1]);
-                m = fmaxf(m, s[63]);
+                for (int j = 1; j < 31; j += 2) m = max3(m, s[j], s[j + 1]);
+                m = fmaxf(m, s[31]);
+                sp_st_shared_f32(xmax_me, m);
+                sp_named_sync(1 + q, 64);
+                m = fmaxf(m, sp_ld_shared_f32(xmax_other));
                 float sum = 0.f;
-                uint32_t ph[32], pl[32];
+                uint32_t ph[16], pl[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const float p0 = ex2(s[2 * j] - m), p1 = ex2(s[2 * j + 1] - m);
                     sum += p0 + p1;
                     split_f16x2(p0, p1, ph[j], pl[j]);
                 }
-                tmem_st_x32(tm + CF::tS + lane_addr, ph);
-                tmem_st_x32(tm + CF::tS + lane_addr + 32, pl);
+                sp_st_shared_f32(xsum_me, sum);
+                tmem_st_x16(tm + CF::tS + lane_addr + ch * 16, ph);
+                tmem_st_x16(tm + CF::tS + lane_addr + 32 + ch * 16, pl);
                 tmem_wait_st();
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bPReady);
-                const float inv = 1.0f / sum;
-                // ---- O / rowsum -> fp16 hi / lo, the projection's A operand
+                tick(17);                                                        // 17: softmax
+                // ---- O / rowsum -> fp16 hi / lo, the projection's A operand (written over O in place: both threads of a
+                //      row must have read their columns before either writes)
                 mbar_wait(bars + CF::bOFull, G & 1);
                 tc_fence_after_sync();
-                uint32_t oraw[D];
+                tick(18);                                                        // 18: wait O
+                uint32_t oraw[DH];
 #pragma unroll
-                for (int c = 0; c < D / 8; ++c) {
-                    uint32_t t8[8];
-                    tmem_ld_x8(tm + CF::tO + lane_addr + wslot * D + c * 8, t8);
+                for (int c = 0; c < DH / 4; ++c) {
+                    uint32_t t4[4];
+                    tmem_ld_x4(tm + CF::tO + lane_addr + wslot * D + ch * DH + c * 4, t4);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) oraw[c * 8 + j] = t8[j];
+                    for (int j = 0; j < 4; ++j) oraw[c * 4 + j] = t4[j];
                 }
                 tmem_wait_ld();
-                if (CF::kSepOA && G > 0) mbar_wait(bars + CF::bOAFree, (G - 1) & 1);
-                uint32_t oh[16], ol[16];
+                sp_named_sync(1 + q, 64);
+                const float inv = 1.0f / (sum + sp_ld_shared_f32(xsum_other));
+                uint32_t oh[NP], ol[NP];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (2 * j < D) split_f16x2(__uint_as_float(oraw[2 * j]) * inv, __uint_as_float(oraw[2 * j + 1]) * inv, oh[j], ol[j]);
-                    else oh[j] = ol[j] = 0u;
+                for (int j = 0; j < NP; ++j)
+                    split_f16x2(__uint_as_float(oraw[2 * j]) * inv, __uint_as_float(oraw[2 * j + 1]) * inv, oh[j], ol[j]);
+                const uint32_t ta = tm + CF::tOA + lane_addr + ch * NP;
+                if constexpr (NP == 8) {
+                    tmem_st_x8(ta, oh);
+                    tmem_st_x8(ta + 16, ol);
+                } else {
+                    static_assert(NP == 6 || NP == 8, "head dim 24 / 32");
+                    tmem_st_x4(ta, oh[0], oh[1], oh[2], oh[3]);
+                    tmem_st_x2(ta + 4, oh[4], oh[5]);
+                    tmem_st_x4(ta + 16, ol[0], ol[1], ol[2], ol[3]);
+                    tmem_st_x2(ta + 20, ol[4], ol[5]);
+                    if (ch == 1) {                               // k = 24 .. 31 of the projection operand: zeros
+                        tmem_st_x4(tm + CF::tOA + lane_addr + 12, 0u, 0u, 0u, 0u);
+                        tmem_st_x4(tm + CF::tOA + lane_addr + 28, 0u, 0u, 0u, 0u);
+                    }
                 }
-                tmem_st_x16(tm + CF::tOA + lane_addr, oh);
-                tmem_st_x16(tm + CF::tOA + lane_addr + 16, ol);
                 tmem_wait_st();
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bOAReady);
+                tick(19);                                                        // 19: normalisation
             }
         }
     } else {
@@ -754,12 +810,13 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         const int dw = warp - kSpDr0, r = dw * 32 + lane, wslot = r >> 6, tok = r & 63;
         const uint32_t lane_addr = static_cast<uint32_t>(dw * 32) << 16;
         const uint32_t rowoff = (tok >> 3) * 1024 + (tok & 7) * 128, sx = tok & 7;
-        const uint32_t qk_row = sb + CF::oQK + wslot * 16384 + rowoff;
+        const uint32_t qk_row = sb + CF::oQK + wslot * 8192 + rowoff;
         const float* s_bq = reinterpret_cast<const float*>(smem + CF::oBq);
         for (int G = 0; G < total; ++G) {
             const int h = G % H;
             mbar_wait(bars + CF::bDqFull, G & 1);
             tc_fence_after_sync();
+            tick(24);                                                            // 24: wait D_qkv
             uint32_t raw[2 * D];                               // q | k columns
 #pragma unroll
             for (int c = 0; c < 2 * D / 8; ++c) {
@@ -770,6 +827,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
             tmem_wait_ld();
             if (G > 0) mbar_wait(bars + CF::bQkFree, (G - 1) & 1);
+            tick(25);                                                            // 25: load q | k + wait Q | K rows free
 #pragma unroll
             for (int ch = 0; ch < D / 8; ++ch) {               // q (+ bias) -> chunks 0.., k -> chunks 4..
                 uint32_t pq[4], pk[4];
@@ -784,18 +842,33 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
             fence_proxy_async_smem();
             mbar_arrive(bars + CF::bQkReady);
-            uint32_t rv[D];                                    // v columns
+            tick(26);                                                            // 26: q | k -> shared memory
+            uint32_t rv[D];                                    // v columns (d = 24: x_hi Wv_hi + x_lo Wv_hi, plus x_hi Wv_lo below)
 #pragma unroll
             for (int c = 0; c < D / 8; ++c) {
                 uint32_t t8[8];
-                tmem_ld_x8(tm + CF::tDq + lane_addr + 2 * D + c * 8, t8);
+                tmem_ld_x8(tm + CF::tDq + lane_addr + CF::kVhiRow + c * 8, t8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rv[c * 8 + j] = t8[j];
+            }
+            if constexpr (CF::kMergedLo) {
+                uint32_t rl[D];
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tDq + lane_addr + CF::kVloRow + c * 8, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rl[c * 8 + j] = t8[j];
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < D; ++c) rv[c] = __float_as_uint(__uint_as_float(rv[c]) + __uint_as_float(rl[c]));
             }
             tmem_wait_ld();
             tc_fence_before_sync();
             mbar_arrive(bars + CF::bDqEmpty);                  // the accumulator may be overwritten by QKV(G + 1)
             if (G > 0) mbar_wait(bars + CF::bVFree, (G - 1) & 1);
+            tick(27);                                                            // 27: load v + wait V rows free
 #pragma unroll
             for (int ch = 0; ch < D / 8; ++ch) {               // v -> hi / lo rows [key][slot 0 d | slot 1 d]
                 uint32_t vh[4], vl[4];
@@ -810,6 +883,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
             fence_proxy_async_smem();
             mbar_arrive(bars + CF::bVReady);
+            tick(28);                                                            // 28: v -> shared memory
         }
     }
 

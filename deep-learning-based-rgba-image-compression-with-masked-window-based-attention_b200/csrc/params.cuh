@@ -53,7 +53,7 @@ __host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
 __host__ __device__ inline int64_t mwa_sp_section_bytes(int C, int heads, int ws) {
     if (!(C == 192 && ws == 8 && (heads == 8 || heads == 6))) return 0;
     const int64_t tbl = (2 * ws - 1) * (2 * ws - 1);
-    return int64_t(heads) * 3 * 16384 + int64_t(heads) * 2 * 12288 + 2 * int64_t(C) * 4 + align_up(heads * tbl * 4, 1024) + 2048;
+    return int64_t(heads) * 3 * (4 * (C / heads) * 128) + int64_t(heads) * 2 * 12288 + 2 * int64_t(C) * 4 + align_up(heads * tbl * 4, 1024) + 2048;
 }
 
 struct MwaParamLayout {
