@@ -117,23 +117,31 @@ def require_cuda_f32(t: torch.Tensor, name: str) -> None:
         raise MwaB200Error(f"{name} must be float32 (got {t.dtype})")
 
 
+# Opt-in (default OFF: the reference's gradients are fp32 end to end).  MWA_B200_WGRAD_TF32=1 in the environment, or
+# `mwa_b200._abi.WGRAD_TF32 = True`, lets the LARGE-K parameter-gradient GEMMs use TF32 products (see tf32_reduction).
+WGRAD_TF32 = os.environ.get("MWA_B200_WGRAD_TF32", "0") == "1"
+
+
 class tf32_reduction:
     """Context for the LARGE-K parameter-gradient GEMMs of the backward (dW = dY^T X over all tokens, dgamma = dn (x^2)^T
-    over all pixels: K = 10^4 ... 10^6): lets the library GEMM use TF32 tensor-core products with fp32 accumulation.
-    A 2^-11 relative error per product averages out over that many terms (observed ~1e-5 relative on the sums), while the
-    fp32 SIMT SGEMM these shapes otherwise fall to was 27 % of the training step.  The per-pixel / per-token contractions
-    (K = C) stay in full fp32."""
+    over all pixels: K = 10^4 ... 10^6).  A no-op unless WGRAD_TF32 was switched on explicitly: then the library GEMM
+    may use TF32 tensor-core products with fp32 accumulation (a 2^-11 relative error per product averages out over that
+    many terms, observed ~1e-5 relative on the sums; the fp32 SIMT SGEMM these shapes otherwise fall to is 27 % of the
+    training step).  The switch it flips, `torch.backends.cuda.matmul.allow_tf32`, is process-global: with it on, a
+    matmul running concurrently on another thread can pick up TF32 too -- which is why this is opt-in.  The per-pixel /
+    per-token contractions (K = C) always stay in full fp32."""
 
     MIN_K = 8192        # below this the averaging argument is weak and the fp32 GEMM is cheap anyway
 
     def __init__(self, k: int):
-        self.on = k >= self.MIN_K
+        self.on = WGRAD_TF32 and k >= self.MIN_K
 
     def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
         if self.on:
+            self.prev = torch.backends.cuda.matmul.allow_tf32
             torch.backends.cuda.matmul.allow_tf32 = True
 
     def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = self.prev
         return False

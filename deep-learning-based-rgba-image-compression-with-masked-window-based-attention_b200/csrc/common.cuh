@@ -248,6 +248,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A from TMEM with an output lane mask (see umma_f16_ss_lanes); verified by tools/umma_ts_probe.cu (mode `half`)
+__device__ __forceinline__ void umma_f16_ts_lanes(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
 // instruction-descriptor flag: the B operand is MN-major (stored [k][n], n contiguous; with SWIZZLE_128B the same
 // physical layout as a K-major [rows = k][64] buffer).  Verified by tools/umma_ts_probe.cu.
 constexpr uint32_t kUmmaBMajorMN = 1u << 16;

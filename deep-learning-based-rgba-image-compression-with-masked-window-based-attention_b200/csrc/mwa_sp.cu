@@ -1,30 +1,36 @@
 // Fused masked window attention forward in SPLIT PRECISION (fp32-faithful results on the tensor cores), sm_100a only.
 // Reference semantics: layers/masked_win_attention.py:169-251 (block) and :96-131 (window attention), whose arithmetic
 // is fp32 end to end.  A single fp16 pass per contraction (csrc/mwa_ws.cu) misses the 1e-3 rel / 1e-4 abs contract on
-// ~0.1 % of the outputs; tools/precision_study.py shows which operand roundings cost what.  Here every operand on the
-// value path (x, Wv, V, P, O, Wproj) is carried as fp16 hi + lo and contracted in three passes
-// (hi*hi + lo*hi + hi*lo, fp32 accumulation), the logit path (q, k) stays single fp16: rms error 8e-6, worst
-// err / tolerance 0.4 at the north-star protocol (N(0,1) inputs, random init) against 1.1-1.2 for plain fp16.
+// ~0.1 % of the outputs at random init and by far more on weights with large logits; tools/precision_study.py shows
+// which operand roundings cost what.  Here EVERY operand of EVERY contraction (x, Wqkv, q, k, v, P, O, Wproj) is carried
+// as fp16 hi + lo and contracted in three passes (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM): ~2^-21 relative
+// per product instead of 2^-11.
 //
-// EVERY contraction runs on tcgen05 with accumulators in TMEM, and one thread owns one token (= TMEM lane) from the
-// QKV drain to the projection epilogue, so nothing but Q / K / V goes through shared memory:
+// One thread owns one token (= TMEM lane) from the QKV drain to the projection epilogue; only K and V go through
+// shared memory (they are B operands), everything else stays in TMEM:
 //
 //   tile = 128 tokens = 2 kept 8x8 windows (rows 0-63 window slot 0, 64-127 slot 1), one head at a time:
-//   QKV(h)   D_qkv[128 x 3d]  = X_hi Wh_hi^T  (+ X_lo Wv_hi^T + X_hi Wv_lo^T on the v columns); X_lo is a TMEM operand
-//   drain    thread = token: q (+bias, pre-scaled by scale*log2e), k -> fp16 [Q | K] rows; v -> fp16 hi / lo [key][w0 d | w1 d]
-//   S(h)     [128 x 64] = [Q_w0; 0] K_w0^T + [0; Q_w1] K_w1^T   (zero-block trick: no junk columns, 64 TMEM columns)
-//   softmax  thread = row: + relative-position bias (+ SW-MSA region mask), exp2, row sum; P -> fp16 hi / lo written
-//            back over S in TMEM (A operand of P V)
-//   PV(h)    O[128 x 2d] = P V  (V is the MN-major B operand; a row's own window is one d-wide half), 3 passes
-//   norm     thread = row: O / rowsum -> fp16 hi / lo in TMEM (A operand of the projection)
-//   proj(h)  D_out[128 x 192] += O_h Wproj_h^T, 3 passes, accumulated over the heads in TMEM
+//   QKV(h)   D_qkv[128 x 3d] = X_hi Wh_hi^T + X_lo Wh_hi^T + X_hi Wh_lo^T        (X_hi in shared memory, X_lo in TMEM)
+//   drain    thread = token: q (+bias, pre-scaled by scale*log2e) -> fp16 hi / lo in TMEM (A operand of S);
+//            k, v -> fp16 hi / lo rows in shared memory
+//   S(h)     [128 x 64]: rows of window slot w against the 64 keys of slot w: two lane-masked MMAs per k step and pass
+//   softmax  thread = (row, half of the keys): + relative-position bias (+ SW-MSA region mask), exp2, row sum;
+//            P -> fp16 hi / lo written back over S in TMEM (A operand of P V)
+//   PV(h)    O[128 x d] = P V_w  (V is the MN-major B operand [key][slot 0 d | slot 1 d]; again two lane-masked MMAs,
+//            the second with its operand start advanced by d columns inside the swizzle atom)
+//   norm     thread = row: O / rowsum -> fp16 hi / lo in TMEM over O (A operand of the projection)
+//   proj(h)  D_out[128 x 192] += O_h Wproj_h^T, accumulated over the heads in TMEM
 //   residual D_out is INITIALISED with x itself (X_hi I + X_lo I, 16-column identity MMAs, exact to 2^-22), so the
 //            epilogue is a plain store of D_out + bias: no second read of x, no reduction, no pre-copy of the tensor.
 //
-// Roles (20 warps, setmaxnreg): 0 MMA issuer | 1 weight feeder (two rings of bulk copies) | 2-3 TMA gather issuers
+// The issuer runs the heads as a software pipeline: slot G issues  P V(G) | S(G+1) | QKV(G+2) | proj(G)  so that the
+// QKV and projection MMAs fill the tensor pipe while the softmax warps work on S(G+1); the tensor pipe executes in
+// issue order, which is what makes the in-place reuse (P over S, the projection operand over O) safe without waits.
+//
+// Roles (24 warps, setmaxnreg): 0 MMA issuer | 1 weight feeder (two rings of bulk copies) | 2-3 TMA gather issuers
 // (one per window slot, [16 ch][8][8] boxes of x) | 4-11 x converter + epilogue (fp32 boxes -> X_hi in shared memory,
 // X_lo kept in registers until the previous tile's last QKV MMA has retired, then stored to TMEM; epilogue interleaved
-// with the conversion of the next tile) | 12-15 softmax + normalisation | 16-19 QKV drain.
+// with the conversion of the next tile) | 12-19 softmax (two warps per lane quarter) | 20-23 QKV drain + normalisation.
 // Dropped windows are copied through by a separate small kernel (only the dropped ones).
 #include <cstring>
 #include <cuda.h>          // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
@@ -51,8 +57,8 @@ constexpr int kSpWarps = 24;
 constexpr int kSpThreads = kSpWarps * 32;
 constexpr int kSpMma = 0, kSpFeed = 1, kSpTma0 = 2;
 constexpr int kSpPe0 = 4, kSpNumPe = 8, kSpSm0 = 12, kSpNumSm = 8, kSpDr0 = 20;
-// register pool of the CTA = 24 warps x 80 (launch bound); per SM sub-partition 40 + 2 x 96 + 2 x 88 + 72 = 480 = 6 x 80
-constexpr int kSpRegsCtl = 40, kSpRegsPe = 96, kSpRegsSm = 88, kSpRegsDr = 72;
+// register pool of the CTA = 24 warps x 80 (launch bound); per SM sub-partition 40 + 2 x 96 + 2 x 80 + 88 = 480 = 6 x 80
+constexpr int kSpRegsCtl = 40, kSpRegsPe = 96, kSpRegsSm = 80, kSpRegsDr = 88;
 constexpr float kNegMaskL2 = kNegMask * kLog2e;
 
 template <int HEADS_>
@@ -60,56 +66,48 @@ struct SpCfg {
     static constexpr int C = 192, WS = 8, NTOK = 64, HEADS = HEADS_, D = C / HEADS;
     static_assert(D == 24 || D == 32, "head dim 24 / 32");
     static constexpr int KB = 3, KSTEPS = 12;
-    // QKV weight chunk of a (head, 64-channel K block), one bulk copy, rows of 128 B (K-major SW128), no padding rows:
-    //   d = 24:  [q 24][k 24][v lo 24][v hi 24] = 96 rows.  ONE MMA with N = 96 over x_hi yields q, k, x_hi Wv_lo^T and
-    //            x_hi Wv_hi^T in 96 accumulator columns; the x_lo Wv_hi^T pass (A from TMEM, N = 32 from row 72: the 8
-    //            rows past the chunk are whatever follows in shared memory and only feed columns 96-103, never read)
-    //            accumulates onto columns 72-103; the drain adds the two v parts.
-    //   d = 32:  [q 32][k 32][v hi 32][v lo 32] = 128 rows.  N = 96 over x_hi, then two N = 32 passes onto columns 64-95
-    //            (x_lo Wv_hi^T from TMEM, x_hi Wv_lo^T): 128 accumulator columns do not fit the TMEM budget.
-    static constexpr bool kMergedLo = (D == 24);
-    static constexpr int NQH = 96;                           // N of the main QKV MMA
-    static constexpr int DQW = kMergedLo ? 104 : 96;         // accumulator columns of D_qkv
-    static constexpr int kVhiRow = kMergedLo ? 72 : 64;      // first v hi row of the chunk = first column of the TMEM pass
-    static constexpr int kVloRow = kMergedLo ? 48 : 96;      // first v lo row
-    static constexpr int TBL = 225;
-    static constexpr int ON = 2 * D;                         // P V output columns: [window slot 0 d | slot 1 d]
-    static constexpr uint32_t kWqChunk = 4 * D * 128;
+    // QKV weight ring element = (head, 64-channel K block, part): rows [q d][k d][v d] of the fp16 hi (part 0) or lo
+    // (part 1) image, 128 B per row (K-major SW128), one bulk copy.  N of the QKV MMAs is 3d rounded up to a multiple
+    // of 16: for d = 24 the 8 rows past the element are whatever follows in shared memory and only feed accumulator
+    // columns 72-79, which nobody reads.
+    static constexpr int NQ = (3 * D + 15) / 16 * 16;
+    static constexpr uint32_t kWqElem = 3 * D * 128;
+    static constexpr int kWqSlots = (D == 24) ? 4 : 3;
     static constexpr uint32_t kWpChunk = 96 * 128;
-    static constexpr int kWqSlots = (HEADS == 8) ? 3 : 2;    // a whole head's QKV weights in flight where they fit
-    // TMEM columns (the projection's A operand overwrites O in place)
-    static constexpr uint32_t tDq = 0, tPj = DQW, tS = tPj + C, tO = tS + 64, tOA = tO, tXl = 416;
-    static_assert(tO + ON <= tXl, "TMEM budget");
+    static constexpr int TBL = 225;
+    // TMEM columns: D_qkv | D_out | S (P hi / lo in place) | O (projection operand in place) | Q hi, lo | X_lo
+    static constexpr uint32_t tDq = 0, tPj = 96, tS = 288, tO = 352, tOA = tO, tQ = 384, tXl = 416;
+    static_assert(NQ <= 96, "TMEM budget");
     // shared memory map
     static constexpr uint32_t oXh = 0;                       // 2 x (KB x [128 x 64] fp16)
-    static constexpr uint32_t oQK = 2 * 49152;               // [128 rows] x 128 B: q (64 B) | k (64 B) of the head
-    static constexpr uint32_t oVh = oQK + 16384, oVl = oVh + 8192;
-    static constexpr uint32_t oWq = oVl + 8192;              // kWqSlots slots
-    static constexpr uint32_t oWp = oWq + kWqSlots * kWqChunk;   // 2 slots
+    static constexpr uint32_t oK = 2 * 49152;                // [128 keys] x 128 B: k hi (64 B) | k lo (64 B) of the head
+    static constexpr uint32_t oVh = oK + 16384, oVl = oVh + 8192;   // [64 keys] x 128 B: [slot 0 d | slot 1 d]
+    static constexpr uint32_t oWq = oVl + 8192;              // kWqSlots elements
+    static constexpr uint32_t oWp = oWq + kWqSlots * kWqElem;    // 2 slots
     static constexpr uint32_t oStage = oWp + 2 * kWpChunk;   // 3 slots x 2 windows x 4 KB
     static constexpr uint32_t oI16 = oStage + 24576;
     static constexpr uint32_t oTbl = oI16 + 2048;
     static constexpr uint32_t oBq = (oTbl + HEADS * TBL * 4 + 15) / 16 * 16;
     static constexpr uint32_t oBpf = oBq + C * 4;
-    static constexpr uint32_t oXch = oBpf + C * 4;            // fp32 [max | sum][column half][128 rows]: softmax warp pairs
-    static constexpr uint32_t oBars = oXch + 2048;
+    static constexpr uint32_t oXch = oBpf + C * 4;            // fp32 row max [column half][128] | row sums [head parity][column half][128]
+    static constexpr uint32_t oBars = oXch + 3072;
     static constexpr uint32_t oTmem = oBars + 64 * 8;
     static constexpr uint32_t oTotal = oTmem + 16;
     static_assert(oTotal <= 227 * 1024, "shared memory budget");
-    static_assert(kWqChunk % 1024 == 0 && oWq % 1024 == 0 && oWp % 1024 == 0 && oI16 % 1024 == 0, "operand alignment");
+    static_assert(kWqElem % 1024 == 0 && oWq % 1024 == 0 && oWp % 1024 == 0 && oI16 % 1024 == 0, "operand alignment");
     // barriers
-    static constexpr int bXhFull = 0, bXhEmpty = 2, bXlFull = 4, bXlEmpty = 5, bWqFull = 6, bWqEmpty = 9, bWpFull = 12,
-                         bWpEmpty = 14, bDqFull = 16, bDqEmpty = 17, bQkReady = 18, bVReady = 19, bQkFree = 20, bVFree = 21,
-                         bSFull = 22, bPReady = 23, bOFull = 24, bOAReady = 25, bPjFull = 26, bPjEmpty = 27,
-                         bStFull = 28, bStEmpty = 34, bEnd = 40;
+    static constexpr int bXhFull = 0, bXhEmpty = 2, bXlFull = 4, bXlEmpty = 5, bWqFull = 6, bWqEmpty = 10, bWpFull = 14,
+                         bWpEmpty = 16, bDqFull = 18, bDqEmpty = 19, bQkReady = 20, bVReady = 21, bQkFree = 22, bVFree = 23,
+                         bSFull = 24, bPReady = 25, bOFull = 26, bOAReady = 27, bPjFull = 28, bPjEmpty = 29,
+                         bStFull = 30, bStEmpty = 36, bEnd = 42;
     static_assert(bEnd <= 64, "barrier slots");
 };
 
 // layout of the split-precision section of the parameter block (offsets from MwaParamLayout::img_sp)
 template <class CF>
 struct SpParams {
-    static constexpr int64_t wq = 0;                                                   // [HEADS][KB] x kWqChunk
-    static constexpr int64_t wp = wq + int64_t(CF::HEADS) * CF::KB * CF::kWqChunk;     // [HEADS][2] x kWpChunk
+    static constexpr int64_t wq = 0;                                                   // [HEADS][KB][hi, lo] x kWqElem
+    static constexpr int64_t wp = wq + int64_t(CF::HEADS) * CF::KB * 2 * CF::kWqElem;  // [HEADS][2] x kWpChunk
     static constexpr int64_t bq = wp + int64_t(CF::HEADS) * 2 * CF::kWpChunk;          // fp32 [C]  q bias * scale * log2e
     static constexpr int64_t bpf = bq + CF::C * 4;                                     // fp32 [C]  proj.bias + Wproj b_v
     static constexpr int64_t tbl = bpf + CF::C * 4;                                    // fp32 [HEADS][TBL] * log2e
@@ -132,14 +130,10 @@ __global__ void mwa_sp_prepare_kernel(const float* __restrict__ qkv_w, const flo
         const int part = n / D, c = n % D;
         float w = qkv_w[int64_t(part * C + h * D + c) * C + kb * 64 + kk];
         if (part == 0) w *= qs;
-        uint8_t* chunk = out + SpParams<CF>::wq + int64_t(h * CF::KB + kb) * CF::kWqChunk;
+        uint8_t* elem = out + SpParams<CF>::wq + int64_t((h * CF::KB + kb) * 2) * CF::kWqElem;
         const float hi = f16_round(w);
-        if (part < 2) {
-            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(n, kk)) = f16_bits(w);
-        } else {
-            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(CF::kVhiRow + c, kk)) = f16_bits(w);
-            *reinterpret_cast<uint16_t*>(chunk + sw128_offset(CF::kVloRow + c, kk)) = f16_bits(w - hi);
-        }
+        *reinterpret_cast<uint16_t*>(elem + sw128_offset(n, kk)) = f16_bits(w);
+        *reinterpret_cast<uint16_t*>(elem + CF::kWqElem + sw128_offset(n, kk)) = f16_bits(w - hi);
     }
     for (int e = tid; e < H * 2 * 96 * D; e += nth) {
         const int h = e / (2 * 96 * D), nh = (e / (96 * D)) % 2, n = (e / D) % 96, kk = e % D;
@@ -310,7 +304,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         mbar_init(bars + CF::bSFull, 1);
         mbar_init(bars + CF::bPReady, kSpNumSm * 32);
         mbar_init(bars + CF::bOFull, 1);
-        mbar_init(bars + CF::bOAReady, kSpNumSm * 32);
+        mbar_init(bars + CF::bOAReady, 128);
         mbar_init(bars + CF::bPjFull, 1);
         mbar_init(bars + CF::bPjEmpty, kSpNumPe * 32);
         for (int i = 0; i < 6; ++i) {
@@ -329,9 +323,9 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         for (int i = tid; i < 2 * C; i += kSpThreads) sbq[i] = gb[i];
         const uint4* gi = reinterpret_cast<const uint4*>(sp + SpParams<CF>::i16);
         for (int i = tid; i < 2048 / 16; i += kSpThreads) reinterpret_cast<uint4*>(smem + CF::oI16)[i] = gi[i];
-        // Q | K rows incl. the zero block and the pad chunks, V rows: must read as zeros wherever nothing is written
-        for (int i = tid; i < (CF::oWq - CF::oQK) / 16; i += kSpThreads)
-            reinterpret_cast<uint4*>(smem + CF::oQK)[i] = make_uint4(0, 0, 0, 0);
+        // K and V rows incl. their pad chunks: must read as zeros (finite) wherever nothing is written
+        for (int i = tid; i < (CF::oWq - CF::oK) / 16; i += kSpThreads)
+            reinterpret_cast<uint4*>(smem + CF::oK)[i] = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -370,15 +364,14 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             // One elected thread of a CONVERGED warp (not `lane == 0`: a divergent branch makes every tcgen05.mma cost ~45
             // cycles of issue, tools/umma_rate_probe.cu) issues every MMA of the CTA.  Measured cost per MMA (M = 128,
             // K = 16): A from shared memory max(N/2, 32 + N/4) cycles, A from TMEM N/2.
-            constexpr uint32_t id_q = umma_idesc(kFmtF16, kFmtF16, 128, CF::NQH), id_c = umma_idesc(kFmtF16, kFmtF16, 128, 32);
-            constexpr uint32_t id_s = umma_idesc(kFmtF16, kFmtF16, 128, 64);
-            constexpr uint32_t id_o = umma_idesc(kFmtF16, kFmtF16, 128, CF::ON) | kUmmaBMajorMN;
+            constexpr uint32_t id_q = umma_idesc(kFmtF16, kFmtF16, 128, CF::NQ), id_s = umma_idesc(kFmtF16, kFmtF16, 128, 64);
+            constexpr uint32_t id_o = umma_idesc(kFmtF16, kFmtF16, 128, 32) | kUmmaBMajorMN;
             constexpr uint32_t id_p = umma_idesc(kFmtF16, kFmtF16, 128, 96), id_r = umma_idesc(kFmtF16, kFmtF16, 128, 16);
             const uint64_t d_x = umma_desc_k_sw128(sb + CF::oXh), d_wq = umma_desc_k_sw128(sb + CF::oWq),
-                           d_wp = umma_desc_k_sw128(sb + CF::oWp), d_qk = umma_desc_k_sw128(sb + CF::oQK),
+                           d_wp = umma_desc_k_sw128(sb + CF::oWp), d_k = umma_desc_k_sw128(sb + CF::oK),
                            d_vh = umma_desc_k_sw128(sb + CF::oVh), d_vl = umma_desc_k_sw128(sb + CF::oVl),
                            d_i = umma_desc_k_sw128(sb + CF::oI16);
-            uint32_t nq = 0, np = 0;                       // weight chunks consumed from the two rings
+            uint32_t nq = 0, np = 0;                       // weight ring elements consumed from the two rings
             int next_q = 0;                                // next head whose QKV MMAs are to be issued
             auto issue_qkv = [&](int q) {
                 const int it = q / H, h = q - it * H, xb = it & 1;
@@ -390,18 +383,24 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kb = 0; kb < CF::KB; ++kb) {
-                    const uint32_t slot = nq % CF::kWqSlots;
-                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);
-                    tc_fence_after_sync();
                     const uint64_t a0 = d_x + ((xb * 49152 + kb * 16384) >> 4);
-                    const uint64_t b0 = d_wq + ((slot * CF::kWqChunk) >> 4);
+                    uint32_t slot = nq % CF::kWqSlots;
+                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W hi of the K block
+                    tc_fence_after_sync();
+                    uint64_t b0 = d_wq + ((slot * CF::kWqElem) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, (kb | ks) != 0);
-                        umma_f16_ts(tm + CF::tDq + CF::kVhiRow, tm + CF::tXl + (kb * 4 + ks) * 8, b0 + CF::kVhiRow * 8 + ks * 2, id_c, 1);
-                        if constexpr (!CF::kMergedLo)
-                            umma_f16_ss(tm + CF::tDq + CF::kVhiRow, a0 + ks * 2, b0 + CF::kVloRow * 8 + ks * 2, id_c, 1);
+                        umma_f16_ts(tm + CF::tDq, tm + CF::tXl + (kb * 4 + ks) * 8, b0 + ks * 2, id_q, 1);
                     }
+                    umma_commit(bars + CF::bWqEmpty + slot);
+                    ++nq;
+                    slot = nq % CF::kWqSlots;
+                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W lo
+                    tc_fence_after_sync();
+                    b0 = d_wq + ((slot * CF::kWqElem) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, 1);
                     umma_commit(bars + CF::bWqEmpty + slot);
                     ++nq;
                 }
@@ -411,15 +410,41 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     umma_commit(bars + CF::bXlEmpty);
                 }
             };
+            // S(G): rows 0-63 (window slot 0) against the keys of slot 0, rows 64-127 against those of slot 1: two MMAs per
+            // k step with the other half of the output lanes disabled; passes q_hi k_hi + q_lo k_hi + q_hi k_lo
+            auto issue_s = [&](int G) {
+                mbar_wait(bars + CF::bQkReady, G & 1);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = tm + CF::tQ + (pass == 1 ? 16 : 0);
+                    const uint64_t b = d_k + (pass == 2 ? 4 : 0);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t acc = (pass | ks) != 0;
+                        umma_f16_ts_lanes(tm + CF::tS, a + ks * 8, b + ks * 2, id_s, acc, 0u, 0u, ~0u, ~0u);
+                        umma_f16_ts_lanes(tm + CF::tS, a + ks * 8, b + 512 + ks * 2, id_s, acc, ~0u, ~0u, 0u, 0u);
+                    }
+                }
+                umma_commit(bars + CF::bSFull);
+                umma_commit(bars + CF::bQkFree);
+            };
+            // O(G) = P V: 16 keys per k step (= 2048 bytes of the [key][128 B] buffers), a row's own window is one d-wide
+            // part of the V rows; N = 32 (>= d: columns d .. 31 of O receive finite junk that nobody reads)
             auto issue_pv = [&](int G) {
                 mbar_wait(bars + CF::bVReady, G & 1);
                 mbar_wait(bars + CF::bPReady, G & 1);
                 tc_fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {           // 16 keys per step = 2048 bytes of the [key][128 B] buffers
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, d_vh + ks * 128, id_o, ks != 0);
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + 32 + ks * 8, d_vh + ks * 128, id_o, 1);
-                    umma_f16_ts(tm + CF::tO, tm + CF::tS + ks * 8, d_vl + ks * 128, id_o, 1);
+                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t a = tm + CF::tS + (pass == 1 ? 32 : 0) + ks * 8;
+                        const uint64_t b = (pass == 2 ? d_vl : d_vh) + ks * 128;
+                        const uint32_t acc = (pass | ks) != 0;
+                        umma_f16_ts_lanes(tm + CF::tO, a, b, id_o, acc, 0u, 0u, ~0u, ~0u);
+                        umma_f16_ts_lanes(tm + CF::tO, a, b + ((D * 2) >> 4), id_o, acc, ~0u, ~0u, 0u, 0u);
+                    }
                 }
                 umma_commit(bars + CF::bOFull);
                 umma_commit(bars + CF::bVFree);
@@ -455,44 +480,35 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 }
                 if (h == H - 1) umma_commit(bars + CF::bPjFull);
             };
-            for (int G = 0; G < total; ++G) {
-                if (next_q <= G) issue_qkv(next_q++);
-                tick(0);                                                         // 0: (first) QKV issue
-                // ---- S(G): rows 0-63 (window slot 0) against the keys of slot 0, rows 64-127 against those of slot 1: two
-                //      MMAs per k step with the other half of the output lanes disabled -- no junk columns, 64 TMEM columns
-                mbar_wait(bars + CF::bQkReady, G & 1);
-                tc_fence_after_sync();
-                tick(1);                                                         // 1: wait Q | K of the head
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    umma_f16_ss_lanes(tm + CF::tS, d_qk + ks * 2, d_qk + 4 + ks * 2, id_s, ks != 0, 0u, 0u, ~0u, ~0u);
-                    umma_f16_ss_lanes(tm + CF::tS, d_qk + ks * 2, d_qk + 512 + 4 + ks * 2, id_s, ks != 0, ~0u, ~0u, 0u, 0u);
-                }
-                umma_commit(bars + CF::bSFull);
-                umma_commit(bars + CF::bQkFree);
-                tick(2);                                                         // 2: S issue
-                if (next_q < total) issue_qkv(next_q++);     // QKV(G + 1) fills the tensor pipe during softmax(G)
-                tick(3);                                                         // 3: QKV(G + 1) issue incl. its waits
-                if (G > 0) issue_proj(G - 1);                // reads the projection operand before P V(G) overwrites it
-                tick(5);                                                         // 5: wait O operand (+ accumulator) + proj issue
-                issue_pv(G);
-                tick(4);                                                         // 4: wait P, V + P V issue
+            if (total > 0) {
+                issue_qkv(next_q++);
+                issue_s(0);
+                if (next_q < total) issue_qkv(next_q++);
             }
-            if (total > 0) issue_proj(total - 1);
+            for (int G = 0; G < total; ++G) {
+                issue_pv(G);
+                tick(0);                                                         // 0: wait P, V + P V issue
+                if (G + 1 < total) issue_s(G + 1);           // right behind P V(G): overwrites P(G) in issue order
+                tick(1);                                                         // 1: wait Q, K + S issue
+                if (next_q < total) issue_qkv(next_q++);     // QKV(G + 2) and proj(G) fill the tensor pipe during softmax(G + 1)
+                tick(2);                                                         // 2: QKV(G + 2) issue incl. its waits
+                issue_proj(G);
+                tick(3);                                                         // 3: wait O operand (+ accumulator) + proj issue
+            }
         } else if (warp == kSpFeed && elect_one()) {
             // weight feeder: two rings of bulk copies, each in exactly the order the issuer consumes it
             const uint8_t* gq = sp + SpParams<CF>::wq;
             const uint8_t* gp = sp + SpParams<CF>::wp;
-            const uint32_t nQ = uint32_t(total) * CF::KB, nP = uint32_t(total) * 2;
+            const uint32_t nQ = uint32_t(total) * CF::KB * 2, nP = uint32_t(total) * 2;
             uint32_t iq = 0, ip = 0;
             while (iq < nQ || ip < nP) {
                 if (iq < nQ) {
                     const uint32_t slot = iq % CF::kWqSlots;
                     if (iq < uint32_t(CF::kWqSlots) || mbar_test_wait(bars + CF::bWqEmpty + slot, ((iq / CF::kWqSlots) - 1) & 1)) {
-                        const uint32_t h = (iq / CF::KB) % H, kb = iq % CF::KB;
-                        mbar_arrive_expect_tx(bars + CF::bWqFull + slot, CF::kWqChunk);
-                        bulk_g2s(smem + CF::oWq + slot * CF::kWqChunk, gq + int64_t(h * CF::KB + kb) * CF::kWqChunk,
-                                 CF::kWqChunk, bars + CF::bWqFull + slot);
+                        const uint32_t h = (iq / (CF::KB * 2)) % H, e = iq % (CF::KB * 2);      // e = kb * 2 + part
+                        mbar_arrive_expect_tx(bars + CF::bWqFull + slot, CF::kWqElem);
+                        bulk_g2s(smem + CF::oWq + slot * CF::kWqElem, gq + int64_t(h * CF::KB * 2 + e) * CF::kWqElem,
+                                 CF::kWqElem, bars + CF::bWqFull + slot);
                         ++iq;
                     }
                 }
@@ -681,10 +697,10 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
         }
     } else if (warp < kSpDr0) {
-        // =========================================================================================== softmax + normalisation
+        // =========================================================================================== softmax
         // Two warps per 32-row lane quarter (both on the same SM sub-partition, as the TMEM lane rule demands): each takes
-        // 32 of the row's 64 logits and half of its d output columns; row max and row sum go through shared memory and a
-        // 64-thread named barrier.  One warp per quarter was latency-bound at ~2 k cycles per head (profiles/).
+        // 32 of the row's 64 logits; the row max goes through shared memory and a 64-thread named barrier, the two partial
+        // row sums are left in shared memory for the thread that normalises O (per head parity: it reads them one head later).
         sp_reg_inc<kSpRegsSm>();
         const int sw = warp - kSpSm0, q = sw & 3, ch = sw >> 2;
         const int r = q * 32 + lane, wslot = r >> 6, tok = r & 63;
@@ -693,8 +709,7 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
         // this lane's entry of the relative-position table for key 32 * ch (keys run down the table: - (yj * 15 + xj))
         const uint32_t tbl0 = sb + CF::oTbl + 4 * ((yi + WS - 1 - 4 * ch) * (2 * WS - 1) + xi + WS - 1);
         const uint32_t xmax_me = sb + CF::oXch + 4 * (ch * 128 + r), xmax_other = sb + CF::oXch + 4 * ((ch ^ 1) * 128 + r);
-        const uint32_t xsum_me = xmax_me + 1024, xsum_other = xmax_other + 1024;
-        constexpr int DH = D / 2, NP = D / 4;                // output columns / packed fp16 columns of this thread
+        const uint32_t xsum_me = sb + CF::oXch + 1024 + 4 * (ch * 128 + r);
         for (int it = 0; it < my_tiles; ++it) {
             // SW-MSA region mask bits of this row's 32 keys (:194-216); zero unless the window touches the wrapped border
             uint32_t mb = 0;
@@ -756,134 +771,151 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                     sum += p0 + p1;
                     split_f16x2(p0, p1, ph[j], pl[j]);
                 }
-                sp_st_shared_f32(xsum_me, sum);
+                sp_st_shared_f32(xsum_me + (G & 1) * 1024, sum);
                 tmem_st_x16(tm + CF::tS + lane_addr + ch * 16, ph);
                 tmem_st_x16(tm + CF::tS + lane_addr + 32 + ch * 16, pl);
                 tmem_wait_st();
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bPReady);
                 tick(17);                                                        // 17: softmax
-                // ---- O / rowsum -> fp16 hi / lo, the projection's A operand (written over O in place: both threads of a
-                //      row must have read their columns before either writes)
-                mbar_wait(bars + CF::bOFull, G & 1);
+            }
+        }
+    } else {
+        // =========================================================================================== QKV drain + normalisation
+        // thread = token.  Iteration n: q, k, v of head n out of D_qkv (fp16 hi / lo: q -> TMEM, k and v -> shared memory),
+        // then O(n - 1) / rowsum -> fp16 hi / lo over O in TMEM (the projection's A operand).  The v rows of head n and the
+        // normalisation of head n - 1 both wait for P V(n - 1), so the two jobs never wait on each other.
+        sp_reg_inc<kSpRegsDr>();
+        const int dw = warp - kSpDr0, r = dw * 32 + lane, wslot = r >> 6, tok = r & 63;
+        const uint32_t lane_addr = static_cast<uint32_t>(dw * 32) << 16;
+        const uint32_t rowoff = (tok >> 3) * 1024 + (tok & 7) * 128, sx = tok & 7;
+        const uint32_t k_row = sb + CF::oK + wslot * 8192 + rowoff;
+        const float* s_bq = reinterpret_cast<const float*>(smem + CF::oBq);
+        const uint32_t xsum = sb + CF::oXch + 1024 + 4 * r;
+        constexpr int NP = D / 2;                            // packed fp16 columns of a d-wide operand
+        {                                                    // Q hi / lo columns incl. their pads start as zeros
+            uint32_t z[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0u;
+            tmem_st_x32(tm + CF::tQ + lane_addr, z);
+            tmem_wait_st();
+        }
+        auto st_operand = [&](uint32_t taddr, const uint32_t (&hi)[NP], const uint32_t (&lo)[NP]) {
+            if constexpr (NP == 16) {
+                tmem_st_x16(taddr, hi);
+                tmem_st_x16(taddr + 16, lo);
+            } else {
+                static_assert(NP == 12 || NP == 16, "head dim 24 / 32");
+                uint32_t a[8], b[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[j] = hi[j]; b[j] = lo[j]; }
+                tmem_st_x8(taddr, a);
+                tmem_st_x4(taddr + 8, hi[8], hi[9], hi[10], hi[11]);
+                tmem_st_x8(taddr + 16, b);
+                tmem_st_x4(taddr + 24, lo[8], lo[9], lo[10], lo[11]);
+            }
+        };
+        for (int n = 0; n <= total; ++n) {
+            if (n < total) {
+                const int h = n % H;
+                mbar_wait(bars + CF::bDqFull, n & 1);
                 tc_fence_after_sync();
-                tick(18);                                                        // 18: wait O
-                uint32_t oraw[DH];
+                tick(24);                                                        // 24: wait D_qkv
+                uint32_t raw[D];
 #pragma unroll
-                for (int c = 0; c < DH / 4; ++c) {
-                    uint32_t t4[4];
-                    tmem_ld_x4(tm + CF::tO + lane_addr + wslot * D + ch * DH + c * 4, t4);
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tDq + lane_addr + c * 8, t8);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) oraw[c * 4 + j] = t4[j];
+                    for (int j = 0; j < 8; ++j) raw[c * 8 + j] = t8[j];
                 }
                 tmem_wait_ld();
-                sp_named_sync(1 + q, 64);
-                const float inv = 1.0f / (sum + sp_ld_shared_f32(xsum_other));
+                uint32_t qh[NP], ql[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    split_f16x2(__uint_as_float(raw[2 * j]) + s_bq[h * D + 2 * j],
+                                __uint_as_float(raw[2 * j + 1]) + s_bq[h * D + 2 * j + 1], qh[j], ql[j]);
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tDq + lane_addr + D + c * 8, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) raw[c * 8 + j] = t8[j];
+                }
+                if (n > 0) mbar_wait(bars + CF::bQkFree, (n - 1) & 1);    // S(n - 1) has read Q and K
+                tc_fence_after_sync();
+                st_operand(tm + CF::tQ + lane_addr, qh, ql);
+                tmem_wait_ld();
+                tick(25);                                                        // 25: q -> TMEM (+ wait Q, K free)
+#pragma unroll
+                for (int ch = 0; ch < D / 8; ++ch) {           // k hi -> chunks 0.., k lo -> chunks 4..
+                    uint32_t kh[4], kl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        split_f16x2(__uint_as_float(raw[ch * 8 + 2 * j]), __uint_as_float(raw[ch * 8 + 2 * j + 1]), kh[j], kl[j]);
+                    st_shared_v4(k_row + ((uint32_t(ch) ^ sx) << 4), kh[0], kh[1], kh[2], kh[3]);
+                    st_shared_v4(k_row + ((uint32_t(4 + ch) ^ sx) << 4), kl[0], kl[1], kl[2], kl[3]);
+                }
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tDq + lane_addr + 2 * D + c * 8, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) raw[c * 8 + j] = t8[j];
+                }
+                tmem_wait_st();
+                tc_fence_before_sync();
+                fence_proxy_async_smem();
+                mbar_arrive(bars + CF::bQkReady);
+                tick(26);                                                        // 26: k -> shared memory
+                tmem_wait_ld();
+                tc_fence_before_sync();
+                mbar_arrive(bars + CF::bDqEmpty);              // the accumulator may be overwritten by QKV(n + 1)
+                if (n > 0) mbar_wait(bars + CF::bVFree, (n - 1) & 1);     // P V(n - 1) has read the V rows
+                tick(27);                                                        // 27: load v + wait V rows free
+#pragma unroll
+                for (int ch = 0; ch < D / 8; ++ch) {           // v -> hi / lo rows [key][slot 0 d | slot 1 d]
+                    uint32_t vh[4], vl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        split_f16x2(__uint_as_float(raw[ch * 8 + 2 * j]), __uint_as_float(raw[ch * 8 + 2 * j + 1]), vh[j], vl[j]);
+                    const uint32_t off = rowoff + ((uint32_t(wslot * (D / 8) + ch) ^ sx) << 4);
+                    st_shared_v4(sb + CF::oVh + off, vh[0], vh[1], vh[2], vh[3]);
+                    st_shared_v4(sb + CF::oVl + off, vl[0], vl[1], vl[2], vl[3]);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(bars + CF::bVReady);
+                tick(28);                                                        // 28: v -> shared memory
+            }
+            if (n >= 1) {
+                const int G = n - 1;
+                mbar_wait(bars + CF::bOFull, G & 1);
+                tc_fence_after_sync();
+                tick(29);                                                        // 29: wait O
+                uint32_t oraw[D];
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    uint32_t t8[8];
+                    tmem_ld_x8(tm + CF::tO + lane_addr + c * 8, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) oraw[c * 8 + j] = t8[j];
+                }
+                const float inv = 1.0f / (sp_ld_shared_f32(xsum + (G & 1) * 1024) + sp_ld_shared_f32(xsum + (G & 1) * 1024 + 512));
+                tmem_wait_ld();
                 uint32_t oh[NP], ol[NP];
 #pragma unroll
                 for (int j = 0; j < NP; ++j)
                     split_f16x2(__uint_as_float(oraw[2 * j]) * inv, __uint_as_float(oraw[2 * j + 1]) * inv, oh[j], ol[j]);
-                const uint32_t ta = tm + CF::tOA + lane_addr + ch * NP;
-                if constexpr (NP == 8) {
-                    tmem_st_x8(ta, oh);
-                    tmem_st_x8(ta + 16, ol);
-                } else {
-                    static_assert(NP == 6 || NP == 8, "head dim 24 / 32");
-                    tmem_st_x4(ta, oh[0], oh[1], oh[2], oh[3]);
-                    tmem_st_x2(ta + 4, oh[4], oh[5]);
-                    tmem_st_x4(ta + 16, ol[0], ol[1], ol[2], ol[3]);
-                    tmem_st_x2(ta + 20, ol[4], ol[5]);
-                    if (ch == 1) {                               // k = 24 .. 31 of the projection operand: zeros
-                        tmem_st_x4(tm + CF::tOA + lane_addr + 12, 0u, 0u, 0u, 0u);
-                        tmem_st_x4(tm + CF::tOA + lane_addr + 28, 0u, 0u, 0u, 0u);
-                    }
+                st_operand(tm + CF::tOA + lane_addr, oh, ol);
+                if constexpr (NP == 12) {                        // k = 24 .. 31 of the projection operand: zeros
+                    tmem_st_x4(tm + CF::tOA + lane_addr + 12, 0u, 0u, 0u, 0u);
+                    tmem_st_x4(tm + CF::tOA + lane_addr + 28, 0u, 0u, 0u, 0u);
                 }
                 tmem_wait_st();
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bOAReady);
-                tick(19);                                                        // 19: normalisation
+                tick(30);                                                        // 30: normalisation
             }
-        }
-    } else {
-        // =========================================================================================== QKV drain
-        sp_reg_dec<kSpRegsDr>();
-        const int dw = warp - kSpDr0, r = dw * 32 + lane, wslot = r >> 6, tok = r & 63;
-        const uint32_t lane_addr = static_cast<uint32_t>(dw * 32) << 16;
-        const uint32_t rowoff = (tok >> 3) * 1024 + (tok & 7) * 128, sx = tok & 7;
-        const uint32_t qk_row = sb + CF::oQK + wslot * 8192 + rowoff;
-        const float* s_bq = reinterpret_cast<const float*>(smem + CF::oBq);
-        for (int G = 0; G < total; ++G) {
-            const int h = G % H;
-            mbar_wait(bars + CF::bDqFull, G & 1);
-            tc_fence_after_sync();
-            tick(24);                                                            // 24: wait D_qkv
-            uint32_t raw[2 * D];                               // q | k columns
-#pragma unroll
-            for (int c = 0; c < 2 * D / 8; ++c) {
-                uint32_t t8[8];
-                tmem_ld_x8(tm + CF::tDq + lane_addr + c * 8, t8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) raw[c * 8 + j] = t8[j];
-            }
-            tmem_wait_ld();
-            if (G > 0) mbar_wait(bars + CF::bQkFree, (G - 1) & 1);
-            tick(25);                                                            // 25: load q | k + wait Q | K rows free
-#pragma unroll
-            for (int ch = 0; ch < D / 8; ++ch) {               // q (+ bias) -> chunks 0.., k -> chunks 4..
-                uint32_t pq[4], pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = ch * 8 + 2 * j;
-                    pq[j] = pack_f16x2(__uint_as_float(raw[c]) + s_bq[h * D + c], __uint_as_float(raw[c + 1]) + s_bq[h * D + c + 1]);
-                    pk[j] = pack_f16x2(__uint_as_float(raw[D + c]), __uint_as_float(raw[D + c + 1]));
-                }
-                st_shared_v4(qk_row + ((uint32_t(ch) ^ sx) << 4), pq[0], pq[1], pq[2], pq[3]);
-                st_shared_v4(qk_row + ((uint32_t(4 + ch) ^ sx) << 4), pk[0], pk[1], pk[2], pk[3]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(bars + CF::bQkReady);
-            tick(26);                                                            // 26: q | k -> shared memory
-            uint32_t rv[D];                                    // v columns (d = 24: x_hi Wv_hi + x_lo Wv_hi, plus x_hi Wv_lo below)
-#pragma unroll
-            for (int c = 0; c < D / 8; ++c) {
-                uint32_t t8[8];
-                tmem_ld_x8(tm + CF::tDq + lane_addr + CF::kVhiRow + c * 8, t8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rv[c * 8 + j] = t8[j];
-            }
-            if constexpr (CF::kMergedLo) {
-                uint32_t rl[D];
-#pragma unroll
-                for (int c = 0; c < D / 8; ++c) {
-                    uint32_t t8[8];
-                    tmem_ld_x8(tm + CF::tDq + lane_addr + CF::kVloRow + c * 8, t8);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rl[c * 8 + j] = t8[j];
-                }
-                tmem_wait_ld();
-#pragma unroll
-                for (int c = 0; c < D; ++c) rv[c] = __float_as_uint(__uint_as_float(rv[c]) + __uint_as_float(rl[c]));
-            }
-            tmem_wait_ld();
-            tc_fence_before_sync();
-            mbar_arrive(bars + CF::bDqEmpty);                  // the accumulator may be overwritten by QKV(G + 1)
-            if (G > 0) mbar_wait(bars + CF::bVFree, (G - 1) & 1);
-            tick(27);                                                            // 27: load v + wait V rows free
-#pragma unroll
-            for (int ch = 0; ch < D / 8; ++ch) {               // v -> hi / lo rows [key][slot 0 d | slot 1 d]
-                uint32_t vh[4], vl[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = ch * 8 + 2 * j;
-                    split_f16x2(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]), vh[j], vl[j]);
-                }
-                const uint32_t off = rowoff + ((uint32_t(wslot * (D / 8) + ch) ^ sx) << 4);
-                st_shared_v4(sb + CF::oVh + off, vh[0], vh[1], vh[2], vh[3]);
-                st_shared_v4(sb + CF::oVl + off, vl[0], vl[1], vl[2], vl[3]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(bars + CF::bVReady);
-            tick(28);                                                            // 28: v -> shared memory
         }
     }
 

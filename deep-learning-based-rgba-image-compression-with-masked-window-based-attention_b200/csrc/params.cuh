@@ -46,14 +46,14 @@ __host__ __device__ inline int64_t mwa_tc_section_bytes(int C, int heads) {
     return ng * (kb * nqkv * 128 + int64_t(C) * 128) + ng * nqkv * 4 + int64_t(C) * 4;
 }
 
-// size of the split-precision section (csrc/mwa_sp.cu, layout: SpParams<> there): per head the fp16 hi (+ lo for the v
-// rows) K-major SW128 slabs of Wq|Wk|Wv per 64-channel K block in ring-slot sized chunks, per head and output half the
+// size of the split-precision section (csrc/mwa_sp.cu, layout: SpParams<> there): per head the fp16 hi and lo
+// K-major SW128 slabs of Wq|Wk|Wv per 64-channel K block as ring-slot sized elements, per head and output half the
 // [hi | lo] slab of Wproj, the scaled q bias, the projection bias with the v bias folded in, the relative-position
 // table times log2(e) and a 16 x 16 identity operand.  0 when the geometry is not covered.
 __host__ __device__ inline int64_t mwa_sp_section_bytes(int C, int heads, int ws) {
     if (!(C == 192 && ws == 8 && (heads == 8 || heads == 6))) return 0;
     const int64_t tbl = (2 * ws - 1) * (2 * ws - 1);
-    return int64_t(heads) * 3 * (4 * (C / heads) * 128) + int64_t(heads) * 2 * 12288 + 2 * int64_t(C) * 4 + align_up(heads * tbl * 4, 1024) + 2048;
+    return int64_t(heads) * 3 * 2 * (3 * (C / heads) * 128) + int64_t(heads) * 2 * 12288 + 2 * int64_t(C) * 4 + align_up(heads * tbl * 4, 1024) + 2048;
 }
 
 struct MwaParamLayout {

@@ -15,7 +15,7 @@ from torch.nn import functional as F
 from torch.autograd import Function
 
 from .. import _abi
-from ._params import ParamBlock
+from ._params import ParamBlock, ParamBlockOwner
 
 
 class LowerBound(Function):
@@ -143,7 +143,7 @@ class _GDNFunction(Function):
         return gx, gb, gg, None
 
 
-class GDN(nn.Module):
+class GDN(ParamBlockOwner, nn.Module):
     """Generalized divisive normalization layer (B200 kernels).
     y[i] = x[i] / sqrt(beta[i] + sum_j(gamma[i, j] * x[j]^2))
     """

@@ -7,8 +7,7 @@ table gradient, and leave four token-major scratch tensors), followed by the wei
 as plain GEMMs and column sums over all tokens (library GEMM: `dWqkv = dqkv^T xw`, `dWproj = dy^T ao`).
 With `algo = ALGO_SIMT` one all-in-one kernel does the token GEMMs too; otherwise (default) the three token GEMMs
 (qkv recompute, dAO = dy Wproj, dXw = dqkv Wqkv) run in the library GEMM as well and hand-written gather / per-window
-core / scatter kernels do the rest (3.5x faster).  `_differentiable_block` is a torch re-statement kept ONLY as a
-cross-check for the tests.
+core / scatter kernels do the rest (3.5x faster).
 """
 from __future__ import annotations
 
@@ -17,7 +16,7 @@ from torch import nn
 from torch.autograd import Function
 
 from .. import _abi
-from ._params import ParamBlock
+from ._params import ParamBlock, ParamBlockOwner
 
 
 def _window_partition(x, window_size):
@@ -30,44 +29,6 @@ def _window_reverse(windows, window_size, H, W):
     B = int(windows.shape[0] / (H * W / window_size / window_size))
     x = windows.view(B, H // window_size, W // window_size, window_size, window_size, -1)
     return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
-
-
-def _band(n, size, ws, s, device):
-    c = torch.arange(n, device=device)
-    return (c >= size - ws).long() + (c >= size - s).long()
-
-
-def _differentiable_block(x, alpha, qkv_w, qkv_b, proj_w, proj_b, table, index, heads, ws, shift, scale):
-    """torch re-statement used ONLY to obtain gradients (see module docstring)."""
-    B, C, H, W = x.shape
-    N = ws * ws
-    xs = x.permute(0, 2, 3, 1)
-    if shift > 0:
-        xs = torch.roll(xs, shifts=(-shift, -shift), dims=(1, 2))
-    xw = _window_partition(xs, ws).reshape(-1, N, C)
-    if alpha is None:
-        keep = torch.ones(xw.shape[0], dtype=torch.bool, device=x.device)
-    else:
-        a = alpha.permute(0, 2, 3, 1)
-        if shift > 0:
-            a = torch.roll(a, shifts=(-shift, -shift), dims=(1, 2))
-        keep = _window_partition(a, ws).sum(dim=(1, 2, 3)) != 0
-    d = C // heads
-    qkv = torch.nn.functional.linear(xw, qkv_w, qkv_b).reshape(-1, N, 3, heads, d).permute(2, 0, 3, 1, 4)
-    att = (qkv[0] * scale) @ qkv[1].transpose(-2, -1)
-    att = att + table[index.view(-1)].view(N, N, -1).permute(2, 0, 1).unsqueeze(0)
-    if shift > 0:
-        rid = 3 * _band(H, H, ws, shift, x.device)[:, None] + _band(W, W, ws, shift, x.device)[None, :]
-        rid = _window_partition(rid.view(1, H, W, 1).float(), ws).view(-1, N)
-        m = (rid[:, :, None] != rid[:, None, :]).float() * -100.0
-        att = att + m.repeat(B, 1, 1)[:, None]
-    y = (torch.softmax(att, dim=-1) @ qkv[2]).transpose(1, 2).reshape(-1, N, C)
-    y = torch.nn.functional.linear(y, proj_w, proj_b)
-    y = y * keep[:, None, None].to(y.dtype)
-    ys = _window_reverse(y.view(-1, ws, ws, C), ws, H, W)
-    if shift > 0:
-        ys = torch.roll(ys, shifts=(shift, shift), dims=(1, 2))
-    return x + ys.permute(0, 3, 1, 2)
 
 
 class WindowAttentionFunction(Function):
@@ -229,7 +190,7 @@ class TokenAttentionFunction(Function):
         return (gx if need[0] else None), None, gw1, gb1, gw2, gb2, (gtab if need[6] else None), None
 
 
-class WindowAttentionBase(nn.Module):
+class WindowAttentionBase(ParamBlockOwner, nn.Module):
     """Window based multi-head self attention (W-MSA) with relative position bias -- parameter container and
     token-level forward.  Same constructor / attributes / state-dict keys as the reference class
     (layers/masked_win_attention.py:49-131 == layers/win_attention.py:37-115)."""

@@ -46,6 +46,10 @@ for cfg in cfgs:
 run(192, 8, 8, 4, 2, 64, 96, "blob", 1.0, True)
 run(192, 8, 8, 4, 2, 64, 96, "blob", 3.0, True)
 run(192, 6, 8, 4, 2, 64, 96, "blob", 1.0, True)
+run(192, 6, 8, 4, 2, 64, 96, "blob", 3.0, True)
+run(192, 8, 8, 4, 2, 64, 96, "blob", 10.0, True)
+run(192, 8, 8, 4, 1, 8, 8, "ones", 1.0, True)
+run(192, 6, 8, 0, 1, 8, 24, "ones", 1.0, True)
 # quick timing
 m = pkg.MaskedWinBasedAttention(192, 8, 8, 4).to(dev)
 x = torch.randn(16, 192, 128, 192, device=dev); a = torch.ones(16, 1, 128, 192, device=dev)

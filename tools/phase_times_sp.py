@@ -31,11 +31,11 @@ cyc = torch.tensor(t[64:64 + 148], dtype=torch.float64); til = torch.tensor(t[32
 tiles0 = max(til[0].item(), 1)
 print(f"h={heads}: all launches {plain*1e3:.0f} us (timing build {e0.elapsed_time(e1)*1e3:.0f} us); per-CTA cycles min {cyc.min():.0f} median {cyc.median():.0f} "
       f"max {cyc.max():.0f}; tiles/CTA {til.min():.0f}-{til.max():.0f}; cycles/tile median {(cyc / til.clamp(min=1)).median():.0f}")
-names = {0: "QKV issue (first)", 1: "wait Q|K", 2: "S issue", 3: "QKV(G+1) issue+waits", 4: "wait P,V + PV issue", 5: "wait OA/acc + proj issue",
+names = {0: "wait P,V + PV issue", 1: "wait Q,K + S issue", 2: "QKV(G+2) issue+waits", 3: "wait OA/acc + proj issue",
          8: "set-up + wait X_hi free", 9: "wait proj complete", 10: "epilogue+conversion", 11: "wait X_lo free", 12: "X_lo->TMEM", 13: "(acc released)",
-         16: "wait S", 17: "softmax", 18: "wait O", 19: "normalise",
-         24: "wait D_qkv", 25: "ld q|k + wait QK free", 26: "q|k->smem", 27: "ld v + wait V free", 28: "v->smem"}
-roles = ["MMA issuer", "converter/epilogue", "softmax", "drain"]
+         16: "wait S", 17: "softmax",
+         24: "wait D_qkv", 25: "q->TMEM (+wait QK free)", 26: "k->smem", 27: "ld v + wait V free", 28: "v->smem", 29: "wait O", 30: "normalise"}
+roles = ["MMA issuer", "converter/epilogue", "softmax", "drain+normalise"]
 ev, tot = [], {}
 for role_i in range(4):
     prev = 0

@@ -7,6 +7,9 @@
 //          taken at a row offset inside the same slab (the V-column correction passes of the QKV GEMM)
 //   koff   A and B taken from the two 64-byte halves of one [128 x 64] K-major SW128 buffer (Q | K side by side), plus
 //          the zero-block trick: D = [A_top; 0] B0^T + [0; A_bot] B1^T
+//   half   P V with one accumulator half per window: A from TMEM, B MN-major [key][w0 n | w1 n] (n = N / 2 columns per
+//          window inside one 128-byte row), two lane-masked MMAs per k step, the second with its B start address advanced
+//          by n * 2 bytes INSIDE the swizzle atom: D[0:64] = A[0:64] B[:, 0:n], D[64:128] = A[64:128] B[:, n:2n]
 //   war    an MMA that reads its A operand from TMEM columns which the NEXT MMA (issued right behind it) overwrites
 //          as its accumulator: the first result must be unaffected (in-order execution of the tensor pipe)
 #include <cstdio>
@@ -26,18 +29,9 @@ using namespace b200;
         }                                                                                  \
     } while (0)
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 constexpr uint32_t kBMajorMN = 1u << 16;
 
-enum Mode { TS = 0, MN = 1, TSMN = 2, ACC = 3, KOFF = 4, WAR = 5 };
+enum Mode { TS = 0, MN = 1, TSMN = 2, ACC = 3, KOFF = 4, WAR = 5, HALF = 6 };
 
 // A [128][K] fp16 row-major; B: K-major modes [N][K], MN-major modes [K][N]; D [128][N] fp32
 __global__ void __launch_bounds__(128, 1)
@@ -52,8 +46,8 @@ probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, flo
     uint8_t* sZ = smem + 4 * 16384;           // 8 KB of zeros
     for (int i = tid; i < (4 * 16384 + 8192) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const bool a_tmem = (mode == TS || mode == TSMN || mode == WAR);
-    const bool b_mn = (mode == MN || mode == TSMN);
+    const bool a_tmem = (mode == TS || mode == TSMN || mode == WAR || mode == HALF);
+    const bool b_mn = (mode == MN || mode == TSMN || mode == HALF);
     if (!a_tmem && mode != KOFF)
         for (int i = tid; i < 128 * K; i += 128) {
             int r = i / K, k = i % K;
@@ -128,6 +122,14 @@ probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, flo
                     // second MMA: accumulator over the columns that hold A (and beyond); operands from smem (zeros)
                     const uint32_t idesc2 = umma_idesc(kFmtF16, kFmtF16, 128, 128);
                     umma_f16_ss(tm + tD2, umma_desc_k_sw128(smem_u32(sA)), umma_desc_k_sw128(smem_u32(sA)), idesc2, 0);   // sA is all zeros in this mode
+                }
+            } else if (mode == HALF) {
+                const int n = N / 2;
+                const uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, 128, n) | kBMajorMN;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t b0 = smem_u32(sB) + ks * 2048;
+                    umma_f16_ts_lanes(tm + tD, tm + tA + ks * 8, umma_desc_k_sw128(b0), idesc, ks > 0, 0u, 0u, ~0u, ~0u);
+                    umma_f16_ts_lanes(tm + tD, tm + tA + ks * 8, umma_desc_k_sw128(b0 + n * 2), idesc, ks > 0, ~0u, ~0u, 0u, 0u);
                 }
             } else if (mode == ACC) {
                 // first N columns from all B rows; then columns [N-32, N) get a second helping from B rows [N-32, N)
@@ -205,13 +207,15 @@ static int run_case(const char* name, int mode, int N, int K, int reps = 1) {
     srand(99 + N * 7 + K + mode);
     for (size_t i = 0; i < hA.size(); ++i) { hA[i] = f2h((rand() % 2001 - 1000) / 500.f); fA[i] = h2f(hA[i]); }
     for (size_t i = 0; i < hB.size(); ++i) { hB[i] = f2h((rand() % 2001 - 1000) / 500.f); fB[i] = h2f(hB[i]); }
-    const bool b_mn = (mode == MN || mode == TSMN);
+    const bool b_mn = (mode == MN || mode == TSMN || mode == HALF);
     for (int m = 0; m < 128; ++m)
         for (int n = 0; n < N; ++n) {
             double acc = 0;
+            if (mode == HALF && n >= N / 2) { ref[m * N + n] = 0.f; continue; }
             for (int k = 0; k < K; ++k) {
                 double b;
-                if (mode == KOFF) b = fB[((m < 64 ? 0 : N) + n) * K + k];
+                if (mode == HALF) b = fB[k * N + (m < 64 ? 0 : N / 2) + n];
+                else if (mode == KOFF) b = fB[((m < 64 ? 0 : N) + n) * K + k];
                 else b = b_mn ? fB[k * N + n] : fB[n * K + k];
                 acc += double(fA[m * K + k]) * b;
             }
@@ -239,6 +243,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps = 1) {
     CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0;
     for (size_t i = 0; i < hD.size(); ++i) {
+        if (mode == HALF && int(i % N) >= N / 2) continue;
         double e = fabs(double(hD[i]) - ref[i]);
         if (!(e <= maxerr)) maxerr = e;
     }
@@ -262,6 +267,9 @@ int main() {
     bad += run_case("tsmn", TSMN, 48, 64);
     bad += run_case("tsmn", TSMN, 64, 64);
     bad += run_case("tsmn", TSMN, 16, 128);
+    bad += run_case("half", HALF, 64, 64);
+    bad += run_case("half", HALF, 48, 64);
+    bad += run_case("half", HALF, 32, 64);
     bad += run_case("acc", ACC, 80, 64);
     bad += run_case("acc", ACC, 96, 128);
     bad += run_case("koff", KOFF, 64, 32);
