@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path (masked window attention + GDN/IGDN + latent rounding) on B200.
+"""Benchmark on B200: the RGBA codec's encode + decode forward, its hot path, and the kernels' rooflines.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs forward,hotpath,config4,config5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload "C2-hotpath" (BASELINE.json configs[1], per GPU): every hot-path call that ONE
-AutoEncoderRGB_Journal encode+decode forward makes on a batch of 16 synthetic 768x512 RGBA images, at the
-call-site shapes: 4 masked window attentions, 6 GDN/IGDN, 22 rounding launches.
-A "step" is one pass over all of them.  value = images/s = 16 * N / step time (device time, max over ranks).
-Images are independent -> ranks shard by image with no collective (weak scaling, 16 images per GPU).
-Prints ONE JSON line (rank 0).
+Workload "C2-forward" (BASELINE.json configs[1], per GPU): the full AutoEncoderRGB_Journal encode + decode forward
+(<package>/codec.py: the reference's module tree on the B200 modules, convolutions through cuDNN in fp32) on a batch of
+16 synthetic 768x512 RGBA images, random-init weights.  A "step" is one forward of the batch incl. the alpha pyramids.
+value = images/s = 16 * N / step time (device time, max over ranks); e2e = the same with the RGBA batch coming from
+pinned host memory and x_hat going back, copies inside the timed region.  Images are independent -> ranks shard by image
+with no collective (weak scaling, 16 images per GPU).  The hot-path kernels are timed live inside the same steps with
+CUDA events around the module calls; `roofline` is the masked window-attention kernel the metric names.
+Extra legs on the same JSON line: `hotpath` (round 1's workload: only the hot-path call sites, back to back),
+`config4` (attention microbench, 6 heads, 0-100 % masked), `config5` (training step of the codec on 256x256 crops with
+the NCCL gradient all-reduce).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -29,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "768x512 RGBA images/s (hot path: masked window attention + GDN/IGDN + latent rounding)"
+METRIC = "768x512 RGBA images/s (AutoEncoderRGB_Journal encode + decode forward); masked-attn kernel % of roofline"
 UNIT = "images/s"
 BATCH_PER_GPU = 16
 IMG_H, IMG_W = 512, 768
@@ -188,80 +192,403 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+
+
+# ------------------------------------------------------------------------------------------------ plumbing
+def _env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0")))
+
+
+class Dist:
+    """barrier + max-over-ranks on the device (NCCL); the inference data path has no collective"""
+
+    def __init__(self, dev, world):
+        self.dev, self.world, self.dist = dev, world, None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(fn, steps, warmup, D: Dist):
+    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream"""
+    for _ in range(warmup):
+        fn()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    D.barrier()
+    return D.max_ms(e0.elapsed_time(e1)) / steps, t0, time.time()
+
+
+# ------------------------------------------------------------------------------------------------ the codec workload
+def synthetic_rgba(batch: int, seed0: int) -> torch.Tensor:
+    """(B, 4, H, W) in [0, 1]: smooth colour fields + noise, alpha = soft ellipse blobs; the colour planes are zero
+    where alpha is (what the dataset feeds: my_datasets pre-multiply by the binarised alpha)"""
+    alpha = synthetic_alpha(batch, seed0)
+    yy = torch.linspace(0, 1, IMG_H).view(1, 1, IMG_H, 1)
+    xx = torch.linspace(0, 1, IMG_W).view(1, 1, 1, IMG_W)
+    out = torch.empty(batch, 4, IMG_H, IMG_W)
+    for b in range(batch):
+        g = torch.Generator().manual_seed(seed0 + b + 5000)
+        f = (1.0 + 4.0 * torch.rand(6, generator=g)).tolist()
+        rgb = torch.cat([0.5 + 0.4 * torch.sin(6.28 * (f[0] * xx + f[1] * yy)), 0.5 + 0.4 * torch.cos(6.28 * (f[2] * yy - f[3] * xx)),
+                         0.5 + 0.3 * torch.sin(6.28 * (f[4] * xx * yy) + f[5])], dim=1)[0]
+        rgb = (rgb + 0.05 * torch.randn(3, IMG_H, IMG_W, generator=g)).clamp(0, 1)
+        out[b, :3] = rgb * (alpha[b] > 0).float()
+        out[b, 3] = alpha[b, 0]
+    return out
+
+
+class OpTimer:
+    """CUDA events around every hot-path module call (forward hooks), recorded on the launching stream inside the timed
+    steps: the per-kernel durations behind `rooflines` are measured live, in the run that prints them"""
+
+    def __init__(self, net, pkg):
+        self.names, self.events, self.on = [], {}, False
+        for name, m in net.named_modules():
+            if isinstance(m, (pkg.GDN, pkg.MaskedWinBasedAttention)):
+                self.names.append(name)
+                self.events[name] = []
+                m.register_forward_pre_hook(self._pre(name))
+                m.register_forward_hook(self._post(name))
+
+    def _pre(self, name):
+        def hook(mod, args):
+            if self.on:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self.events[name].append([e, None])
+        return hook
+
+    def _post(self, name):
+        def hook(mod, args, out):
+            if self.on:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self.events[name][-1][1] = e
+        return hook
+
+    def mean_ms(self):
+        return {n: statistics.mean(a.elapsed_time(b) for a, b in ev) for n, ev in self.events.items() if ev}
+
+
+# our kernels per forward: 2 alpha pyramids (2 + 1 launches), 4 attention calls x (scan, compact, dropped-window copy,
+# main), 6 GDN, 4 gates, z rounding + 10 x (quantise, lrp add)
+LAUNCHES_PER_FORWARD = 3 + 4 * 4 + 6 + 4 + 1 + 20
+# round 1's hot-path-only step: 4 attention calls x 4 + 6 GDN + 22 rounding launches
+LAUNCHES_PER_HOTPATH_STEP = 4 * 4 + 6 + (2 + 20)
+
+
+def traffic_table():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (tools/ncu_traffic.py writes the table together
+    with the sha256 of the capture it was read from and the digest of the library that was profiled)"""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
+def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None, want_e2e=True, sampler=None):
+    torch.backends.cudnn.allow_tf32 = bool(tf32_convs)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(234)
+    net = pkg.RGBACodec().eval().to(dev)
+    timer = OpTimer(net, pkg)
+    rgba_host = synthetic_rgba(BATCH_PER_GPU, seed0=BATCH_PER_GPU * rank).pin_memory()
+    rgba = rgba_host.to(dev)
+    image, alpha = rgba[:, :3].contiguous(), rgba[:, 3:4].contiguous()
+
+    def step(img=image, a=alpha):
+        me = net.EncMakeMask(a)                                  # trainRGB.py:283
+        return net(img, a, a, me[0], me[1], me[2], me[3])        # trainRGB.py:289 (reconmask = the alpha itself)
+
+    steps = steps or args.steps
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        D.barrier()
+        if sampler is not None:                                  # keep the GPU under load until the sampler is live
+            t_dead = time.time() + 4.0
+            while not sampler.rows and time.time() < t_dead and sampler.proc is not None:
+                step()
+                torch.cuda.synchronize()
+        timer.on = True
+        ms_per_step, t0, t1 = timed_steps(step, steps, 0, D)
+        timer.on = False
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    per_op = timer.mean_ms()
+    value = BATCH_PER_GPU * world / (ms_per_step * 1e-3)
+
+    # ---- rooflines of the hot-path kernels inside the forward (rank 0's kernels): algorithmic work / measured duration
+    pyr = _host_pyramid(rgba_host[:, 3:4])
+    traffic = traffic_table()
+    roofs = []
+    big = [n for n in per_op if n.endswith("attention1.attn") and n.startswith("Encoder") or
+           n.endswith("attention2.attn") and n.startswith("Decoder")]
+    kept8 = int(_host_kept_windows(pyr[1].contiguous(), 8, 4).sum())
+    nwin8 = BATCH_PER_GPU * (IMG_H // 32) * (IMG_W // 32)
+    if big:
+        ms8 = sum(per_op[n] for n in big)
+        fl8 = len(big) * kept8 * FLOPS_PER_WINDOW[(192, 8)]
+        t8 = traffic.get("attention_8x8")
+        roofs.append({"kernel": "masked window attention 8x8 C=192, split-precision tcgen05 (op = scan + compact + dropped-window "
+                                f"copy + main kernel; {len(big)} ops/step)",
+                      "bound": "tensor", "achieved": fl8 / (ms8 * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
+                      "frac": fl8 / (ms8 * 1e-3) / 1e12 / pk["tensor"],
+                      "traffic": t8["dram_bytes_per_launch"] if t8 else None, "traffic_source": t8["source"] if t8 else None,
+                      "hbm_gbs": len(big) * nwin8 * 98560 / (ms8 * 1e-3) / 1e9, "ms_per_op": ms8 / len(big),
+                      "kept_windows_per_op": kept8, "windows_per_op": nwin8,
+                      "note": "algorithmic FLOPs (22.02 MFLOP per kept window) over the bf16 dense peak; the kernel runs "
+                              "3 fp16 passes per contraction to be fp32-faithful, so its own ceiling is peak / 3"})
+    small = [n for n in per_op if n.endswith(".attn") and n not in big]
+    if small:
+        kept4 = int(_host_kept_windows(pyr[2].contiguous(), 4, 2).sum())
+        ms4 = sum(per_op[n] for n in small)
+        by4 = len(small) * BATCH_PER_GPU * (IMG_H // 32) * (IMG_W // 32) * 10304
+        roofs.append({"kernel": f"masked window attention 4x4 C=80, fp32 ({len(small)} ops/step)", "bound": "hbm",
+                      "achieved": by4 / (ms4 * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": by4 / (ms4 * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "ms_per_op": ms4 / len(small),
+                      "tflops": len(small) * kept4 * FLOPS_PER_WINDOW[(80, 4)] / (ms4 * 1e-3) / 1e12})
+    gdn = [n for n in per_op if "gdn" in n]
+    if gdn:
+        px = BATCH_PER_GPU * sum((IMG_H // d) * (IMG_W // d) for d in (2, 4, 8)) * 2
+        msg = sum(per_op[n] for n in gdn)
+        tg = traffic.get("gdn")
+        roofs.append({"kernel": f"GDN/IGDN C=192 ({len(gdn)} launches/step)", "bound": "hbm",
+                      "achieved": px * 1536 / (msg * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": px * 1536 / (msg * 1e-3) / 1e9 / pk["hbm"],
+                      "traffic": tg["dram_bytes_per_step"] if tg else None, "traffic_source": tg["source"] if tg else None,
+                      "ms_per_step": msg})
+    hot_ms = sum(per_op.values())
+
+    # ---- e2e: RGBA batch from pinned host memory -> H2D -> forward -> x_hat D2H, all inside the timed region
+    e2e = None
+    if want_e2e:
+        out_host = torch.empty(BATCH_PER_GPU, 3, IMG_H, IMG_W).pin_memory()
+        stage = torch.empty_like(rgba)
+
+        def e2e_step():
+            stage.copy_(rgba_host, non_blocking=True)
+            x_hat = step(stage[:, :3], stage[:, 3:4])[0]
+            out_host.copy_(x_hat, non_blocking=True)
+
+        n = max(3, min(steps, 8))
+        with torch.no_grad():
+            ms_e2e, _, _ = timed_steps(e2e_step, n, 1, D)
+        e2e = {"value": BATCH_PER_GPU * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": rgba_host.numel() * 4,
+               "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e, "steps": n,
+               "how": "pinned host RGBA batch -> H2D -> AutoEncoder.forward (alpha pyramids, analysis, hyperprior, slice "
+                      "loop, synthesis, bpp) -> D2H of x_hat; copies inside the timed region"}
+    del net
+    torch.cuda.empty_cache()
+    return dict(value=value, ms_per_step=ms_per_step, per_op_ms=per_op, rooflines=roofs, e2e=e2e, clocks=clocks,
+                hot_path_ms_per_step=hot_ms, hot_path_share=hot_ms / ms_per_step, steps=steps)
+
+
+# ------------------------------------------------------------------------------------------------ hot path only
+def leg_hotpath(pkg, dev, rank, world, D, args, pk, steps):
+    """round 1's workload: the hot-path call sites of one forward, back to back, inputs resident (13.9 GB per step)"""
+    ops = to_device(build_workload(pkg, dev, BATCH_PER_GPU, seed0=BATCH_PER_GPU * rank), dev)
+    stream = torch.cuda.current_stream()
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            for op in ops:
+                run_op(pkg, op)
+        D.barrier()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(steps)]
+        for s in range(steps):
+            ev[s][0].record(stream)
+            for i, op in enumerate(ops):
+                run_op(pkg, op)
+                ev[s][i + 1].record(stream)
+        D.barrier()
+    ms = D.max_ms(ev[0][0].elapsed_time(ev[-1][-1])) / steps
+    per_op = [statistics.mean(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(steps)) for i in range(len(ops))]
+    big = [(op, t) for op, t in zip(ops, per_op) if op["kind"] == "attn" and op["C"] == 192]
+    fl = sum(op["kept"] * FLOPS_PER_WINDOW[(192, 8)] for op, _ in big)
+    tb = sum(t for _, t in big)
+    gd = [(op, t) for op, t in zip(ops, per_op) if op["kind"] == "gdn"]
+    gb = sum(op["x"].numel() // 192 * 1536 for op, _ in gd)
+    tg = sum(t for _, t in gd)
+    rnd_ms = sum(t for op, t in zip(ops, per_op) if op["kind"] == "round")
+    rnd_bytes = BATCH_PER_GPU * (491520 * (12 + 12) + 18432 * 8 + IMG_H * IMG_W * 8)
+    res = {"value": BATCH_PER_GPU * world / (ms * 1e-3), "unit": "images/s (hot-path call sites only)", "ms_per_step": ms,
+           "steps": steps, "gpu_launches": LAUNCHES_PER_HOTPATH_STEP * steps,
+           "per_op_ms": {op["name"]: t for op, t in zip(ops, per_op)},
+           "attention_8x8": {"tflops": fl / (tb * 1e-3) / 1e12, "frac_of_tensor_peak": fl / (tb * 1e-3) / 1e12 / pk["tensor"],
+                             "kept": f'{big[0][0]["kept"]}/{big[0][0]["windows"]}', "ms_per_op": tb / len(big)},
+           "gdn": {"gbs": gb / (tg * 1e-3) / 1e9, "frac_of_hbm_peak": gb / (tg * 1e-3) / 1e9 / pk["hbm"], "ms_per_step": tg},
+           "rounding": {"gbs": rnd_bytes / (rnd_ms * 1e-3) / 1e9, "frac_of_hbm_peak": rnd_bytes / (rnd_ms * 1e-3) / 1e9 / pk["hbm"],
+                        "ms_per_step": rnd_ms}}
+    del ops
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 4
+def leg_config4(pkg, dev, pk, iters=8):
+    """masked window-attention microbench: 8x8 windows, C = 192, 6 heads, 0 / 25 / 50 / 75 / 100 % of the windows masked
+    out, as blobs (4 x 4 windows, what transparent regions of real images look like) and as independent windows (the
+    worst case for the gather: no neighbour shares a sector).  L2 flushed between launches."""
+    flush = torch.zeros(128 * 1024 * 1024, device=dev)
+    torch.manual_seed(3)
+    m = pkg.MaskedWinBasedAttention(192, 6, 8, 4).to(dev)
+    x = torch.randn(16, 192, 128, 192, device=dev)
+    out = {}
+    with torch.no_grad():
+        for pattern, cell in (("blobs", 4), ("independent", 1)):
+            rows = {}
+            for masked in (0.0, 0.25, 0.5, 0.75, 1.0):
+                g = torch.Generator(device=dev).manual_seed(int(masked * 100) + cell)
+                keep = (torch.rand(16, 1, 16 // cell, 24 // cell, device=dev, generator=g) >= masked).float()
+                a = torch.roll(keep.repeat_interleave(8 * cell, 2).repeat_interleave(8 * cell, 3), (4, 4), (2, 3))
+                kept = int(keep.sum().item()) * cell * cell
+                for _ in range(2):
+                    m(x, a)
+                ts = []
+                for _ in range(iters):
+                    flush.add_(1.0)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); m(x, a); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = statistics.median(ts)
+                tf = kept * FLOPS_PER_WINDOW[(192, 8)] / (ms * 1e-3) / 1e12
+                rows[f"{int(masked * 100)}%"] = {"ms": ms, "kept_windows": kept, "tflops": tf, "frac_of_tensor_peak": tf / pk["tensor"],
+                                                 "hbm_gbs": 6144 * 98560 / (ms * 1e-3) / 1e9}
+            out[pattern] = rows
+    del flush
+    torch.cuda.empty_cache()
+    return {"workload": "C4: MaskedWinBasedAttention(192, 6 heads, ws 8, shift 4) on (16, 192, 128, 192) = 6144 windows, "
+                        "default (fp32-faithful) kernel, median of %d launches, L2 flushed" % iters, "masked_out": out}
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 5
+def leg_config5(pkg, dev, rank, world, D, steps=6, warmup=2):
+    """RGBA training step on 256x256 crops, 8 per GPU (batch 64 on 8 GPUs): forward + backward of the whole codec (our
+    backward kernels under the drop-in modules, cuDNN for the convolutions), rate-distortion loss as trainRGB.py:176-186,
+    bucketed NCCL gradient all-reduce + the reference's +-5 clip after the reduction, Adam step."""
+    crop, per_gpu = 256, 8
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(234)
+    net = pkg.RGBACodec().train().to(dev)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    ar = pkg.GradientAllReduce(params, clip_value=5.0)
+    g = torch.Generator().manual_seed(1000 + rank)
+    img = torch.rand(per_gpu, 3, crop, crop, generator=g).to(dev)
+    a = (torch.rand(per_gpu, 1, crop // 32, crop // 32, generator=g) > 0.35).float().repeat_interleave(32, 2).repeat_interleave(32, 3).to(dev)
+    img = img * a
+    ms_parts = {}
+
+    def fwd_bwd():
+        me = net.EncMakeMask(a)
+        x_hat, mse, bpp, _, _ = net(img, a, a, me[0], me[1], me[2], me[3])
+        loss = 4096 * mse + bpp
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+
+    def step():
+        fwd_bwd()
+        ar()
+        opt.step()
+
+    ms, _, _ = timed_steps(step, steps, warmup, D)
+    ms_fb, _, _ = timed_steps(fwd_bwd, max(2, steps // 2), 0, D)
+    ms_ar, _, _ = timed_steps(ar, max(2, steps // 2), 0, D)
+    nparam = sum(p.numel() for p in params)
+    res = {"workload": "C5: AutoEncoderRGB_Journal training step, 256x256 crops, 8 per GPU, fwd + bwd + bucketed gradient "
+                       "all-reduce (NCCL) + clip + Adam", "value": per_gpu * world / (ms * 1e-3), "unit": "crops/s",
+           "ms_per_step": ms, "fwd_bwd_ms": ms_fb, "grad_exchange_ms": ms_ar, "grad_bytes": 4 * nparam, "global_batch": per_gpu * world,
+           "steps": steps, "weight_gradient_gemms": "fp32" if not pkg._abi.WGRAD_TF32 else "tf32 products (opt-in)"}
+    if world > 1:
+        res["allreduce_busbw_gbs"] = 2 * (world - 1) / world * 4 * nparam / (ms_ar * 1e-3) / 1e9
+    del net, opt, ar
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs
-def cpu_hot_path_images_per_s(seconds_budget: float, seed0: int):
-    """the oracle port (oracle/ref_ops.py = the reference's algorithm on torch CPU, all host threads) over the
-    same call sites, ONE image per pass; returns (images/s, cores, sample description, passes)"""
-    from oracle import ref_ops as R
+def cpu_forward_images_per_s(seconds_budget: float, max_passes: int = 200):
+    """the oracle port (oracle/ref_model.py = the reference's AutoEncoder.forward restated on torch CPU, pinned on outputs
+    of the unmodified reference model; all host threads) on ONE synthetic 768x512 RGBA image per pass"""
+    from oracle import golden_cases as G
+    from oracle import ref_model as M
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    with open(os.path.join(ROOT, "tests", "golden", "model_rgb_keys.json")) as f:
+        table = json.load(f)
+    w = G.model_state(table, 234)
+    rgba = synthetic_rgba(1, seed0=0)
+    image, alpha = rgba[:, :3].contiguous(), rgba[:, 3:4].contiguous()
+    with torch.no_grad():
+        M.rgb_forward(w, image, alpha, alpha)             # warm-up
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < max_passes):
+            t0 = time.perf_counter()
+            M.rgb_forward(w, image, alpha, alpha)
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    sample = (f"{len(times)} passes of the full encode + decode forward on 1 synthetic 768x512 RGBA image "
+              f"(oracle/ref_model.py), torch CPU fp32, {cores} threads, median")
+    return 1.0 / med, cores, sample, med
 
-    class _P:  # parameter holder built with plain torch (no product code on this path)
-        pass
-    torch.manual_seed(234)
-    alpha = synthetic_alpha(1, seed0)
-    pyr = R.alpha_pyramid(alpha)
-    gen = torch.Generator().manual_seed(seed0 + 999)
-    sites = []
-    for name, C, heads, ws, shift, div, lvl in ATTN_SITES:
-        w = dict(qkv_w=torch.randn(3 * C, C, generator=gen) * C ** -0.5, qkv_b=torch.zeros(3 * C),
-                 proj_w=torch.randn(C, C, generator=gen) * C ** -0.5, proj_b=torch.zeros(C),
-                 table=torch.randn((2 * ws - 1) ** 2, heads, generator=gen) * 0.02)
-        x = torch.randn(1, C, IMG_H // div, IMG_W // div, generator=gen)
-        sites.append(("attn", x, pyr[lvl], w, heads, ws, shift))
+
+def cpu_config1_hot_path_ms():
+    """BASELINE config 1: AutoEncoderMask_Journal on one 768x512 alpha mask on CPU -- its hot path is the six GDN / IGDN
+    of models/AutoEncoderMask_Journal.py:153-176 (192 channels at 1/2, 1/4, 1/8 scale); oracle port, all host threads"""
+    from oracle import ref_ops as R
+    gen = torch.Generator().manual_seed(1)
     pedestal = 2.0 ** -36
-    for name, div, inverse in GDN_SITES:
-        beta = torch.sqrt(torch.ones(192) * (0.5 + torch.rand(192, generator=gen)) + pedestal)
-        gamma = torch.sqrt(0.1 * torch.eye(192) + torch.rand(192, 192, generator=gen) * 0.02 + pedestal)
-        sites.append(("gdn", torch.randn(1, 192, IMG_H // div, IMG_W // div, generator=gen), beta, gamma, inverse))
-    y = torch.randn(1, 80, 64, 96, generator=gen) * 4
-    mu = torch.randn(1, 80, 64, 96, generator=gen)
-    lrp = torch.randn(1, 80, 64, 96, generator=gen)
-    z = torch.randn(1, 192, 8, 12, generator=gen)
-    med = torch.zeros(1, 192, 1, 1)
-
-    def one_pass():
-        with torch.no_grad():
-            for s in sites:
-                if s[0] == "attn":
-                    _, x, a, w, heads, ws, shift = s
-                    R.masked_window_attention(x, a, w["qkv_w"], w["qkv_b"], w["proj_w"], w["proj_b"], w["table"],
-                                              heads, ws, shift)
-                else:
-                    _, x, beta, gamma, inverse = s
-                    R.gdn(x, beta, gamma, inverse=inverse)
-            R.quantize_levels(alpha)
-            R.quantize_offset(z, med)
-            for ys, ms, ls in zip(y.chunk(10, 1), mu.chunk(10, 1), lrp.chunk(10, 1)):
-                R.lrp_add(R.quantize_offset(ys, ms), ls)
-
-    one_pass()                                   # warm-up
-    times = []
-    t_start = time.perf_counter()
-    while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 200):
-        t0 = time.perf_counter()
-        one_pass()
-        times.append(time.perf_counter() - t0)
-    med_t = statistics.median(times)
-    sample = (f"{len(times)} passes of the hot path on 1 synthetic 768x512 image (4 attention + 6 GDN + rounding "
-              f"call sites), torch CPU fp32, {cores} threads, median")
-    return 1.0 / med_t, cores, sample, len(times), med_t
+    beta = torch.sqrt(torch.ones(192) + pedestal)
+    gamma = torch.sqrt(0.1 * torch.eye(192) + torch.rand(192, 192, generator=gen) * 0.01 + pedestal)
+    xs = [torch.randn(1, 192, IMG_H // d, IMG_W // d, generator=gen) for d in (2, 4, 8, 8, 4, 2)]
+    def one():
+        for i, x in enumerate(xs):
+            R.gdn(x, beta, gamma, inverse=i >= 3)
+    with torch.no_grad():
+        one()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); one(); ts.append(time.perf_counter() - t0)
+    return statistics.median(ts) * 1e3
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and
-    cannot travel to the GPU box, so this is the oracle port (kind 'port'), all host threads."""
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot travel
+    to the GPU box, so this is the oracle port (kind 'port'), all host threads; every step is ONE image (a bounded sample
+    of the batch-16 workload), at most K steps or ~150 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_budget = 4.0
-    ips, cores, sample, n, med_t = cpu_hot_path_images_per_s(min(per_step_budget * max(args.steps, 1), 120.0), seed0=0)
+    ips, cores, sample, med = cpu_forward_images_per_s(150.0, max_passes=max(args.steps, 3))
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": med_t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2-hotpath: hot-path call sites of one AutoEncoderRGB_Journal encode+decode forward, "
-                               "768x512, 1 image per CPU pass (bounded sample of the batch-16 workload)"},
+        "config": {"workload": "C2-forward: AutoEncoderRGB_Journal encode + decode forward, 768x512 RGBA, 1 image per CPU pass "
+                               "(bounded sample of the batch-16 workload)"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,263 +600,92 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--legs", default="forward,tf32,hotpath,config4,config5,config1",
+                    help="comma list of the extra legs to run next to the headline forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi clock sampler (profiling runs)")
-    ap.add_argument("--no-graph", action="store_true", help="skip the informational CUDA-graph replay leg")
-    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    legs = set(args.legs.split(","))
 
     import mwa_b200 as pkg
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = _env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    D = Dist(dev, world)
     pk = peaks()
 
-    # rank r holds images [16 r, 16 r + 16) of the global batch
-    ops = to_device(build_workload(pkg, dev, BATCH_PER_GPU, seed0=BATCH_PER_GPU * rank), dev, pin=not args.no_e2e)
-    algo = {"auto": pkg.ALGO_AUTO, "simt": pkg.ALGO_SIMT, "tcgen05": pkg.ALGO_TCGEN05}[args.algo]
-    for op in ops:
-        if "mod" in op:
-            op["mod"].algo = algo
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    stream = torch.cuda.current_stream()
     sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None      # needs ~0.5 s to start
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            for op in ops:
-                run_op(pkg, op)
-        barrier()
-        if sampler is not None:                               # keep the GPU under load until the sampler is live
-            t_dead = time.time() + 4.0
-            while not sampler.rows and time.time() < t_dead and sampler.proc is not None:
-                for op in ops:
-                    run_op(pkg, op)
-                torch.cuda.synchronize()
-            barrier() if world == 1 else None
-        barrier()
-        # ---- timed region: K steps, device time on the launching stream; per-op events feed the roofline
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(args.steps)]
-        t_wall0 = time.time()
-        for s in range(args.steps):
-            ev[s][0].record(stream)
-            for i, op in enumerate(ops):
-                run_op(pkg, op)
-                ev[s][i + 1].record(stream)
-        barrier()
-        t_wall1 = time.time()
-    total_ms = ev[0][0].elapsed_time(ev[-1][-1])
-    per_op_ms = [statistics.mean(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps))
-                 for i in range(len(ops))]
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = BATCH_PER_GPU * world / (ms_per_step * 1e-3)
-
-    # ---- rooflines (rank 0's kernels): algorithmic work / measured duration
-    roofs = []
-    attn_flops = sum(op["kept"] * FLOPS_PER_WINDOW[(op["C"], op["ws"])] for op in ops if op["kind"] == "attn")
-    attn_ms = sum(ms for op, ms in zip(ops, per_op_ms) if op["kind"] == "attn")
-    big = [(op, ms) for op, ms in zip(ops, per_op_ms) if op["kind"] == "attn" and op["C"] == 192]
-    big_flops = sum(op["kept"] * FLOPS_PER_WINDOW[(192, 8)] for op, _ in big)
-    big_ms = sum(ms for _, ms in big)
-    big_bytes = sum(op["windows"] * 98560 for op, _ in big)
-    roofs.append({"kernel": "masked window attention 8x8 C=192 (2 launches/step)", "bound": "tensor",
-                  "achieved": big_flops / (big_ms * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
-                  "frac": big_flops / (big_ms * 1e-3) / 1e12 / pk["tensor"], "traffic": None,
-                  "hbm_gbs": big_bytes / (big_ms * 1e-3) / 1e9, "ms_per_launch": big_ms / max(len(big), 1),
-                  "kept_windows_per_launch": big[0][0]["kept"], "windows_per_launch": big[0][0]["windows"]})
-    gdn = [(op, ms) for op, ms in zip(ops, per_op_ms) if op["kind"] == "gdn"]
-    gdn_bytes = sum(op["x"].numel() // 192 * 1536 for op, _ in gdn)
-    gdn_ms = sum(ms for _, ms in gdn)
-    roofs.append({"kernel": "GDN/IGDN C=192 (6 launches/step)", "bound": "hbm",
-                  "achieved": gdn_bytes / (gdn_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                  "frac": gdn_bytes / (gdn_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
-                  "ms_per_step": gdn_ms})
-    rnd_ms = sum(ms for op, ms in zip(ops, per_op_ms) if op["kind"] == "round")
-    rnd_bytes = BATCH_PER_GPU * (491520 * (12 + 12) + 18432 * 8 + IMG_H * IMG_W * 8)
-    roofs.append({"kernel": "latent rounding (22 launches/step)", "bound": "hbm",
-                  "achieved": rnd_bytes / (rnd_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                  "frac": rnd_bytes / (rnd_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "ms_per_step": rnd_ms})
-    dominant = roofs[1] if gdn_ms >= big_ms else roofs[0]
-    roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-    roofline["kernel"] = dominant["kernel"]
-    roofline["peak_source"] = pk["source"] + " (MEASURED_PEAKS.json burst figures)" if pk["source"] == "measured" \
-        else "fallback (B200_PROFILING.md)"
-
-    # DRAM traffic from the committed ncu --set full captures of this command (dram__bytes_read.sum + dram__bytes_write.sum):
-    # GDN: profiles/r01_gdn_tc_ncu_raw_final.csv (first capture: ..._v2.csv), the three shapes, x2 for IGDN, in GB per step like the algorithmic 6.34 GB
-    # behind `achieved`; attention: profiles/r01_attn_ws_ncu_raw_final.csv, main kernel of one 8x8 launch (3798 kept windows:
-    # 0.374 GB algorithmic for the kept windows; the reductions re-fetch `out` lines that left L2)
-    roofs[1]["traffic"] = 2 * (1.209517 + 1.149031 + 0.302230 + 0.243435 + 0.075690 + 0.019050)
-    roofs[1]["traffic_unit"] = "GB per step (6 launches), ncu capture under profiles/"
-    roofs[0]["traffic"] = 0.450246 + 0.167950
-    roofs[0]["traffic_unit"] = "GB per launch (main kernel), ncu capture under profiles/"
-    if dominant is roofs[1]:
-        roofline["traffic"] = roofs[1]["traffic"]
-        roofline["traffic_unit"] = roofs[1]["traffic_unit"]
-
-    # ---- informational: the same step replayed as ONE CUDA graph (the forward has no host synchronisation, unlike the
-    #      reference's three nonzero() calls per attention block), i.e. without per-launch CPU overhead
-    graph_info = None
-    if not args.no_graph:
+    fwd = leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, want_e2e=not args.no_e2e, sampler=sampler)
+    extra = {}
+    if "tf32" in legs:
+        t = leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=True, steps=max(3, min(args.steps, 10)), want_e2e=False)
+        extra["forward_tf32_convs"] = {"value": t["value"], "unit": UNIT, "ms_per_step": t["ms_per_step"], "steps": t["steps"],
+                                       "note": "same forward with torch.backends.cudnn.allow_tf32 = True (torch's default, i.e. what "
+                                               "the unmodified reference runs on a GPU); our kernels unchanged"}
+    if "hotpath" in legs:
+        extra["hotpath"] = leg_hotpath(pkg, dev, rank, world, D, args, pk, steps=max(5, min(args.steps, 50)))
+    if "config5" in legs:
         try:
-            with torch.no_grad():
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for op in ops:
-                        run_op(pkg, op)
-                torch.cuda.current_stream().wait_stream(side)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for op in ops:
-                        run_op(pkg, op)
-                for _ in range(3):
-                    g.replay()
-                barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(args.steps):
-                    g.replay()
-                e1.record()
-                barrier()
-            tg = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            graph_info = {"ms_per_step": float(tg.item()), "value": BATCH_PER_GPU * world / (float(tg.item()) * 1e-3),
-                          "unit": UNIT, "note": "whole step captured once, replayed `steps` times"}
-            del g
-        except Exception as exc:      # noqa: BLE001 -- informational leg only
-            graph_info = {"error": str(exc)[:200]}
-
-    # ---- e2e: same step through the nn.Module API with HOST buffers (pinned), copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(pkg, ops, dev, args, world)
+            extra["config5_training"] = leg_config5(pkg, dev, rank, world, D)
+        except Exception as exc:      # noqa: BLE001 -- an extra leg must not take the headline down
+            extra["config5_training"] = {"error": repr(exc)[:300]}
+    if "config4" in legs and rank == 0 and world == 1:
+        extra["config4_attention_microbench"] = leg_config4(pkg, dev, pk)
+    if "config1" in legs and rank == 0 and world == 1:
+        torch.manual_seed(1)
+        gd = [pkg.GDN(192, inverse=i >= 3).to(dev) for i in range(6)]
+        xs = [torch.randn(1, 192, IMG_H // d, IMG_W // d, device=dev) for d in (2, 4, 8, 8, 4, 2)]
+        with torch.no_grad():
+            ms1, _, _ = timed_steps(lambda: [m(x) for m, x in zip(gd, xs)], 20, 3, D)
+        extra["config1_mask_model_hot_path"] = {"workload": "C1: the six GDN / IGDN of AutoEncoderMask_Journal on one 768x512 "
+                                                            "alpha mask (batch 1)", "gpu_ms": ms1}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, cores, sample, n, med_t = cpu_hot_path_images_per_s(12.0, seed0=0)
-        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        ips, cores, sample, med = cpu_forward_images_per_s(12.0)
+        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "config1_hot_path_ms": cpu_config1_hot_path_ms()}
 
     if rank == 0:
+        roofs = fwd["rooflines"]
+        roofline = None
+        if roofs:
+            r0 = roofs[0]
+            roofline = {k: r0.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source")}
+            roofline["peak_source"] = (pk["source"] + " (MEASURED_PEAKS.json burst figures)") if pk["source"] == "measured" \
+                else "fallback (B200_PROFILING.md)"
+        gdn_r = next((r for r in roofs if r["kernel"].startswith("GDN")), None)
+        hot_launches = LAUNCHES_PER_FORWARD * fwd["steps"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 in/out; attention GEMMs f16 operands + f32 accumulate, "
-                                          "GDN contraction bf16x3 split + f32 accumulate (tcgen05 kernels); "
-                                          "f32 everywhere (SIMT kernels)",
+            "metric": METRIC, "value": fwd["value"], "unit": UNIT, "n_gpus": world, "steps": fwd["steps"],
+            "warmup": args.warmup, "ms_per_step": fwd["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32 (attention: fp16 hi+lo split operands, 3 tcgen05 passes, f32 accumulate = f32-faithful; 4x4 attention "
+                     "plain f32; GDN contraction bf16x3 split + f32 accumulate; convolutions cuDNN f32, TF32 off)",
             "data": "synthetic",
-            "config": {"workload": "C2-hotpath: the 4 masked window attention + 6 GDN/IGDN + 22 rounding launches of "
-                                   "one AutoEncoderRGB_Journal encode+decode forward, batch 16 x 768x512 per GPU, "
-                                   "random-init weights (seed 234), alpha = soft ellipse blobs",
-                       "images_per_gpu": BATCH_PER_GPU, "algo": args.algo,
-                       "l2": "per-step working set 13.9 GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "attention_windows_kept": {op["name"]: f'{op["kept"]}/{op["windows"]}' for op in ops
-                                                  if op["kind"] == "attn"}},
-            "roofline": roofline, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks, "cuda_graph": graph_info,
-            "per_op_ms": {op["name"]: ms for op, ms in zip(ops, per_op_ms)},
+            "config": {"workload": "C2-forward: AutoEncoderRGB_Journal encode + decode forward (alpha pyramids, analysis, "
+                                   "hyperprior, 10-slice loop, synthesis, bpp), batch 16 x 768x512 RGBA per GPU, random-init "
+                                   "weights (seed 234), alpha = soft ellipse blobs",
+                       "images_per_gpu": BATCH_PER_GPU,
+                       "l2": "activations of one step >> 126 MB L2 (1.2 GB per 1/2-scale tensor): inputs larger than L2, no flush",
+                       "hot_path_share_of_step": fwd["hot_path_share"]},
+            "roofline": roofline, "roofline_gdn": gdn_r, "rooflines": roofs, "cpu_baseline": cpu, "e2e": fwd["e2e"],
+            "gpu_launches": hot_launches, "gpu_launches_note": f"{LAUNCHES_PER_FORWARD} launches of this repo's kernels per forward "
+                                                                "(the convolutions are cuDNN launches and are not counted)",
+            "clocks": fwd["clocks"], "per_op_ms": fwd["per_op_ms"], "hot_path_ms_per_step": fwd["hot_path_ms_per_step"],
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_e2e(pkg, ops, dev, args, world):
-    """H2D of every input from pinned host memory -> module call -> D2H of every output, all inside the timed
-    region, three streams (copy-in / compute / copy-out) so that PCIe both ways overlaps the kernels."""
-    import torch.distributed as dist
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    s_cmp = torch.cuda.current_stream()
-    tens = [[k for k in op if k.startswith("h_")] for op in ops]
-    h2d = sum(op[k].numel() * 4 for op, ks in zip(ops, tens) for k in ks)
-    # two sets of device staging buffers (step s uses set s % 2, so the next step's copy-in overlaps this step's
-    # copy-out) and pinned result buffers
-    stages = [[{k[2:]: torch.empty_like(op[k[2:]]) for k in ks} for op, ks in zip(ops, tens)] for _ in range(2)]
-    with torch.no_grad():
-        outs0 = [run_op(pkg, op) for op in ops]
-    host_out = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs] for outs in outs0]
-    d2h = sum(o.numel() * 4 for outs in outs0 for o in outs)
-    del outs0
-    done = [None, None]                       # event: last kernel that read staging set p has finished
-    counter = [0]
-
-    def step():
-        p = counter[0] % 2
-        counter[0] += 1
-        stage = stages[p]
-        evs_in = []
-        with torch.cuda.stream(s_in):
-            if done[p] is not None:
-                s_in.wait_event(done[p])
-            for op, ks, st in zip(ops, tens, stage):
-                for k in ks:
-                    st[k[2:]].copy_(op[k], non_blocking=True)
-                e = torch.cuda.Event(); e.record(s_in); evs_in.append(e)
-        for op, st, e_in, ho in zip(ops, stage, evs_in, host_out):
-            s_cmp.wait_event(e_in)
-            outs = run_op(pkg, op, st)
-            e = torch.cuda.Event(); e.record(s_cmp)
-            s_out.wait_event(e)
-            with torch.cuda.stream(s_out):
-                for o, h in zip(outs, ho):
-                    h.copy_(o, non_blocking=True)
-                    o.record_stream(s_out)
-        done[p] = torch.cuda.Event()
-        done[p].record(s_cmp)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.no_grad():
-        for _ in range(2):
-            step()
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s_cmp)
-        s_in.wait_event(e0)
-        n = max(4, min(args.steps, 8))
-        for _ in range(n):
-            step()
-        s_cmp.wait_stream(s_out)
-        s_cmp.wait_stream(s_in)
-        e1.record(s_cmp)
-        sync_all()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / n
-    return {"value": BATCH_PER_GPU * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": n,
-            "how": "pinned host inputs -> H2D -> nn.Module forward (C ABI kernels) -> D2H of every output; "
-                   "copy-in / compute / copy-out streams overlapped, double-buffered device staging"}
+    D.close()
 
 
 if __name__ == "__main__":

@@ -32,6 +32,12 @@ void mwa_sp_set_timing_buffer(void* p);
 void mwa_sp_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,
                            const float* table, int C, int heads, int ws, float scale, uint8_t* blk, cudaStream_t st);
 
+int mwa_forward_small(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
+                      int heads, int ws, int shift, int32_t* kept_count, void* workspace, int64_t workspace_bytes,
+                      cudaStream_t st);                                                                       // mwa_small.cu
+bool mwa_small_supported(int C, int heads, int ws, int channels_last);
+int64_t mwa_small_workspace_bytes(int64_t nwin);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -308,8 +314,12 @@ void mwa_debug_set_timing_buffer(void* device_u64x4096) {
 int64_t mwa_workspace_bytes(int B, int H, int W, int ws) {
     if (B < 0 || H <= 0 || W <= 0 || ws <= 0) return MWA_ERR_INVALID;
     const int64_t nwin = int64_t(B) * (H / ws) * (W / ws);
-    const int64_t a = mwa_tc_workspace_bytes(nwin), b = mwa_sp_workspace_bytes(nwin);
-    return a > b ? a : b;
+    const int64_t a = mwa_tc_workspace_bytes(nwin), b = mwa_sp_workspace_bytes(nwin), c = mwa_small_workspace_bytes(nwin);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+
+int mwa_fast_path_needs_nchw(int C, int heads, int ws) {
+    return (mwa_sp_supported(C, heads, ws, 8, 8, 0) || mwa_small_supported(C, heads, ws, 0)) ? 1 : 0;
 }
 
 int mwa_forward(const float* x, const float* alpha, float* out, const void* params, int B, int C, int H, int W,
@@ -323,12 +333,22 @@ int mwa_forward(const float* x, const float* alpha, float* out, const void* para
     if (B == 0) return MWA_OK;                              // empty batch: x / out may be null
     if (!x || !out || !params) return MWA_ERR_INVALID;
     const bool tc_ok = mwa_tc_supported(C, heads, ws, H, W, shift, channels_last);
-    // split-precision tcgen05 kernel (meets the fp32 contract on every element): the default wherever it covers the shape
+    // MWA_ALGO_AUTO is fp32-faithful on every shape (the reference's arithmetic is fp32 end to end):
+    //   8x8 windows, C = 192: split-precision tcgen05 kernel (every operand fp16 hi + lo, three passes);
+    //   4x4 windows, C = 80:  plain fp32 kernel for small windows;
+    //   anything else:        the general fp32 SIMT kernel.
+    // The single-pass fp16 tensor-core kernels (faster, ~1e-4 .. 3e-4 absolute error at random init) are opt-in:
+    // MWA_ALGO_TCGEN05_FP16 / MWA_ALGO_TCGEN05_V1, and MWA_ALGO_TCGEN05 where no split-precision kernel covers the shape.
     if ((algo == MWA_ALGO_AUTO || algo == MWA_ALGO_TCGEN05) && mwa_sp_supported(C, heads, ws, H, W, channels_last)) {
         if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
         return mwa_forward_sp(x, alpha, out, params, B, C, H, W, heads, ws, shift, kept_count, workspace, workspace_bytes, st);
     }
-    if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || algo == MWA_ALGO_TCGEN05_FP16 || (algo == MWA_ALGO_AUTO && tc_ok)) {
+    if (algo == MWA_ALGO_AUTO && mwa_small_supported(C, heads, ws, channels_last)) {
+        if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
+        return mwa_forward_small(x, alpha, out, params, B, C, H, W, heads, ws, shift, kept_count, workspace, workspace_bytes,
+                                 st);
+    }
+    if (algo == MWA_ALGO_TCGEN05 || algo == MWA_ALGO_TCGEN05_V1 || algo == MWA_ALGO_TCGEN05_FP16) {
         if (!tc_ok) return MWA_ERR_UNSUPPORTED;
         if (!aligned16(x) || !aligned16(out)) return MWA_ERR_ALIGNMENT;
         // warp-specialised pipeline where it covers the layout, else the phase-serial v1 kernel

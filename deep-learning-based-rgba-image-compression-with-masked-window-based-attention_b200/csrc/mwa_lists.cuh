@@ -1,0 +1,132 @@
+// Kept / dropped window lists and the copy of the dropped windows, shared by the kernels that work from an ordered list
+// of kept windows (csrc/mwa_sp.cu: 8x8 windows on tcgen05; csrc/mwa_small.cu: 4x4 windows in fp32).
+// Reference semantics: layers/masked_win_attention.py:35-47 (keep predicate), :237-249 (dropped windows contribute zeros,
+// i.e. the block is the identity there).
+#pragma once
+#include "mwa_tc_shared.cuh"
+
+namespace b200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ scan / compaction
+struct ListWs {             // workspace layout: counts (kept, dropped), keep flags, kept list, dropped list
+    int64_t count, flags, list, dlist, total;
+    __host__ __device__ explicit ListWs(int64_t nwin) {
+        count = 0;
+        flags = 16;
+        list = align_up(flags + nwin, 16);
+        dlist = align_up(list + 4 * (nwin + 16), 16);
+        total = align_up(dlist + 4 * (nwin + 16), 256);
+    }
+};
+
+// single block: ordered lists of kept and of dropped windows (flags == nullptr: every window kept)
+__global__ void __launch_bounds__(1024)
+mwa_list_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __restrict__ list, int32_t* __restrict__ dlist,
+                      int32_t* __restrict__ count) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (nwin + 1023) / 1024;
+    const int beg = min(tid * per, nwin), end = min(beg + per, nwin);
+    int n = 0;
+    for (int i = beg; i < end; ++i) n += flags ? flags[i] : 1;
+    part[tid] = n;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int pos = part[tid] - n, dpos = beg - pos;
+    for (int i = beg; i < end; ++i) {
+        if (!flags || flags[i]) list[pos++] = i;
+        else dlist[dpos++] = i;
+    }
+    if (tid == 1023) {
+        count[0] = part[1023];
+        count[1] = nwin - part[1023];
+    }
+}
+
+// out = x on the dropped windows (the block is the identity there, layers/masked_win_attention.py:249 adds zeros).
+// Work item = (SEGMENT of up to 8 horizontally adjacent dropped windows, channel part), one warp each: with
+// shift = ws / 2 a window row sits at half a row's offset (8x8 windows: 32 bytes at a 16-byte offset, i.e. it straddles
+// two 32-byte sectors) -- copied window by window every sector would be fetched and written twice (measured 1.7 TB/s);
+// a segment is one contiguous row piece of 4 * WS * len bytes per (channel, row), copied as consecutive vectors.
+// Transparent regions of real alpha planes are blobs, so segments are long; they are cut at multiples of 8 windows so
+// that a fully transparent row still spreads over many warps.  A dropped window starts a segment if wx % 8 == 0 or its
+// left neighbour is kept.
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> { using type = float4; };
+template <>
+struct VecT<2> { using type = float2; };
+
+template <int WS, int VEC>
+__device__ __forceinline__ void copy_segment(const float* __restrict__ xs, float* __restrict__ os, const Geom& g, int wy, int wx,
+                                             int len, int cpp, int64_t hw, int lane) {
+    using V = typename VecT<VEC>::type;
+    constexpr int U = 8;
+    // positions of a (channel, segment): WS rows x (WS / VEC) * len vectors; short segments take several channels per sweep
+    const int per_row = (WS / VEC) * len, npos = WS * per_row;
+    const int csplit = (npos <= 8) ? 4 : (npos <= 16) ? 2 : 1, lanes = 32 / csplit;
+    const int csub = lane / lanes;
+    for (int pos = lane % lanes; pos < npos; pos += lanes) {
+        const int r = pos / per_row, k = pos - r * per_row;
+        int py = wy * WS + r + g.shift, px = wx * WS + g.shift + VEC * k;
+        if (py >= g.H) py -= g.H;
+        if (px >= g.W) px -= g.W;
+        const int64_t off = int64_t(py) * g.W + px + int64_t(csub) * hw;
+        for (int c = 0; c < cpp; c += csplit * U) {
+            V v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c + csplit * u + csub < cpp) v[u] = __ldcs(reinterpret_cast<const V*>(xs + off + int64_t(c + csplit * u) * hw));
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c + csplit * u + csub < cpp) __stcs(reinterpret_cast<V*>(os + off + int64_t(c + csplit * u) * hw), v[u]);
+        }
+    }
+}
+
+template <int WS>
+__global__ void __launch_bounds__(256)
+mwa_copy_dropped_kernel(const float* __restrict__ x, float* __restrict__ out, Geom g, int C,
+                        const uint8_t* __restrict__ flags, const int32_t* __restrict__ dlist,
+                        const int32_t* __restrict__ count) {
+    constexpr int PARTS = 8, SEG = 8;
+    const int n = count[1];
+    const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int64_t hw = int64_t(g.H) * g.W;
+    const int cpp = (C + PARTS - 1) / PARTS;
+    for (int i = gw; i < n * PARTS; i += nw) {
+        const int win = dlist[i / PARTS];
+        int b, wy, wx;
+        window_coords(g, win, b, wy, wx);
+        if (wx % SEG != 0 && !flags[win - 1]) continue;      // not the head of its segment
+        int len = 1;
+        while ((wx + len) % SEG != 0 && wx + len < g.nwx && !flags[win + len]) ++len;
+        const int c0 = (i % PARTS) * cpp;
+        const int nc = min(cpp, C - c0);
+        if (nc <= 0) continue;
+        const float* xs = x + (int64_t(b) * C + c0) * hw;
+        float* os = out + (int64_t(b) * C + c0) * hw;
+        if (WS % 4 == 0 && g.shift % 4 == 0 && g.W % 4 == 0) {
+            copy_segment<WS, 4>(xs, os, g, wy, wx, len, nc, hw, lane);
+        } else if (g.shift % 2 == 0 && g.W % 2 == 0) {
+            copy_segment<WS, 2>(xs, os, g, wy, wx, len, nc, hw, lane);
+        } else {
+            for (int t = lane; t < WS * WS * len; t += 32) {
+                int py, px;
+                token_pixel<WS>(g, wy, wx + t / (WS * WS), t % (WS * WS), py, px);
+                const int64_t off = int64_t(py) * g.W + px;
+                for (int c = 0; c < nc; ++c) os[off + c * hw] = __ldg(xs + off + c * hw);
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace b200

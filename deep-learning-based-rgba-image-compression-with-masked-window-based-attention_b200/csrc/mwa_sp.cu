@@ -29,25 +29,20 @@
 //
 // Roles (24 warps, setmaxnreg): 0 MMA issuer | 1 weight feeder (two rings of bulk copies) | 2-3 TMA gather issuers
 // (one per window slot, [16 ch][8][8] boxes of x) | 4-11 x converter + epilogue (fp32 boxes -> X_hi in shared memory,
-// X_lo kept in registers until the previous tile's last QKV MMA has retired, then stored to TMEM; epilogue interleaved
-// with the conversion of the next tile) | 12-19 softmax (two warps per lane quarter) | 20-23 QKV drain + normalisation.
+// X_lo kept in registers until the previous tile's last QKV MMA has retired, then stored to TMEM; epilogue of the
+// previous tile first) | 12-19 softmax (two warps per lane quarter) | 20-23 QKV drain + normalisation.
 // Dropped windows are copied through by a separate small kernel (only the dropped ones).
 #include <cstring>
 #include <cuda.h>          // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "mwa_tc_shared.cuh"
+#include "mwa_lists.cuh"
 
 // bring-up switches (tools/build_variants.py)
 #ifndef MWA_SP_NO_TMA
 #define MWA_SP_NO_TMA 0          // 1: every window through the LSU gather
 #endif
-#ifndef MWA_SP_FUSE_BLOCKING
-#define MWA_SP_FUSE_BLOCKING 0   // 1: one epilogue step per box, blocking box waits (no polling)
-#endif
 #ifndef MWA_SP_EPI_NOSTORE
 #define MWA_SP_EPI_NOSTORE 0     // 1: (debug) epilogue without its global stores
-#endif
-#ifndef MWA_SP_NO_FUSE
-#define MWA_SP_NO_FUSE 0         // 1: epilogue first, then the conversion of the next tile (no interleaving)
 #endif
 
 namespace b200 {
@@ -57,8 +52,8 @@ constexpr int kSpWarps = 24;
 constexpr int kSpThreads = kSpWarps * 32;
 constexpr int kSpMma = 0, kSpFeed = 1, kSpTma0 = 2;
 constexpr int kSpPe0 = 4, kSpNumPe = 8, kSpSm0 = 12, kSpNumSm = 8, kSpDr0 = 20;
-// register pool of the CTA = 24 warps x 80 (launch bound); per SM sub-partition 40 + 2 x 96 + 2 x 80 + 88 = 480 = 6 x 80
-constexpr int kSpRegsCtl = 40, kSpRegsPe = 96, kSpRegsSm = 80, kSpRegsDr = 88;
+// register pool of the CTA = 24 warps x 80 (launch bound); per SM sub-partition 56 + 2 x 88 + 2 x 80 + 88 = 480 = 6 x 80
+constexpr int kSpRegsCtl = 56, kSpRegsPe = 88, kSpRegsSm = 80, kSpRegsDr = 88;
 constexpr float kNegMaskL2 = kNegMask * kLog2e;
 
 template <int HEADS_>
@@ -154,89 +149,6 @@ __global__ void mwa_sp_prepare_kernel(const float* __restrict__ qkv_w, const flo
         reinterpret_cast<float*>(out + SpParams<CF>::tbl)[e] = table[(e % CF::TBL) * H + e / CF::TBL] * kLog2e;
     for (int n = tid; n < 16; n += nth)
         *reinterpret_cast<uint16_t*>(out + SpParams<CF>::i16 + sw128_offset(n, n)) = f16_bits(1.0f);
-}
-
-// ------------------------------------------------------------------------------------------------ scan / compaction
-struct SpWs {             // workspace layout: counts (kept, dropped), keep flags, kept list, dropped list
-    int64_t count, flags, list, dlist, total;
-    __host__ __device__ explicit SpWs(int64_t nwin) {
-        count = 0;
-        flags = 16;
-        list = align_up(flags + nwin, 16);
-        dlist = align_up(list + 4 * (nwin + 16), 16);
-        total = align_up(dlist + 4 * (nwin + 16), 256);
-    }
-};
-
-// single block: ordered lists of kept and of dropped windows (flags == nullptr: every window kept)
-__global__ void __launch_bounds__(1024)
-mwa_sp_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __restrict__ list, int32_t* __restrict__ dlist,
-                      int32_t* __restrict__ count) {
-    __shared__ int part[1024];
-    const int tid = threadIdx.x;
-    const int per = (nwin + 1023) / 1024;
-    const int beg = min(tid * per, nwin), end = min(beg + per, nwin);
-    int n = 0;
-    for (int i = beg; i < end; ++i) n += flags ? flags[i] : 1;
-    part[tid] = n;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = (tid >= o) ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    int pos = part[tid] - n, dpos = beg - pos;
-    for (int i = beg; i < end; ++i) {
-        if (!flags || flags[i]) list[pos++] = i;
-        else dlist[dpos++] = i;
-    }
-    if (tid == 1023) {
-        count[0] = part[1023];
-        count[1] = nwin - part[1023];
-    }
-}
-
-// out = x on the dropped windows (the block is the identity there, layers/masked_win_attention.py:249 adds zeros).
-// One warp per (window, 48-channel part): a warp iteration moves 2 channels x 8 rows x 8 px as float4s.
-__global__ void __launch_bounds__(256)
-mwa_sp_copy_dropped_kernel(const float* __restrict__ x, float* __restrict__ out, Geom g, int C,
-                           const int32_t* __restrict__ dlist, const int32_t* __restrict__ count) {
-    constexpr int WS = 8, PARTS = 4;
-    const int n = count[1];
-    const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
-    const int64_t hw = int64_t(g.H) * g.W;
-    const int cpp = C / PARTS;
-    const bool vec = (g.shift % 4 == 0) && (g.W % 4 == 0);
-    for (int i = gw; i < n * PARTS; i += nw) {
-        int b, wy, wx;
-        window_coords(g, dlist[i / PARTS], b, wy, wx);
-        const int c0 = (i % PARTS) * cpp;
-        if (vec) {
-            const int ty = (lane & 15) >> 1, tx = (lane & 1) * 4;
-            int py = wy * WS + ty + g.shift, px = wx * WS + tx + g.shift;
-            if (py >= g.H) py -= g.H;
-            if (px >= g.W) px -= g.W;
-            const int64_t off = (int64_t(b) * C + c0 + (lane >> 4)) * hw + int64_t(py) * g.W + px;
-            constexpr int U = 8;
-            for (int c = 0; c < cpp; c += 2 * U) {
-                float4 v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (c + 2 * u < cpp) v[u] = __ldcs(reinterpret_cast<const float4*>(x + off + int64_t(c + 2 * u) * hw));
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (c + 2 * u < cpp) __stcs(reinterpret_cast<float4*>(out + off + int64_t(c + 2 * u) * hw), v[u]);
-            }
-        } else {
-            for (int t = lane; t < 64; t += 32) {
-                int py, px;
-                token_pixel<WS>(g, wy, wx, t, py, px);
-                const int64_t off = (int64_t(b) * C + c0) * hw + int64_t(py) * g.W + px;
-                for (int c = 0; c < cpp; ++c) out[off + c * hw] = __ldg(x + off + c * hw);
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -373,42 +285,49 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                            d_i = umma_desc_k_sw128(sb + CF::oI16);
             uint32_t nq = 0, np = 0;                       // weight ring elements consumed from the two rings
             int next_q = 0;                                // next head whose QKV MMAs are to be issued
-            auto issue_qkv = [&](int q) {
+            // QKV(q) in three K blocks (so that other MMAs can be issued in between: the weight ring holds two K blocks and
+            // refills in ~1 k cycles, a head's six elements back to back would outrun it)
+            auto qkv_block = [&](int q, int kb) {
                 const int it = q / H, h = q - it * H, xb = it & 1;
-                if (h == 0) {
-                    mbar_wait(bars + CF::bXhFull + xb, (it >> 1) & 1);
-                    mbar_wait(bars + CF::bXlFull, it & 1);
-                }
-                if (q > 0) mbar_wait(bars + CF::bDqEmpty, (q - 1) & 1);
-                tc_fence_after_sync();
-#pragma unroll
-                for (int kb = 0; kb < CF::KB; ++kb) {
-                    const uint64_t a0 = d_x + ((xb * 49152 + kb * 16384) >> 4);
-                    uint32_t slot = nq % CF::kWqSlots;
-                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W hi of the K block
-                    tc_fence_after_sync();
-                    uint64_t b0 = d_wq + ((slot * CF::kWqElem) >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, (kb | ks) != 0);
-                        umma_f16_ts(tm + CF::tDq, tm + CF::tXl + (kb * 4 + ks) * 8, b0 + ks * 2, id_q, 1);
+                if (kb == 0) {
+                    if (h == 0) {
+                        mbar_wait(bars + CF::bXhFull + xb, (it >> 1) & 1);
+                        mbar_wait(bars + CF::bXlFull, it & 1);
                     }
-                    umma_commit(bars + CF::bWqEmpty + slot);
-                    ++nq;
-                    slot = nq % CF::kWqSlots;
-                    mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W lo
+                    if (q > 0) mbar_wait(bars + CF::bDqEmpty, (q - 1) & 1);
                     tc_fence_after_sync();
-                    b0 = d_wq + ((slot * CF::kWqElem) >> 4);
+                }
+                const uint64_t a0 = d_x + ((xb * 49152 + kb * 16384) >> 4);
+                uint32_t slot = nq % CF::kWqSlots;
+                mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W hi of the K block
+                tc_fence_after_sync();
+                uint64_t b0 = d_wq + ((slot * CF::kWqElem) >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, 1);
-                    umma_commit(bars + CF::bWqEmpty + slot);
-                    ++nq;
+                for (int ks = 0; ks < 4; ++ks) {
+                    umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, (kb | ks) != 0);
+                    umma_f16_ts(tm + CF::tDq, tm + CF::tXl + (kb * 4 + ks) * 8, b0 + ks * 2, id_q, 1);
                 }
-                umma_commit(bars + CF::bDqFull);
-                if (h == H - 1) {
-                    umma_commit(bars + CF::bXhEmpty + xb);
-                    umma_commit(bars + CF::bXlEmpty);
+                umma_commit(bars + CF::bWqEmpty + slot);
+                ++nq;
+                slot = nq % CF::kWqSlots;
+                mbar_wait(bars + CF::bWqFull + slot, (nq / CF::kWqSlots) & 1);      // W lo
+                tc_fence_after_sync();
+                b0 = d_wq + ((slot * CF::kWqElem) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16_ss(tm + CF::tDq, a0 + ks * 2, b0 + ks * 2, id_q, 1);
+                umma_commit(bars + CF::bWqEmpty + slot);
+                ++nq;
+                if (kb == CF::KB - 1) {
+                    umma_commit(bars + CF::bDqFull);
+                    if (h == H - 1) {
+                        umma_commit(bars + CF::bXhEmpty + xb);
+                        umma_commit(bars + CF::bXlEmpty);
+                    }
                 }
+            };
+            auto issue_qkv = [&](int q) {
+#pragma unroll
+                for (int kb = 0; kb < CF::KB; ++kb) qkv_block(q, kb);
             };
             // S(G): rows 0-63 (window slot 0) against the keys of slot 0, rows 64-127 against those of slot 1: two MMAs per
             // k step with the other half of the output lanes disabled; passes q_hi k_hi + q_lo k_hi + q_hi k_lo
@@ -449,36 +368,35 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 umma_commit(bars + CF::bOFull);
                 umma_commit(bars + CF::bVFree);
             };
-            auto issue_proj = [&](int G) {
+            auto proj_half = [&](int G, int nh) {
                 const int it = G / H, h = G - it * H, xb = it & 1;
-                mbar_wait(bars + CF::bOAReady, G & 1);
-                if (h == 0) {
-                    // the accumulator starts as the residual x itself: D[:, 16j .. 16j+15] = X_hi(j) I + X_lo(j) I
-                    if (it > 0) mbar_wait(bars + CF::bPjEmpty, (it - 1) & 1);
-                    tc_fence_after_sync();
+                if (nh == 0) {
+                    mbar_wait(bars + CF::bOAReady, G & 1);
+                    if (h == 0) {
+                        // the accumulator starts as the residual x itself: D[:, 16j .. 16j+15] = X_hi(j) I + X_lo(j) I
+                        if (it > 0) mbar_wait(bars + CF::bPjEmpty, (it - 1) & 1);
+                        tc_fence_after_sync();
 #pragma unroll
-                    for (int ks = 0; ks < CF::KSTEPS; ++ks) {
-                        umma_f16_ss(tm + CF::tPj + ks * 16, d_x + ((xb * 49152 + (ks >> 2) * 16384) >> 4) + (ks & 3) * 2, d_i, id_r, 0);
-                        umma_f16_ts(tm + CF::tPj + ks * 16, tm + CF::tXl + ks * 8, d_i, id_r, 1);
+                        for (int ks = 0; ks < CF::KSTEPS; ++ks) {
+                            umma_f16_ss(tm + CF::tPj + ks * 16, d_x + ((xb * 49152 + (ks >> 2) * 16384) >> 4) + (ks & 3) * 2, d_i, id_r, 0);
+                            umma_f16_ts(tm + CF::tPj + ks * 16, tm + CF::tXl + ks * 8, d_i, id_r, 1);
+                        }
                     }
+                    tc_fence_after_sync();
                 }
+                const uint32_t slot = np & 1;
+                mbar_wait(bars + CF::bWpFull + slot, (np >> 1) & 1);
                 tc_fence_after_sync();
+                const uint64_t b0 = d_wp + ((slot * CF::kWpChunk) >> 4);
 #pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
-                    const uint32_t slot = np & 1;
-                    mbar_wait(bars + CF::bWpFull + slot, (np >> 1) & 1);
-                    tc_fence_after_sync();
-                    const uint64_t b0 = d_wp + ((slot * CF::kWpChunk) >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + ks * 2, id_p, 1);
-                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + 16 + ks * 8, b0 + ks * 2, id_p, 1);
-                        umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + 4 + ks * 2, id_p, 1);
-                    }
-                    umma_commit(bars + CF::bWpEmpty + slot);
-                    ++np;
+                for (int ks = 0; ks < 2; ++ks) {
+                    umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + ks * 2, id_p, 1);
+                    umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + 16 + ks * 8, b0 + ks * 2, id_p, 1);
+                    umma_f16_ts(tm + CF::tPj + nh * 96, tm + CF::tOA + ks * 8, b0 + 4 + ks * 2, id_p, 1);
                 }
-                if (h == H - 1) umma_commit(bars + CF::bPjFull);
+                umma_commit(bars + CF::bWpEmpty + slot);
+                ++np;
+                if (nh == 1 && h == H - 1) umma_commit(bars + CF::bPjFull);
             };
             if (total > 0) {
                 issue_qkv(next_q++);
@@ -490,10 +408,18 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tick(0);                                                         // 0: wait P, V + P V issue
                 if (G + 1 < total) issue_s(G + 1);           // right behind P V(G): overwrites P(G) in issue order
                 tick(1);                                                         // 1: wait Q, K + S issue
-                if (next_q < total) issue_qkv(next_q++);     // QKV(G + 2) and proj(G) fill the tensor pipe during softmax(G + 1)
-                tick(2);                                                         // 2: QKV(G + 2) issue incl. its waits
-                issue_proj(G);
-                tick(3);                                                         // 3: wait O operand (+ accumulator) + proj issue
+                // QKV(G + 2) and proj(G) fill the tensor pipe during softmax(G + 1), interleaved K block by K block
+                const bool has_q = next_q < total;
+                const int q = next_q;
+                if (has_q) qkv_block(q, 0);
+                if (has_q) qkv_block(q, 1);
+                proj_half(G, 0);                             // its operand (O(G) normalised) is ~1 k cycles behind P V(G)
+                if (has_q) {
+                    qkv_block(q, 2);
+                    ++next_q;
+                }
+                proj_half(G, 1);
+                tick(2);                                                         // 2: QKV(G + 2) + proj(G) issue incl. their waits
             }
         } else if (warp == kSpFeed && elect_one()) {
             // weight feeder: two rings of bulk copies, each in exactly the order the issuer consumes it
@@ -612,11 +538,6 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             // cycles late), and the TMA would overwrite the box under them.  Seen on the hardware as stale tail channels.
             if (release != nullptr) mbar_arrive(release);
         };
-        auto box_ready = [&](const Win& wi, int jj) -> bool {
-            if (!wi.staged) return true;
-            const uint32_t nb = stage_n + jj, slot = nb % 3;
-            return __all_sync(0xffffffffu, mbar_test_wait(bars + CF::bStFull + wslot * 3 + slot, (nb / 3) & 1));
-        };
         auto publish_lo = [&](int it_next) {                 // X_lo of tile it_next -> TMEM (columns = channel pairs)
 #pragma unroll
             for (int i = 0; i < 6; ++i) tmem_st_x8(tm + CF::tXl + lane_addr + (half * 6 + i) * 8, lo[i]);
@@ -634,59 +555,59 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             mbar_arrive(bars + CF::bXhFull + 0);
             publish_lo(0);
         }
-        // iteration `it` runs while tile `it` is computed: epilogue of tile it - 1 interleaved with the conversion of
-        // tile it + 1.  The box index is a compile-time constant (the lo parts live in registers), the epilogue step is
-        // not: one epilogue step per box, plus as many as fit while a box has not landed yet.
+        // iteration `it` runs while tile `it` is computed: epilogue of tile it - 1, then the conversion of tile it + 1.
+        // The issuer needs the projection accumulator back one head period after the tile's last projection (for the
+        // residual MMAs of the next tile), so the epilogue hands it back as early as it can: the first 48 of a thread's
+        // 96 columns go load -> store in steps of 8, the other 48 are read into registers in one go, the accumulator is
+        // released, and only then are they stored.  (Interleaving the epilogue with the next conversion, as an earlier
+        // version did, held the accumulator for ~16 k cycles and stalled the issuer at every tile boundary.)
         for (int it = 0; it <= my_tiles; ++it) {
             const bool do_epi = it >= 1, do_gather = it + 1 < my_tiles;
             if (!do_epi && !do_gather) continue;
-            Win wn{false, false, 0}, wp{false, false, 0};
             const int xb = (it + 1) & 1;
-            if (do_gather) {
-                wn = win_of(tile_of(it + 1));
-                if (it >= 1) mbar_wait(bars + CF::bXhEmpty + xb, ((it - 1) >> 1) & 1);
-            }
-            float* orow = out;
-            int estep = 12;
             if (do_epi) {
-                wp = win_of(tile_of(it - 1));
-                orow = out + wp.base + int64_t(half * 96) * hw;
-                tick(8);                                                         // 8: tile set-up + wait X_hi buffer free
+                const Win wp = win_of(tile_of(it - 1));
+                float* orow = out + wp.base + int64_t(half * 96) * hw;
+                const float* bp = s_bpf + half * 96;
+                const bool store = wp.valid && !MWA_SP_EPI_NOSTORE;
+                tick(8);                                                         // 8: tile set-up
                 mbar_wait(bars + CF::bPjFull, (it - 1) & 1);
                 tc_fence_after_sync();
                 tick(9);                                                         // 9: wait projection complete
-                estep = 0;
-            }
-            auto epi_step = [&]() {
-                uint32_t acc[8];
-                tmem_ld_x8(tm + CF::tPj + lane_addr + half * 96 + estep * 8, acc);
+#pragma unroll
+                for (int st = 0; st < 6; ++st) {
+                    uint32_t acc[8];
+                    tmem_ld_x8(tm + CF::tPj + lane_addr + half * 96 + st * 8, acc);
+                    tmem_wait_ld();
+                    if (store) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) orow[int64_t(st * 8 + j) * hw] = __uint_as_float(acc[j]) + bp[st * 8 + j];
+                    }
+                }
+                uint32_t rest[6][8];
+#pragma unroll
+                for (int st = 0; st < 6; ++st) tmem_ld_x8(tm + CF::tPj + lane_addr + half * 96 + 48 + st * 8, rest[st]);
                 tmem_wait_ld();
-                if (estep == 11) {                           // last TMEM read of the tile: hand the accumulator back
-                    tc_fence_before_sync();
-                    mbar_arrive(bars + CF::bPjEmpty);
-                    tick(13);                                                    // 13: (marker) accumulator released
-                }
-                if (wp.valid && !MWA_SP_EPI_NOSTORE) {
-                    float* o = orow + int64_t(estep * 8) * hw;
-                    const float* bp = s_bpf + half * 96 + estep * 8;
+                tc_fence_before_sync();
+                mbar_arrive(bars + CF::bPjEmpty);            // every column has been read: the accumulator goes back
+                tick(13);                                                        // 13: (marker) accumulator released
+                if (store) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[int64_t(j) * hw] = __uint_as_float(acc[j]) + bp[j];
-                }
-                ++estep;
-            };
-            if (do_gather) {
+                    for (int st = 0; st < 6; ++st)
 #pragma unroll
-                for (int jj = 0; jj < 12; ++jj) {
-                    do {
-                        if (estep < 12) epi_step();
-                    } while (!MWA_SP_FUSE_BLOCKING && estep < 12 && (MWA_SP_NO_FUSE || !box_ready(wn, jj)));
-                    gather_box(wn, jj, xb);
+                        for (int j = 0; j < 8; ++j)
+                            orow[int64_t(48 + st * 8 + j) * hw] = __uint_as_float(rest[st][j]) + bp[48 + st * 8 + j];
                 }
             }
-            while (estep < 12) epi_step();
-            tick(10);                                                            // 10: epilogue + conversion interleaved
             if (do_gather) {
+                const Win wn = win_of(tile_of(it + 1));
+                if (it >= 1) mbar_wait(bars + CF::bXhEmpty + xb, ((it - 1) >> 1) & 1);
+#pragma unroll
+                for (int jj = 0; jj < 12; ++jj) gather_box(wn, jj, xb);
                 if (wn.staged) stage_n += 12;
+            }
+            tick(10);                                                            // 10: epilogue stores + conversion
+            if (do_gather) {
                 fence_proxy_async_smem();
                 mbar_arrive(bars + CF::bXhFull + xb);
                 mbar_wait(bars + CF::bXlEmpty, it & 1);      // the correction MMAs of tile `it` have read X_lo
@@ -783,8 +704,9 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
     } else {
         // =========================================================================================== QKV drain + normalisation
         // thread = token.  Iteration n: q, k, v of head n out of D_qkv (fp16 hi / lo: q -> TMEM, k and v -> shared memory),
-        // then O(n - 1) / rowsum -> fp16 hi / lo over O in TMEM (the projection's A operand).  The v rows of head n and the
-        // normalisation of head n - 1 both wait for P V(n - 1), so the two jobs never wait on each other.
+        // O(n - 1) / rowsum -> fp16 hi / lo over O in TMEM (the projection's A operand).  Order inside an iteration, most
+        // urgent first: q, k (S(n) is on the softmax chain) | v into registers (frees D_qkv) | normalisation of head n - 1
+        // (the issuer's next projection) | v rows (P V(n) is a whole softmax away).
         sp_reg_inc<kSpRegsDr>();
         const int dw = warp - kSpDr0, r = dw * 32 + lane, wslot = r >> 6, tok = r & 63;
         const uint32_t lane_addr = static_cast<uint32_t>(dw * 32) << 16;
@@ -816,12 +738,12 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
             }
         };
         for (int n = 0; n <= total; ++n) {
+            uint32_t raw[D];                                   // q, then k, then v columns of head n
             if (n < total) {
                 const int h = n % H;
                 mbar_wait(bars + CF::bDqFull, n & 1);
                 tc_fence_after_sync();
                 tick(24);                                                        // 24: wait D_qkv
-                uint32_t raw[D];
 #pragma unroll
                 for (int c = 0; c < D / 8; ++c) {
                     uint32_t t8[8];
@@ -871,23 +793,10 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tmem_wait_ld();
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bDqEmpty);              // the accumulator may be overwritten by QKV(n + 1)
-                if (n > 0) mbar_wait(bars + CF::bVFree, (n - 1) & 1);     // P V(n - 1) has read the V rows
-                tick(27);                                                        // 27: load v + wait V rows free
-#pragma unroll
-                for (int ch = 0; ch < D / 8; ++ch) {           // v -> hi / lo rows [key][slot 0 d | slot 1 d]
-                    uint32_t vh[4], vl[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        split_f16x2(__uint_as_float(raw[ch * 8 + 2 * j]), __uint_as_float(raw[ch * 8 + 2 * j + 1]), vh[j], vl[j]);
-                    const uint32_t off = rowoff + ((uint32_t(wslot * (D / 8) + ch) ^ sx) << 4);
-                    st_shared_v4(sb + CF::oVh + off, vh[0], vh[1], vh[2], vh[3]);
-                    st_shared_v4(sb + CF::oVl + off, vl[0], vl[1], vl[2], vl[3]);
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(bars + CF::bVReady);
-                tick(28);                                                        // 28: v -> shared memory
+                tick(27);                                                        // 27: load v
             }
             if (n >= 1) {
+                // O(n - 1) / rowsum first: the issuer needs it (projection) before it needs the v rows of head n
                 const int G = n - 1;
                 mbar_wait(bars + CF::bOFull, G & 1);
                 tc_fence_after_sync();
@@ -915,6 +824,23 @@ mwa_sp_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_
                 tc_fence_before_sync();
                 mbar_arrive(bars + CF::bOAReady);
                 tick(30);                                                        // 30: normalisation
+            }
+            if (n < total) {
+                // (O(n - 1) complete implies P V(n - 1) has read the V rows; the wait below then returns at once)
+                if (n > 0) mbar_wait(bars + CF::bVFree, (n - 1) & 1);
+#pragma unroll
+                for (int ch = 0; ch < D / 8; ++ch) {           // v -> hi / lo rows [key][slot 0 d | slot 1 d]
+                    uint32_t vh[4], vl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        split_f16x2(__uint_as_float(raw[ch * 8 + 2 * j]), __uint_as_float(raw[ch * 8 + 2 * j + 1]), vh[j], vl[j]);
+                    const uint32_t off = rowoff + ((uint32_t(wslot * (D / 8) + ch) ^ sx) << 4);
+                    st_shared_v4(sb + CF::oVh + off, vh[0], vh[1], vh[2], vh[3]);
+                    st_shared_v4(sb + CF::oVl + off, vl[0], vl[1], vl[2], vl[3]);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(bars + CF::bVReady);
+                tick(28);                                                        // 28: v -> shared memory
             }
         }
     }
@@ -962,7 +888,7 @@ int launch_sp(const float* x, const float* alpha, float* out, const uint8_t* sp,
     const int64_t nwin64 = int64_t(B) * geo.nwx * geo.nwy;
     if (nwin64 > 0x3fffffffll) return MWA_ERR_UNSUPPORTED;
     const int nwin = static_cast<int>(nwin64);
-    const SpWs ws(nwin);
+    const ListWs ws(nwin);
     if (!workspace || workspace_bytes < ws.total) return MWA_ERR_WORKSPACE;
     if (!aligned16(workspace)) return MWA_ERR_ALIGNMENT;
     uint8_t* wsp = static_cast<uint8_t*>(workspace);
@@ -976,11 +902,11 @@ int launch_sp(const float* x, const float* alpha, float* out, const uint8_t* sp,
         rc = check_launch("mwa_forward(scan)");
         if (rc != MWA_OK) return rc;
     }
-    mwa_sp_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, dlist, count);
+    mwa_list_compact_kernel<<<1, 1024, 0, st>>>(alpha ? flags : nullptr, nwin, list, dlist, count);
     rc = check_launch("mwa_forward(compact)");
     if (rc != MWA_OK) return rc;
     if (alpha != nullptr && out != x) {
-        mwa_sp_copy_dropped_kernel<<<kNumSMs * 4, 256, 0, st>>>(x, out, geo, CF::C, dlist, count);
+        mwa_copy_dropped_kernel<CF::WS><<<kNumSMs * 8, 256, 0, st>>>(x, out, geo, CF::C, flags, dlist, count);
         rc = check_launch("mwa_forward(copy dropped)");
         if (rc != MWA_OK) return rc;
     }
@@ -1013,7 +939,7 @@ bool mwa_sp_supported(int C, int heads, int ws, int H, int W, int channels_last)
     if (channels_last) return false;
     return C == 192 && ws == 8 && (heads == 8 || heads == 6) && H % 8 == 0 && W % 8 == 0 && W % 4 == 0;
 }
-int64_t mwa_sp_workspace_bytes(int64_t nwin) { return SpWs(nwin).total; }
+int64_t mwa_sp_workspace_bytes(int64_t nwin) { return ListWs(nwin).total; }
 void mwa_sp_set_timing_buffer(void* p) { g_sp_timing = static_cast<unsigned long long*>(p); }
 
 void mwa_sp_prepare_images(const float* qkv_w, const float* qkv_b, const float* proj_w, const float* proj_b,

@@ -50,8 +50,14 @@ class WindowAttentionFunction(Function):
             return torch.empty_like(x)
         ctx.empty = False
         channels_last = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
-        if not channels_last:
+        # The fp32-faithful fast kernels read NCHW.  A channels-last input goes through them too (one transposing copy
+        # each way: far cheaper than the general SIMT kernel, which is what the C ABI falls back to for NHWC); the output
+        # keeps the input's memory format, as torch ops do.  Only the opt-in fp16 kernels consume NHWC in place.
+        relayout = channels_last and algo in (_abi.ALGO_AUTO, _abi.ALGO_TCGEN05) and \
+            bool(lib.mwa_fast_path_needs_nchw(C, attn_mod.num_heads, ws))
+        if relayout or not channels_last:
             x = x.contiguous()
+            channels_last = False
         if alpha is not None:
             if alpha.shape != (B, 1, H, W):
                 raise RuntimeError(f"img_alpha must have shape {(B, 1, H, W)}, got {tuple(alpha.shape)}")
@@ -63,6 +69,8 @@ class WindowAttentionFunction(Function):
             _abi.check(lib.mwa_forward(x.data_ptr(), _abi.ptr(alpha), out.data_ptr(), blk.data_ptr(), B, C, H, W,
                                        attn_mod.num_heads, ws, shift, int(channels_last), algo, None,
                                        wsp.data_ptr(), wsp.numel(), _abi.stream_handle()), "mwa_forward")
+        if relayout:
+            out = out.contiguous(memory_format=torch.channels_last)
         ctx.cfg = (attn_mod, ws, shift)
         ctx.algo = algo
         ctx.has_bias = qkv_b is not None

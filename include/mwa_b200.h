@@ -40,11 +40,14 @@ enum {
     MWA_ERR_CUDA = -5          /* a CUDA runtime call failed (launch error) */
 };
 
-/* kernel selection: AUTO picks the tcgen05 kernel when the shape is covered, else the SIMT kernel.  For the shapes the
- * split-precision kernel covers (C = 192, 8 x 8 windows, 6 or 8 heads, NCHW) AUTO and TCGEN05 run it: fp16 hi + lo
- * operands, three MMA passes, every output within the reference's fp32 tolerance.  TCGEN05_FP16 forces the round-1
- * single-pass fp16 kernel (faster, ~1e-4 absolute error: opt-in only); TCGEN05_V1 the phase-serial first-generation
- * kernel (kept for A/B measurements). */
+/* kernel selection.  AUTO is fp32-faithful on every shape (the reference's arithmetic is fp32 end to end; every output
+ * within 1e-3 relative / 1e-4 absolute of it):
+ *   C = 192, 8 x 8 windows, 6 or 8 heads, NCHW   split-precision tcgen05 kernel (every operand fp16 hi + lo, 3 MMA passes)
+ *   C = 80, 4 x 4 windows, 8 heads, NCHW         plain fp32 kernel for small windows
+ *   anything else                                general fp32 SIMT kernel (also what SIMT forces)
+ * The single-pass fp16 tensor-core kernels of round 1 (faster, ~1e-4 .. 3e-4 absolute error at random init) are opt-in:
+ * TCGEN05_FP16, TCGEN05_V1 (phase-serial first generation, kept for A/B measurements) and TCGEN05 on the shapes that
+ * have no split-precision kernel. */
 enum { MWA_ALGO_AUTO = 0, MWA_ALGO_SIMT = 1, MWA_ALGO_TCGEN05 = 2, MWA_ALGO_TCGEN05_V1 = 3, MWA_ALGO_TCGEN05_FP16 = 4 };
 
 MWA_API int mwa_b200_abi_version(void);
@@ -120,6 +123,9 @@ MWA_API int mwa_prepare(const float* qkv_w, const float* qkv_b, const float* pro
                 const float* bias_table, int C, int heads, int ws, float scale, void* params,
                 int64_t params_bytes, void* stream);
 MWA_API int64_t mwa_workspace_bytes(int B, int H, int W, int ws);
+/* 1 when MWA_ALGO_AUTO has a fast fp32-faithful kernel for this configuration that reads NCHW only (the host layer then
+ * hands a channels-last tensor over as NCHW instead of letting it fall to the general SIMT kernel), else 0 */
+MWA_API int mwa_fast_path_needs_nchw(int C, int heads, int ws);
 /* development aid: device buffer of 4096 uint64 that the tcgen05 attention kernels fill with clock64() totals
  * ([0,32): per-stage totals of CTA 0; [64,320): cycles per CTA; [320,576): tiles per CTA).  NULL switches it off
  * (the default). */

@@ -22,6 +22,8 @@ win_attention = importlib.import_module(PACKAGE_NAME + ".layers.win_attention")
 Masked_Attention = importlib.import_module(PACKAGE_NAME + ".layers.Masked_Attention")
 SupplyMask = importlib.import_module(PACKAGE_NAME + ".layers.SupplyMask")
 data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
+codec = importlib.import_module(PACKAGE_NAME + ".codec")
+_params = importlib.import_module(PACKAGE_NAME + ".layers._params")
 
 GDN = GDN_mod.GDN
 LowerBound = GDN_mod.LowerBound
@@ -42,6 +44,8 @@ patch_model_rounding = _install.patch_model_rounding
 uninstall = _install.uninstall
 build = build_mod.build
 GradientAllReduce = data_parallel.GradientAllReduce
+RGBACodec = codec.AutoEncoder
+invalidate_param_blocks = _params.invalidate_param_blocks
 MwaB200Error = _abi.MwaB200Error
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_V1 = (_abi.ALGO_AUTO, _abi.ALGO_SIMT, _abi.ALGO_TCGEN05,
                                                           _abi.ALGO_TCGEN05_V1)

@@ -180,3 +180,70 @@ def rounding_inputs():
     lrp = torch.randn(x.numel(), generator=g) * 1.5
     m = torch.rand(x.numel(), generator=g)
     return dict(x=x, mu=mu, lrp=lrp, m=m)
+
+
+# ------------------------------------------------------------------------------------------------ whole-model cases
+MODEL_CASES = {
+    # AutoEncoderRGB_Journal.AutoEncoder forward on (B, 3, H, W) + alpha; H, W multiples of 64 (window sizes x strides x
+    # hyperprior strides) and > 160 (the 4 downsamplings of MS-SSIM)
+    "rgb_1x192x256": dict(B=1, H=192, W=256, drop=0.35, seed=61),
+}
+
+
+def model_inputs(cfg):
+    """image in [0, 1], alpha = k/255 blobs with ~drop of the 32x32 blocks fully transparent (what the dataset feeds,
+    trainRGB.py:275-279: the image is pre-multiplied by its binarised alpha), reconmask = a slightly different alpha (what
+    the mask codec hands over: clamp, quantise, `constraint`)."""
+    g = _gen(cfg["seed"])
+    B, H, W = cfg["B"], cfg["H"], cfg["W"]
+    yy = torch.linspace(0, 1, H).view(1, 1, H, 1)
+    xx = torch.linspace(0, 1, W).view(1, 1, 1, W)
+    base = torch.cat([0.5 + 0.4 * torch.sin(6.0 * xx + 3.0 * yy), 0.5 + 0.4 * torch.cos(5.0 * yy - 2.0 * xx),
+                      0.5 + 0.3 * torch.sin(9.0 * xx * yy + 1.0)], dim=1).expand(B, 3, H, W)
+    image = (base + 0.08 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1)
+    keep = (torch.rand(B, 1, H // 32, W // 32, generator=g) >= cfg["drop"]).float()
+    alpha = keep.repeat_interleave(32, 2).repeat_interleave(32, 3)
+    soft = torch.round((0.3 + 0.7 * torch.rand(B, 1, H, W, generator=g)) * 255) / 255
+    alpha = alpha * soft
+    image = image * (alpha > 0).float()
+    flip = (torch.rand(B, 1, H, W, generator=g) < 0.002).float()
+    reconmask = (alpha * (1 - flip) + flip * 0.5 * (alpha == 0).float()).clamp(0, 1)
+    return dict(image=image, alpha=alpha, reconmask=reconmask)
+
+
+def model_state(table, seed):
+    """Deterministic weights BY KEY NAME for a model whose state dict has the entries of `table` ({key: shape}; the
+    committed tests/golden/model_rgb_keys.json lists the reference model's).  Independent of construction order, so
+    the reference model (build container), the oracle restatement and the B200 codec all load the very same values.
+    Scales keep the activations O(1) through the stack; integer buffers (relative_position_index) are skipped."""
+    pedestal = (2.0 ** -18) ** 2
+    out = {}
+    for key in sorted(table):
+        shape = tuple(table[key])
+        if key.endswith("relative_position_index"):
+            continue
+        g = _gen((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7fffffff)
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf == "beta":
+            v = torch.sqrt(0.6 + 0.8 * torch.rand(shape, generator=g) + pedestal)
+        elif leaf == "gamma":
+            v = torch.sqrt(0.1 * torch.eye(shape[0]) + 0.01 * torch.rand(shape, generator=g) + pedestal)
+        elif leaf == "relative_position_bias_table":
+            v = torch.randn(shape, generator=g) * 0.2
+        elif leaf == "quantiles":
+            v = torch.tensor([-10.0, 0.0, 10.0]).repeat(shape[0], 1, 1)
+            v[:, 0, 1] = torch.randn(shape[0], generator=g) * 0.3
+        elif len(shape) >= 2:
+            # Conv2d (out, in, kh, kw) / ConvTranspose2d (in, out, kh, kw) / Linear (out, in)
+            fan = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+            if len(shape) == 4 and key.startswith("Decoder.x") and shape[2] == 5:
+                fan = shape[0] * 25 / 4                   # transposed, stride 2: a quarter of the taps per output
+            v = torch.randn(shape, generator=g) * (1.0 / fan) ** 0.5
+            if key == "Encoder.x4.weight":
+                v = v * 6.0                               # latents that span several quantisation steps ...
+            if key == "Decoder.x1.weight":
+                v = v * 0.06                              # ... without the three IGDNs blowing the decoder up
+        else:
+            v = torch.randn(shape, generator=g) * 0.05
+        out[key] = v
+    return out

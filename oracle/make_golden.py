@@ -135,6 +135,45 @@ def make_rounding(ref):
     return out
 
 
+def make_model(ref):
+    """whole-model forward of the UNMODIFIED AutoEncoderRGB_Journal.AutoEncoder (weights by key name, G.model_state) +
+    the reference's own masked MS-SSIM / PSNR on its output; also (re)writes the key table the weight recipe needs."""
+    import json
+    rgb = ref.model("rgb")
+    import importlib
+    metric = importlib.import_module("metrics.masked_ms_ssim_torch")      # the masked MS-SSIM of the reference
+    out = {}
+    for name, cfg in G.MODEL_CASES.items():
+        torch.manual_seed(234)
+        net = rgb.AutoEncoder().eval()
+        table = {k: list(v.shape) for k, v in net.state_dict().items()}
+        with open(os.path.join(OUT_DIR, "model_rgb_keys.json"), "w") as f:
+            json.dump(table, f, indent=0, sort_keys=True)
+        missing = net.load_state_dict(G.model_state(table, cfg["seed"]), strict=False)
+        assert not missing.unexpected_keys and all(k.endswith("relative_position_index") for k in missing.missing_keys)
+        p = G.model_inputs(cfg)
+        cap = {}
+        net.Encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("y", o))
+        net.h_a.register_forward_hook(lambda m, i, o: cap.__setitem__("z", o))
+        net.Decoder.register_forward_pre_hook(lambda m, i: cap.__setitem__("y_hat", i[0]))
+        with torch.no_grad():
+            me = net.EncMakeMask(p["alpha"])
+            x_hat, mse, bpp, bpp_y, bpp_z = net(p["image"], p["alpha"], p["reconmask"], me[0], me[1], me[2], me[3])
+            clipped = torch.clamp(x_hat, 0, 1)
+            msssim = metric.ms_ssim(p["image"], clipped, p["alpha"], data_range=1.0, size_average=True)
+            mse_clipped = rgb.reconstruct_error(p["image"], clipped, p["alpha"], p["reconmask"])
+        for k in ("y", "z", "y_hat"):
+            out[f"{name}/{k}"] = _np(cap[k])
+        out[f"{name}/x_hat"] = _np(x_hat)
+        out[f"{name}/mse"] = _np(mse)
+        out[f"{name}/mse_clipped"] = _np(mse_clipped)
+        out[f"{name}/ms_ssim"] = _np(msssim)
+        out[f"{name}/crc"] = np.array(G.checksum(p["image"], p["alpha"], p["reconmask"]), dtype=np.int64)
+        print(f"{name}: mse {float(mse):.6f} psnr {10 * np.log10(1 / float(mse_clipped)):.4f} ms-ssim {float(msssim):.6f} "
+              f"|y| {float(cap['y'].abs().mean()):.3f} |x_hat| {float(x_hat.abs().mean()):.3f}")
+    return out
+
+
 def main():
     ref = live_reference.load()
     torch.set_num_threads(1)           # fixed reduction order
@@ -142,7 +181,7 @@ def main():
     import sys
     only = set(sys.argv[1:])
     makers = (("attention.npz", make_attention), ("gdn.npz", make_gdn), ("rounding.npz", make_rounding),
-              ("wrapper.npz", make_wrapper), ("pyramid.npz", make_pyramid))
+              ("wrapper.npz", make_wrapper), ("pyramid.npz", make_pyramid), ("model_rgb.npz", make_model))
     for fname, data in ((f, mk(ref)) for f, mk in makers if not only or f in only):
         path = os.path.join(OUT_DIR, fname)
         np.savez_compressed(path, **data)

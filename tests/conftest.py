@@ -29,7 +29,15 @@ def lib(pkg):
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
-    return {k: np.load(os.path.join(GOLDEN, k + ".npz")) for k in ("attention", "gdn", "rounding", "wrapper", "pyramid")}
+    return {k: np.load(os.path.join(GOLDEN, k + ".npz")) for k in ("attention", "gdn", "rounding", "wrapper", "pyramid", "model_rgb")}
+
+
+@pytest.fixture(scope="session")
+def model_keys():
+    """state-dict key -> shape of the reference's AutoEncoderRGB_Journal.AutoEncoder (written by oracle/make_golden.py)"""
+    import json
+    with open(os.path.join(GOLDEN, "model_rgb_keys.json")) as f:
+        return json.load(f)
 
 
 @pytest.fixture(scope="session")

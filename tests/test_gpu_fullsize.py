@@ -38,15 +38,10 @@ def test_attention_config2_batch16(pkg, cuda_dev, C, heads, ws, s, H, W):
     pick = torch.cat([pick, last])
     ref = R.window_attention(xw[pick].double(), p["qkv_w"].double(), p["qkv_b"].double(), p["proj_w"].double(),
                              p["proj_b"].double(), p["table"].double(), heads, ws, mask=mask_all[pick].double())
-    emu = R.window_attention(xw[pick].double(), p["qkv_w"].double(), p["qkv_b"].double(), p["proj_w"].double(),
-                             p["proj_b"].double(), p["table"].double(), heads, ws, mask=mask_all[pick].double(),
-                             operand_dtype=torch.float16)
     got = (yw[pick] - xw[pick]).double()
-    err_k, err_e = (got - ref).abs(), (emu - ref).abs()
-    # tcgen05 kernel (fp16 operands): as accurate as its design predicts (see tests/test_gpu_parity._check_attention);
-    # the residual add of O(1) inputs costs another fp32 ulp
-    assert err_k.max() <= 2.0 * err_e.max() + 1e-5, (float(err_k.max()), float(err_e.max()))
-    assert err_k.mean() <= 1.5 * err_e.mean() + 2e-6, (float(err_k.mean()), float(err_e.mean()))
+    # the default kernels are fp32-faithful: north-star tolerance on every sampled element of the attention branch plus
+    # one fp32 ulp of the O(1) residual it was recovered from
+    torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-4 + 5e-7 * float(xw[pick].abs().max()))
 
 
 def test_gdn_igdn_round_trip_full_size(pkg, cuda_dev):

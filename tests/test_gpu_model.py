@@ -1,0 +1,100 @@
+"""The whole RGBA codec forward on the B200 (product: <package>/codec.py on the sm_100a modules, convolutions through
+cuDNN in fp32) against the outputs of the UNMODIFIED reference model committed in tests/golden/model_rgb.npz and against
+the CPU oracle (oracle/ref_model.py) -- BASELINE.json's model-level criteria: x_hat within 1e-3 rel / 1e-4 abs, rounded
+latents bit-exact except where the pre-rounding value sits on a .5 boundary, masked PSNR and masked MS-SSIM equal to 3
+decimals."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import golden_cases as G
+from oracle import ref_model as M
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _codec(pkg, model_keys, seed, dev):
+    net = pkg.RGBACodec().eval()
+    res = net.load_state_dict(G.model_state(model_keys, seed), strict=False)
+    assert not res.unexpected_keys
+    assert all(k.endswith("relative_position_index") or k.startswith("entropy_bottleneck._") for k in res.missing_keys)
+    return net.to(dev)
+
+
+@pytest.mark.parametrize("name", list(G.MODEL_CASES))
+def test_full_forward_matches_reference_model(pkg, cuda_dev, golden, model_keys, name):
+    cfg = G.MODEL_CASES[name]
+    g = golden["model_rgb"]
+    p = G.model_inputs(cfg)
+    assert int(g[name + "/crc"]) == G.checksum(p["image"], p["alpha"], p["reconmask"]), "seeded inputs drifted"
+    net = _codec(pkg, model_keys, cfg["seed"], cuda_dev)
+    image, alpha, recon = (p[k].to(cuda_dev) for k in ("image", "alpha", "reconmask"))
+    with torch.no_grad():
+        r = {k: v.cpu() for k, v in net.detail(image, alpha, recon).items()}
+        me = net.EncMakeMask(alpha)
+        x_hat2, mse, bpp, bpp_y, bpp_z = net(image, alpha, recon, me[0], me[1], me[2], me[3])
+    # the reference-signature forward is the same path (cuDNN may pick a different algorithm on the second call)
+    torch.testing.assert_close(x_hat2.cpu(), r["x_hat"], rtol=1e-4, atol=1e-5)
+    assert torch.isfinite(bpp).all() and float(bpp) > 0
+    # pre-quantiser latent and hyper-latent
+    torch.testing.assert_close(r["y"], _t(g[name + "/y"]), rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(r["z"], _t(g[name + "/z"]), rtol=RTOL, atol=ATOL)
+    # rounded latents: same symbols except where y - mu is within float error of k + 0.5.  A flipped symbol changes the
+    # support of the later slices, so only the slices up to the first flip are comparable symbol by symbol.
+    yq, yq_ref = r["y_hat"], _t(g[name + "/y_hat"])
+    diff = (yq - yq_ref).abs()
+    flipped = diff > 0.5
+    frac = float(flipped.float().mean())
+    assert frac < 2e-3, frac
+    sl = yq.shape[1] // 10
+    first_flip = next((i for i in range(10) if bool(flipped[:, i * sl:(i + 1) * sl].any())), 10)
+    if first_flip > 0:
+        torch.testing.assert_close(yq[:, :first_flip * sl], yq_ref[:, :first_flip * sl], rtol=RTOL, atol=ATOL)
+    if first_flip < 10:
+        # every flip in the first differing slice is a genuine .5 tie: |(y - mu) - round| ~ 0.5 in the ORACLE's values
+        w = G.model_state(model_keys, cfg["seed"])
+        with torch.no_grad():
+            o = M.rgb_forward(w, p["image"], p["alpha"], p["reconmask"])
+        s = slice(first_flip * sl, (first_flip + 1) * sl)
+        resid = (o["y"][:, s] - o["means"][:, s])
+        tie = (resid - torch.floor(resid) - 0.5).abs()
+        assert float(tie[flipped[:, s]].max()) < 2e-3
+    # reconstruction
+    x_ref = _t(g[name + "/x_hat"])
+    if frac == 0.0:
+        torch.testing.assert_close(r["x_hat"], x_ref, rtol=RTOL, atol=ATOL)
+    else:
+        assert float(((r["x_hat"] - x_ref).abs() > ATOL + RTOL * x_ref.abs()).float().mean()) < 0.05
+    # metrics to 3 decimals: the reference's masked MSE -> PSNR (trainRGB.py:303) and masked MS-SSIM on the clipped output
+    clipped = r["x_hat"].clamp(0, 1)
+    psnr = M.psnr(M.masked_mse(p["image"], clipped, p["alpha"]))
+    assert round(psnr, 3) == round(M.psnr(float(g[name + "/mse_clipped"])), 3), (psnr, float(g[name + "/mse_clipped"]))
+    ms = float(M.masked_ms_ssim(p["image"], clipped, p["alpha"]))
+    assert round(ms, 3) == round(float(g[name + "/ms_ssim"]), 3), (ms, float(g[name + "/ms_ssim"]))
+    assert abs(float(mse) - float(g[name + "/mse"])) <= 2e-3 * float(g[name + "/mse"])
+
+
+def test_full_forward_batch_and_baseline_size_against_oracle_samples(pkg, cuda_dev, model_keys):
+    """BASELINE config 2 geometry (768 x 512), batch 2: latent of the first image against the CPU oracle (bounded: the
+    oracle runs the analysis transform of one image), batch items independent of each other"""
+    cfg = dict(B=2, H=512, W=768, drop=0.35, seed=77)
+    p = G.model_inputs(cfg)
+    net = _codec(pkg, model_keys, 61, cuda_dev)
+    with torch.no_grad():
+        r = net.detail(p["image"].to(cuda_dev), p["alpha"].to(cuda_dev), p["reconmask"].to(cuda_dev))
+        r1 = net.detail(p["image"][1:].to(cuda_dev), p["alpha"][1:].to(cuda_dev), p["reconmask"][1:].to(cuda_dev))
+    assert r["x_hat"].shape == (2, 3, 512, 768) and torch.isfinite(r["x_hat"]).all()
+    torch.testing.assert_close(r["y"][1:], r1["y"], rtol=1e-4, atol=1e-5)      # cuDNN picks algorithms per batch size
+    torch.testing.assert_close(r["x_hat"][1:], r1["x_hat"], rtol=1e-3, atol=1e-4)
+    w = G.model_state(model_keys, 61)
+    from oracle import ref_ops as R
+    with torch.no_grad():
+        me = R.alpha_pyramid(p["alpha"][:1])
+        y0 = M.analysis(M._sub(w, "Encoder."), p["image"][:1], me[1], me[2])
+    torch.testing.assert_close(r["y"][:1].cpu(), y0, rtol=RTOL, atol=ATOL)

@@ -41,22 +41,24 @@ def _oracle_attn(cfg, p, dtype=torch.float32):
                                      c(p["proj_b"]), c(p["table"]), cfg["heads"], cfg["ws"], cfg["shift"])
 
 
-def _uses_tcgen05(cfg, algo):
-    return algo == "auto" and (cfg["C"], cfg["heads"], cfg["ws"]) in {(192, 8, 8), (192, 6, 8), (80, 8, 4)}
-
-
 def _check_attention(y, p, cfg, algo, ref32=None):
-    """fp32 SIMT kernel: tight tolerance against the reference.  tcgen05 kernel (fp16 tensor-core operands, fp32
-    accumulation): it must be as accurate as its design predicts -- its error against the fp64 oracle is bounded by
-    the error of the oracle's own fp16-operand model (oracle.ref_ops.window_attention(operand_dtype=float16)) --
-    and stay within 5e-2 of the fp32 reference even on these deliberately harsh weights (logit std ~5)."""
+    """Every kernel selection the modules make by default is fp32-faithful: the auto path (split-precision tcgen05 kernel
+    for 8x8 / C=192, fp32 small-window kernel for 4x4 / C=80, general SIMT kernel otherwise) is held to BASELINE.json's
+    1e-3 relative / 1e-4 absolute against the fp64 oracle AND against the committed outputs of the reference itself, on
+    every element -- also on these deliberately harsh weights (logit std ~5).  The forced SIMT kernel is held tighter."""
     ref64 = _oracle_attn(cfg, p, torch.float64)
     y = y.double().cpu()
-    if not _uses_tcgen05(cfg, algo):
-        torch.testing.assert_close(y, ref64, rtol=1e-4, atol=2e-5)
-        if ref32 is not None:
-            torch.testing.assert_close(y.float(), ref32, rtol=1e-4, atol=2e-5)
-        return
+    rt, at = (RTOL, ATOL) if algo == "auto" else (1e-4, 2e-5)
+    torch.testing.assert_close(y, ref64, rtol=rt, atol=at)
+    if ref32 is not None:
+        torch.testing.assert_close(y.float(), ref32, rtol=rt, atol=at)
+
+
+def _check_fp16_opt_in(y, p, cfg):
+    """the opt-in single-pass fp16 tensor-core kernels: as accurate as their design predicts -- error against the fp64
+    oracle bounded by the error of the oracle's own fp16-operand model -- and within 5e-2 on the harsh golden weights"""
+    ref64 = _oracle_attn(cfg, p, torch.float64)
+    y = y.double().cpu()
     c = lambda t: None if t is None else t.double()
     emu = R.masked_window_attention(c(p["x"]), c(p["alpha"]), c(p["qkv_w"]), c(p["qkv_b"]), c(p["proj_w"]),
                                     c(p["proj_b"]), c(p["table"]), cfg["heads"], cfg["ws"], cfg["shift"],
@@ -110,18 +112,30 @@ def test_attention_forward_vs_oracle_seeded(pkg, cuda_dev, C, heads, ws, s, B, H
     _check_attention(ycl, p, cfg, algo)
 
 
+@pytest.mark.parametrize("name", ["attn_c80_h8_ws4_s2", "attn_c192_h8_ws8_s4", "attn_c192_h6_ws8_s0",
+                                  "attn_c192_h8_ws8_s4_unmasked"])
+def test_attention_fp16_kernels_are_opt_in_and_as_accurate_as_designed(pkg, cuda_dev, name):
+    cfg = G.ATTENTION_CASES[name]
+    p = G.attention_inputs(cfg)
+    m = _mk_attn(pkg, cfg, p, cuda_dev)
+    m.algo = pkg._abi.ALGO_TCGEN05_FP16
+    x = p["x"].to(cuda_dev)
+    with torch.no_grad():
+        y = m(x, p["alpha"].to(cuda_dev)) if cfg["masked"] else m(x)
+    _check_fp16_opt_in(y, p, cfg)
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0])
 @pytest.mark.parametrize("C,heads,ws,s,B,H,W", [(192, 8, 8, 4, 2, 64, 96), (80, 8, 4, 2, 2, 32, 48),
-                                                (192, 6, 8, 4, 1, 64, 64)])
-def test_attention_north_star_tolerance_at_random_init(pkg, cuda_dev, C, heads, ws, s, B, H, W):
+                                                (192, 6, 8, 4, 1, 64, 64), (192, 8, 8, 4, 1, 24, 40)])
+def test_attention_north_star_tolerance_at_random_init(pkg, cuda_dev, C, heads, ws, s, B, H, W, scale):
     """BASELINE.json: "identical synthetic inputs and identical random-init weights: fp32 outputs within 1e-3
-    relative / 1e-4 absolute".  Module default init (what the reference builds), x ~ N(0,1), 40 % of the windows
-    transparent.  The fp32 SIMT kernel meets the bound on every element.  The tcgen05 kernel feeds the tensor cores
-    fp16 operands: >= 99.9 % of the elements meet the bound, the rest (outputs near zero, where only the 1e-4
-    absolute term is left) stay below 5e-4 -- see DESIGN.md "precision"."""
+    relative / 1e-4 absolute".  Module default init (what the reference builds), x ~ N(0, scale^2), 40 % of the windows
+    transparent.  EVERY element of the default path's output meets the bound (and so does the forced SIMT kernel)."""
     torch.manual_seed(C + heads)
     m = pkg.MaskedWinBasedAttention(C, heads, ws, s)
     gen = torch.Generator().manual_seed(7)
-    x = torch.randn(B, C, H, W, generator=gen)
+    x = torch.randn(B, C, H, W, generator=gen) * scale
     alpha = G.blob_alpha(B, H, W, ws, s, 0.4, 99)
     a = m.attn
     ref = R.masked_window_attention(x.double(), alpha.double(), a.qkv.weight.detach().double(),
@@ -133,12 +147,12 @@ def test_attention_north_star_tolerance_at_random_init(pkg, cuda_dev, C, heads, 
         m.algo = ALGOS["simt"]
         y_simt = m(x.to(cuda_dev), alpha.to(cuda_dev)).cpu().double()
         m.algo = ALGOS["auto"]
-        y_tc = m(x.to(cuda_dev), alpha.to(cuda_dev)).cpu().double()
+        y_auto = m(x.to(cuda_dev), alpha.to(cuda_dev)).cpu().double()
+        y_cl = m(x.to(cuda_dev).contiguous(memory_format=torch.channels_last), alpha.to(cuda_dev))
     torch.testing.assert_close(y_simt, ref, rtol=RTOL, atol=ATOL)
-    err = (y_tc - ref).abs()
-    within = err <= ATOL + RTOL * ref.abs()
-    assert within.double().mean() >= 0.999, float(within.double().mean())
-    assert err.max() <= 5e-4, float(err.max())
+    torch.testing.assert_close(y_auto, ref, rtol=RTOL, atol=ATOL)
+    assert y_cl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y_cl.cpu().double(), y_auto)          # channels-last inputs take the same kernels
 
 
 def test_alpha_one_equals_unmasked_bit_exact(pkg, cuda_dev):

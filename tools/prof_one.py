@@ -7,6 +7,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mwa_b200 as pkg  # noqa: E402
+if os.environ.get("MWA_B200_LIB"):          # development: a variant library (tools/build_variants.py)
+    pkg._abi.LIB_PATH = os.path.abspath(os.environ["MWA_B200_LIB"])
 
 what = sys.argv[1] if len(sys.argv) > 1 else "gdn"
 algo = {"auto": 0, "simt": 1, "tc": 2}[sys.argv[2] if len(sys.argv) > 2 else "auto"]

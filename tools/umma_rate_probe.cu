@@ -8,7 +8,9 @@ using namespace b200;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
 
 // MODE 0: SS (A, B from smem)   1: TS (A from TMEM)   2: TS + MN-major B   4: SS lane-masked (half the lanes disabled)
-// 5: the QKV pattern of csrc/mwa_sp.cu (SS N, TS 32, SS 32 per k step)
+// 5: an earlier QKV pattern (SS N, TS 32, SS 32 per k step)   6: the P V pattern of csrc/mwa_sp.cu (TS, MN-major B,
+// lane-masked halves alternating, second B start advanced inside the atom)   7: the S pattern (TS, lane-masked halves)
+// 8: the QKV pattern (SS N, TS N, SS N per k step)
 template <int N, int MODE, bool LANE0>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -24,7 +26,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) 
     tc_fence_after_sync();
     const uint32_t tm = tmem_base_s;
     if (warp == 0) {
-        constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, 128, N) | (MODE == 2 ? kUmmaBMajorMN : 0u);
+        constexpr uint32_t idesc = umma_idesc(kFmtF16, kFmtF16, 128, N) | ((MODE == 2 || MODE == 6) ? kUmmaBMajorMN : 0u);
         constexpr uint32_t id32 = umma_idesc(kFmtF16, kFmtF16, 128, 32);
         const uint64_t ad = umma_desc_k_sw128(smem_u32(smem)), bd = umma_desc_k_sw128(smem_u32(smem + 32768));
         long long t0 = 0, t1 = 0, t2 = 0;
@@ -43,6 +45,16 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) 
                     else if constexpr (MODE == 4) {
                         if (u & 1) umma_f16_ss_lanes(tm, ad + ks * 2, bd + ks * 2, idesc, 1, ~0u, ~0u, 0u, 0u);
                         else umma_f16_ss_lanes(tm, ad + ks * 2, bd + ks * 2, idesc, 1, 0u, 0u, ~0u, ~0u);
+                    } else if constexpr (MODE == 6) {
+                        if (u & 1) umma_f16_ts_lanes(tm, tm + 256 + ks * 8, bd + ks * 128 + 4, idesc, 1, ~0u, ~0u, 0u, 0u);
+                        else umma_f16_ts_lanes(tm, tm + 256 + ks * 8, bd + ks * 128, idesc, 1, 0u, 0u, ~0u, ~0u);
+                    } else if constexpr (MODE == 7) {
+                        if (u & 1) umma_f16_ts_lanes(tm, tm + 256 + ks * 8, bd + 512 + ks * 2, idesc, 1, ~0u, ~0u, 0u, 0u);
+                        else umma_f16_ts_lanes(tm, tm + 256 + ks * 8, bd + ks * 2, idesc, 1, 0u, 0u, ~0u, ~0u);
+                    } else if constexpr (MODE == 8) {
+                        umma_f16_ss(tm, ad + ks * 2, bd + ks * 2, idesc, 1);
+                        umma_f16_ts(tm, tm + 256 + ks * 8, bd + ks * 2, idesc, 1);
+                        umma_f16_ss(tm, ad + ks * 2, bd + 1024 + ks * 2, idesc, 1);
                     } else {
                         umma_f16_ss(tm, ad + ks * 2, bd + ks * 2, idesc, 1);
                         umma_f16_ts(tm + 48, tm + 256 + ks * 8, bd + 48 * 8 + ks * 2, id32, 1);
@@ -65,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) 
 
 template <int N, int MODE, bool LANE0>
 void run(long long* d) {
-    const char* names[] = {"SS", "TS", "TS+MN", "", "SS masked", "QKV mix"};
+    const char* names[] = {"SS", "TS", "TS+MN", "", "SS masked", "QKV old", "PV masked", "S masked", "QKV mix"};
     const int reps = 512;
     CK(cudaFuncSetAttribute(rate_kernel<N, MODE, LANE0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     for (int w = 0; w < 2; ++w) {
@@ -74,7 +86,7 @@ void run(long long* d) {
     }
     long long h[2];
     CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
-    const int n_mma = (MODE == 5) ? 3 * reps : reps;
+    const int n_mma = (MODE == 5 || MODE == 8) ? 3 * reps : reps;
     printf("%-9s N=%3d %s: issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)\n", names[MODE], N,
            LANE0 ? "lane0-branch" : "elect_one", double(h[0]) / n_mma, double(h[1]) / n_mma, N / 2);
 }
@@ -88,6 +100,8 @@ int main() {
     run<48, 2, false>(d); run<64, 2, false>(d);
     run<64, 4, false>(d);
     run<80, 5, false>(d);
+    run<32, 6, false>(d); run<32, 2, false>(d); run<64, 7, false>(d); run<80, 8, false>(d); run<96, 8, false>(d);
+    run<16, 2, false>(d); run<16, 6, false>(d);
     run<32, 0, true>(d); run<96, 0, true>(d); run<192, 0, true>(d); run<32, 1, true>(d); run<80, 5, true>(d);
     return 0;
 }
