@@ -43,6 +43,11 @@ _SIGNATURES = {
     "mwa_debug_set_timing_buffer": (None, [c_void_p]),
     "mwa_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "mwa_fast_path_needs_nchw": (c_int, [c_int, c_int, c_int]),
+    "conv_image_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "conv_split_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "conv_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "conv_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mwa_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "window_attention_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,

@@ -24,19 +24,20 @@ import torch.nn.functional as F
 from . import quant
 from .layers.GDN import GDN
 from .layers.Masked_Attention import Win_noShift_Attention, conv3x3
+from .layers.conv import ACT_RELU, Conv2d, ConvStack, ConvTranspose2d
 from .layers.SupplyMask import SupplyMaskToTransform, alpha_pyramid
 
 
 def _conv(cin, cout, k, stride=1):
-    return nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2)
+    return Conv2d(cin, cout, k, stride=stride, padding=k // 2)
 
 
 def _deconv5(cin, cout):
-    return nn.ConvTranspose2d(cin, cout, 5, stride=2, padding=2, output_padding=1)
+    return ConvTranspose2d(cin, cout, 5, stride=2, padding=2, output_padding=1)
 
 
 def _subpel(cin, cout, r=2):
-    return nn.Sequential(nn.Conv2d(cin, cout * r * r, 3, padding=1), nn.PixelShuffle(r))
+    return nn.Sequential(Conv2d(cin, cout * r * r, 3, padding=1), nn.PixelShuffle(r))
 
 
 class EnhancementBlock(nn.Module):
@@ -44,12 +45,12 @@ class EnhancementBlock(nn.Module):
 
     def __init__(self, n=32):
         super().__init__()
-        self.conv1 = nn.Conv2d(n, n, 3, padding=1)
+        self.conv1 = Conv2d(n, n, 3, padding=1)
         self.relu = nn.ReLU(inplace=True)
-        self.conv2 = nn.Conv2d(n, n, 3, padding=1)
+        self.conv2 = Conv2d(n, n, 3, padding=1)
 
     def forward(self, x):
-        return self.conv2(self.relu(self.conv1(x))) + x
+        return self.conv2(self.conv1(x, act=ACT_RELU), residual=x)
 
 
 class DSE(nn.Module):
@@ -57,14 +58,14 @@ class DSE(nn.Module):
 
     def __init__(self, n=32):
         super().__init__()
-        self.input_conv = nn.Conv2d(3, n, 1)
+        self.input_conv = Conv2d(3, n, 1)
         self.enh1, self.enh2, self.enh3 = EnhancementBlock(n), EnhancementBlock(n), EnhancementBlock(n)
-        self.output_conv = nn.Conv2d(n, 3, 1)
+        self.output_conv = Conv2d(n, 3, 1)
 
     def forward(self, x):
         first = self.input_conv(x)
         t = self.enh3(self.enh2(self.enh1(first)))
-        return self.output_conv(t + first) + x
+        return self.output_conv(t + first, residual=x)
 
 
 class Analysis_transform(nn.Module):
@@ -79,7 +80,7 @@ class Analysis_transform(nn.Module):
         self.attention1 = Win_noShift_Attention(dim=N, num_heads=8, window_size=8, shift_size=4)
         self.x3 = _conv(N, N, 5, 2)
         self.gdn3 = GDN(N)
-        self.x4 = nn.Conv2d(N, M, 1)
+        self.x4 = Conv2d(N, M, 1)
         self.attention2 = Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2)
 
     def forward(self, input, mask, me1, me2, me3, me4):
@@ -96,7 +97,7 @@ class Synthesis_transform(nn.Module):
     def __init__(self, N=196, M=320):
         super().__init__()
         self.attention1 = Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2)
-        self.x1 = nn.Conv2d(M, N, 1)
+        self.x1 = Conv2d(M, N, 1)
         self.igdn1 = GDN(N, inverse=True)
         self.x2 = _deconv5(N, N)
         self.igdn2 = GDN(N, inverse=True)
@@ -192,18 +193,18 @@ class AutoEncoder(nn.Module):
         self.DecMakeMask = SupplyMaskToTransform()
         self.num_slices, self.max_support_slices = 10, 5
         g = nn.GELU
-        self.h_a = nn.Sequential(conv3x3(M, 320, stride=2), g(), conv3x3(320, 288), g(), conv3x3(288, 256, stride=2), g(),
+        self.h_a = ConvStack(conv3x3(M, 320, stride=2), g(), conv3x3(320, 288), g(), conv3x3(288, 256, stride=2), g(),
                                  conv3x3(256, 224), g(), conv3x3(224, 192, stride=2))
 
         def hyper_s():
-            return nn.Sequential(_subpel(192, 192), g(), conv3x3(192, 224), g(), _subpel(224, 256), g(),
+            return ConvStack(_subpel(192, 192), g(), conv3x3(192, 224), g(), _subpel(224, 256), g(),
                                  conv3x3(256, 288), g(), _subpel(288, M))
 
         self.h_mean_s, self.h_scale_s = hyper_s(), hyper_s()
         sl = M // self.num_slices
 
         def cc(cin):
-            return nn.Sequential(_conv(cin, 224, 3), g(), _conv(224, 128, 3), g(), _conv(128, sl, 3))
+            return ConvStack(_conv(cin, 224, 3), g(), _conv(224, 128, 3), g(), _conv(128, sl, 3))
 
         self.cc_mean_transforms = nn.ModuleList(cc(M + sl * min(i, 5)) for i in range(self.num_slices))
         self.cc_scale_transforms = nn.ModuleList(cc(M + sl * min(i, 5)) for i in range(self.num_slices))
@@ -227,39 +228,48 @@ class AutoEncoder(nn.Module):
         sl, ms = M // self.num_slices, self.max_support_slices
         in_place = not (torch.is_grad_enabled() and (y.requires_grad or latent_means.requires_grad))
         if in_place:
-            mean_sup = torch.empty(B, M + (ms + 1) * sl, H, W, device=y.device, dtype=y.dtype)
-            mean_sup[:, :M] = latent_means
-            scale_sup = None
-            if want_scales:
-                scale_sup = torch.empty(B, M + ms * sl, H, W, device=y.device, dtype=y.dtype)
-                scale_sup[:, :M] = latent_scales
+            return self._slice_loop_in_place(y, latent_means, latent_scales, want_scales)
         y_hat_slices, mus, scales = [], [], []
         for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
-            k = min(i, ms)
-            if in_place:
-                mean_support = mean_sup[:, :M + k * sl]
-                scale_support = scale_sup[:, :M + k * sl] if want_scales else None
-            else:
-                mean_support = torch.cat([latent_means] + y_hat_slices[:ms], dim=1)
-                scale_support = torch.cat([latent_scales] + y_hat_slices[:ms], dim=1) if want_scales else None
+            support = y_hat_slices[:ms]
+            mean_support = torch.cat([latent_means] + support, dim=1)
             mu = self.cc_mean_transforms[i](mean_support)[:, :, :H, :W]
             if want_scales:
-                scales.append(self.cc_scale_transforms[i](scale_support)[:, :, :H, :W])
+                scales.append(self.cc_scale_transforms[i](torch.cat([latent_scales] + support, dim=1))[:, :, :H, :W])
             y_hat = quant.quantize_offset(y_slice, mu)
-            # lrp support = [latent means | y_hat_0 .. y_hat_{k-1} | y_hat_i]
-            if in_place:
-                mean_sup[:, M + k * sl:M + (k + 1) * sl] = y_hat
-                lrp_support = mean_sup[:, :M + (k + 1) * sl]
-            else:
-                lrp_support = torch.cat([mean_support, y_hat], dim=1)
-            y_hat = quant.lrp_add(y_hat, self.lrp_transforms[i](lrp_support))
-            if in_place and i < ms:                      # becomes a support slice of the later ones
-                mean_sup[:, M + i * sl:M + (i + 1) * sl] = y_hat
-                if want_scales:
-                    scale_sup[:, M + i * sl:M + (i + 1) * sl] = y_hat
+            y_hat = quant.lrp_add(y_hat, self.lrp_transforms[i](torch.cat([mean_support, y_hat], dim=1)))
             y_hat_slices.append(y_hat)
             mus.append(mu)
         return (torch.cat(y_hat_slices, 1), torch.cat(mus, 1), torch.cat(scales, 1) if want_scales else None)
+
+    def _slice_loop_in_place(self, y, latent_means, latent_scales, want_scales):
+        B, M, H, W = y.shape
+        sl, ms = M // self.num_slices, self.max_support_slices
+        # mean_sup = [latent means | y_hat_0 .. y_hat_4 | scratch slice]; every prefix is one of the reference's cats
+        mean_sup = torch.empty(B, M + (ms + 1) * sl, H, W, device=y.device, dtype=y.dtype)
+        mean_sup[:, :M] = latent_means
+        scale_sup = None
+        if want_scales:
+            scale_sup = torch.empty(B, M + ms * sl, H, W, device=y.device, dtype=y.dtype)
+            scale_sup[:, :M] = latent_scales
+        y_hat_all = torch.empty_like(y)
+        mus, scales = [], []
+        for i, y_slice in enumerate(y.chunk(self.num_slices, 1)):
+            k = min(i, ms)
+            mu = self.cc_mean_transforms[i](mean_sup[:, :M + k * sl])[:, :, :H, :W]
+            if want_scales:
+                scales.append(self.cc_scale_transforms[i](scale_sup[:, :M + k * sl])[:, :, :H, :W])
+            # ste_round(y - mu) + mu lands in the slot right behind the supports: lrp support = that prefix
+            slot = mean_sup[:, M + k * sl:M + (k + 1) * sl]
+            quant.quantize_offset(y_slice, mu, out=slot)
+            lrp = self.lrp_transforms[i](mean_sup[:, :M + (k + 1) * sl])
+            y_hat = quant.lrp_add(slot, lrp, out=y_hat_all[:, i * sl:(i + 1) * sl])
+            if i < ms:                                   # becomes a support slice of the later ones
+                mean_sup[:, M + i * sl:M + (i + 1) * sl] = y_hat
+                if want_scales:
+                    scale_sup[:, M + i * sl:M + (i + 1) * sl] = y_hat
+            mus.append(mu)
+        return y_hat_all, torch.cat(mus, 1), torch.cat(scales, 1) if want_scales else None
 
     def detail(self, input, mask, reconmask, me2=None, me3=None):
         """every tensor of the forward the parity tests look at"""

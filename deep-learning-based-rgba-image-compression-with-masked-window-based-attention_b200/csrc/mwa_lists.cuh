@@ -50,7 +50,7 @@ mwa_list_compact_kernel(const uint8_t* __restrict__ flags, int nwin, int32_t* __
 }
 
 // out = x on the dropped windows (the block is the identity there, layers/masked_win_attention.py:249 adds zeros).
-// Work item = (SEGMENT of up to 8 horizontally adjacent dropped windows, channel part), one warp each: with
+// Work item = (SEGMENT of up to 8 horizontally adjacent dropped windows, 4 channels), one warp each: with
 // shift = ws / 2 a window row sits at half a row's offset (8x8 windows: 32 bytes at a 16-byte offset, i.e. it straddles
 // two 32-byte sectors) -- copied window by window every sector would be fetched and written twice (measured 1.7 TB/s);
 // a segment is one contiguous row piece of 4 * WS * len bytes per (channel, row), copied as consecutive vectors.
@@ -66,28 +66,41 @@ struct VecT<2> { using type = float2; };
 
 template <int WS, int VEC>
 __device__ __forceinline__ void copy_segment(const float* __restrict__ xs, float* __restrict__ os, const Geom& g, int wy, int wx,
-                                             int len, int cpp, int64_t hw, int lane) {
+                                             int len, int nc, int64_t hw, int lane) {
     using V = typename VecT<VEC>::type;
     constexpr int U = 8;
-    // positions of a (channel, segment): WS rows x (WS / VEC) * len vectors; short segments take several channels per sweep
-    const int per_row = (WS / VEC) * len, npos = WS * per_row;
-    const int csplit = (npos <= 8) ? 4 : (npos <= 16) ? 2 : 1, lanes = 32 / csplit;
-    const int csub = lane / lanes;
-    for (int pos = lane % lanes; pos < npos; pos += lanes) {
-        const int r = pos / per_row, k = pos - r * per_row;
-        int py = wy * WS + r + g.shift, px = wx * WS + g.shift + VEC * k;
-        if (py >= g.H) py -= g.H;
-        if (px >= g.W) px -= g.W;
-        const int64_t off = int64_t(py) * g.W + px + int64_t(csub) * hw;
-        for (int c = 0; c < cpp; c += csplit * U) {
-            V v[U];
+    // vector positions of a (channel, segment): WS rows x (WS / VEC) * len; the (channel, position) pairs of the item are
+    // dealt to the lanes position-fastest (consecutive lanes = consecutive vectors of a row), U independent loads in flight
+    // Widen the row piece to whole 32-byte sectors where that stays inside the image row: with shift = ws / 2 a piece
+    // starts and ends in the middle of a sector, and a half-written sector costs a read-modify-write.  The extra 16 bytes
+    // on either side belong to a neighbouring window: if that one is dropped it receives the same values from its own
+    // copy, if it is kept the attention kernel (later in the stream) overwrites every pixel of it.
+    int px_start = wx * WS + g.shift, px_end = px_start + WS * len;
+    if (VEC == 4 && px_end <= g.W) {
+        if (px_start % 8 == 4) px_start -= 4;
+        if (px_end % 8 == 4 && px_end + 4 <= g.W) px_end += 4;
+    }
+    const int per_row = (px_end - px_start) / VEC, npos = WS * per_row, total = npos * nc;
+    for (int base = lane; base < total; base += 32 * U) {
+        V v[U];
+        int64_t off[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (c + csplit * u + csub < cpp) v[u] = __ldcs(reinterpret_cast<const V*>(xs + off + int64_t(c + csplit * u) * hw));
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (c + csplit * u + csub < cpp) __stcs(reinterpret_cast<V*>(os + off + int64_t(c + csplit * u) * hw), v[u]);
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + 32 * u;
+            off[u] = -1;
+            if (idx < total) {
+                const int c = idx / npos, pos = idx - c * npos;
+                const int r = pos / per_row, k = pos - r * per_row;
+                int py = wy * WS + r + g.shift, px = px_start + VEC * k;
+                if (py >= g.H) py -= g.H;
+                if (px >= g.W) px -= g.W;
+                off[u] = int64_t(c) * hw + int64_t(py) * g.W + px;
+                v[u] = __ldcs(reinterpret_cast<const V*>(xs + off[u]));
+            }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) __stcs(reinterpret_cast<V*>(os + off[u]), v[u]);
     }
 }
 
@@ -96,20 +109,20 @@ __global__ void __launch_bounds__(256)
 mwa_copy_dropped_kernel(const float* __restrict__ x, float* __restrict__ out, Geom g, int C,
                         const uint8_t* __restrict__ flags, const int32_t* __restrict__ dlist,
                         const int32_t* __restrict__ count) {
-    constexpr int PARTS = 8, SEG = 8;
+    constexpr int SEG = 8, CPP = 4;                      // channels per work item: many small items, one round each
     const int n = count[1];
     const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
     const int64_t hw = int64_t(g.H) * g.W;
-    const int cpp = (C + PARTS - 1) / PARTS;
-    for (int i = gw; i < n * PARTS; i += nw) {
-        const int win = dlist[i / PARTS];
+    const int parts = (C + CPP - 1) / CPP;
+    for (int64_t i = gw; i < int64_t(n) * parts; i += nw) {
+        const int win = dlist[i / parts];
         int b, wy, wx;
         window_coords(g, win, b, wy, wx);
         if (wx % SEG != 0 && !flags[win - 1]) continue;      // not the head of its segment
         int len = 1;
         while ((wx + len) % SEG != 0 && wx + len < g.nwx && !flags[win + len]) ++len;
-        const int c0 = (i % PARTS) * cpp;
-        const int nc = min(cpp, C - c0);
+        const int c0 = int(i % parts) * CPP;
+        const int nc = min(CPP, C - c0);
         if (nc <= 0) continue;
         const float* xs = x + (int64_t(b) * C + c0) * hw;
         float* os = out + (int64_t(b) * C + c0) * hw;

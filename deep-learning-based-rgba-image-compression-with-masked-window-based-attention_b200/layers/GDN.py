@@ -189,6 +189,7 @@ class GDN(ParamBlockOwner, nn.Module):
             unfold = True
             bs, ch, d, w, h = inputs.size()
             inputs = inputs.view(bs, ch, d * w, h)
+        self._refresh_if_training()
         outputs = _GDNFunction.apply(inputs, self.beta, self.gamma, self)
         if unfold:
             outputs = outputs.view(bs, ch, d, w, h)

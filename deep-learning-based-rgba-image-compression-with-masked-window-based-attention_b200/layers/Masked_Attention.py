@@ -18,16 +18,17 @@ from torch.autograd import Function
 from .. import _abi
 from .masked_win_attention import *  # noqa: F401,F403  (the reference file star-imports it too, :6)
 from .masked_win_attention import WinBasedAttention
+from .conv import ACT_GELU, Conv2d, ConvStack
 
 
 def conv1x1(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
     """1x1 convolution (reference :11-13)."""
-    return nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=stride)
+    return Conv2d(in_ch, out_ch, kernel_size=1, stride=stride)
 
 
 def conv3x3(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
     """3x3 convolution with padding (compressai.layers.conv3x3, imported by the reference :8-10)."""
-    return nn.Conv2d(in_ch, out_ch, kernel_size=3, stride=stride, padding=1)
+    return Conv2d(in_ch, out_ch, kernel_size=3, stride=stride, padding=1)
 
 
 class _GateResidual(Function):
@@ -79,7 +80,7 @@ class Win_noShift_Attention(nn.Module):
 
             def __init__(self):
                 super().__init__()
-                self.conv = nn.Sequential(
+                self.conv = ConvStack(
                     conv1x1(N, N // 2),
                     nn.GELU(),
                     conv3x3(N // 2, N // 2),
@@ -89,11 +90,8 @@ class Win_noShift_Attention(nn.Module):
                 self.relu = nn.GELU()
 
             def forward(self, x):
-                identity = x
-                out = self.conv(x)
-                out += identity
-                out = self.relu(out)
-                return out
+                # conv -> + identity -> GELU: the add and the activation ride in the last convolution's epilogue
+                return self.conv(x, residual=x, final_act=ACT_GELU)
 
         self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
 

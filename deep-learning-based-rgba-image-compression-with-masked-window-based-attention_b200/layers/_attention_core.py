@@ -253,5 +253,6 @@ class WindowAttentionBase(ParamBlockOwner, nn.Module):
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None."""
+        self._refresh_if_training()
         return TokenAttentionFunction.apply(x, mask, self.qkv.weight, self.qkv.bias, self.proj.weight,
                                             self.proj.bias, self.relative_position_bias_table, self)

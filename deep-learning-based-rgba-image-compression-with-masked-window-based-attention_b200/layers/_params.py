@@ -5,9 +5,10 @@ The block is a plain attribute, NOT a registered buffer: the state_dict keys mus
 When is it rebuilt?
 * whenever a parameter it depends on changed version (`_version` bumps on every in-place update through the
   parameter itself: optimizer step, `load_state_dict`, init), moved (`data_ptr`, device) or the block size changed;
-* on EVERY call while autograd is recording for one of the parameters (training) or while the current stream is being
-  captured into a CUDA graph: the prepare kernel is a few microseconds, and this way a replayed graph re-derives the
-  block from the weights it finds at replay time instead of baking in the ones of the capture;
+* on EVERY call while autograd is recording for one of the parameters (training: the modules call
+  `_refresh_if_training()` from their forward) or while the current stream is being captured into a CUDA graph: the
+  prepare kernel is a few microseconds, and this way a replayed graph re-derives the block from the weights it finds at
+  replay time instead of baking in the ones of the capture;
 * after `invalidate()`, which the modules call from `_apply` (`.to()`, `.cuda()`, `.half()` ...) and
   `_load_from_state_dict`.
 
@@ -32,16 +33,18 @@ class ParamBlock:
     def invalidate(self) -> None:
         self.key = None
 
+    def __deepcopy__(self, memo):
+        return ParamBlock()          # a copied module prepares its own block (CUDA events do not copy)
+
     def get(self, tensors, nbytes: int, fill):
         """tensors: iterable of parameters the block depends on; fill(blk) runs the prepare kernel on the current stream."""
         live = [t for t in tensors if t is not None]
         dev = live[0].device
         key = tuple((t.data_ptr(), t._version, str(t.device)) if t is not None else None for t in tensors)
         capturing = torch.cuda.is_current_stream_capturing()
-        training = torch.is_grad_enabled() and any(t.requires_grad for t in live)
         cur = torch.cuda.current_stream(dev)
         fresh = self.blk is None or self.blk.numel() != nbytes or self.blk.device != dev
-        if fresh or capturing or training or key != self.key:
+        if fresh or capturing or key != self.key:
             if fresh:
                 self.blk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             elif self.ready is not None and self.stream != cur and not capturing:
@@ -63,6 +66,12 @@ class ParamBlockOwner:
 
     def invalidate_param_block(self) -> None:
         self._blk.invalidate()
+
+    def _refresh_if_training(self) -> None:
+        """call from the module's forward, OUTSIDE the autograd Function (inside it grad mode is off): when autograd is
+        recording for one of this module's parameters the block is rebuilt on this call, whatever the cache key says"""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            self._blk.invalidate()
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)

@@ -74,6 +74,7 @@ class WinBasedAttention(nn.Module):
 
     def forward(self, x, img_alpha):
         a = self.attn
+        a._refresh_if_training()
         return WindowAttentionFunction.apply(x, img_alpha, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                                              a.relative_position_bias_table, a, self.window_size, self.shift_size,
                                              self.algo)

@@ -52,6 +52,7 @@ class WinBasedAttention(nn.Module):
 
     def forward(self, x):
         a = self.attn
+        a._refresh_if_training()
         return WindowAttentionFunction.apply(x, None, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                                              a.relative_position_bias_table, a, self.window_size, self.shift_size,
                                              self.algo)

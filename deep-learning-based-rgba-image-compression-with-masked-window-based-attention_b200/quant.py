@@ -130,13 +130,63 @@ def ste_round(x: torch.Tensor) -> torch.Tensor:
     return _RoundSTE.apply(x)
 
 
-def quantize_offset(x: torch.Tensor, mu: torch.Tensor) -> torch.Tensor:
-    """ste_round(x - mu) + mu, fused; mu has x's shape or is per-channel (1, C, 1, 1)."""
+def _rows_like(t: torch.Tensor, rows: int, n: int):
+    """row stride of `t` when read as `rows` rows of `n` contiguous floats (what the kernels address), or None"""
+    r = _rows(t)
+    if r is None:
+        return None
+    trows, tn, ts = r
+    if (trows, tn) == (rows, n):
+        return ts
+    if trows == 1 and tn == rows * n:
+        return n
+    return None
+
+
+def _into(fn_name, a, b, out):
+    """inference fast path: the elementwise kernels write straight into `out`, a dense tensor or a channel slice of one
+    (e.g. the slice loop's support buffer), so that no `torch.cat` / copy kernel is needed afterwards"""
+    lib = _abi.load()
+    for name, t in (("input", a), ("second operand", b), ("out", out)):
+        _abi.require_cuda_f32(t, f"{fn_name} {name}")
+    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+        raise _abi.MwaB200Error(f"{fn_name}(out=...) is an inference path: it does not record autograd history")
+    if not (a.shape == b.shape == out.shape):
+        raise _abi.MwaB200Error(f"{fn_name}(out=...): shapes differ")
+    r = _rows(a) or _rows(out)
+    if r is None:
+        a = a.contiguous()
+        r = _rows(a)
+    rows, n, _ = r
+    sa, sb, so = _rows_like(a, rows, n), _rows_like(b, rows, n), _rows_like(out, rows, n)
+    if sa is None:
+        a = a.contiguous(); sa = _rows_like(a, rows, n)
+    if sb is None:
+        b = b.contiguous(); sb = _rows_like(b, rows, n)
+    if so is None or sa is None or sb is None:
+        raise _abi.MwaB200Error(f"{fn_name}(out=...): `out` must be dense or a channel slice of a dense tensor")
+    with torch.cuda.device(a.device):
+        if fn_name == "quantize_offset":
+            st = lib.quantize_offset_forward(a.data_ptr(), b.data_ptr(), out.data_ptr(), rows, n, sa, sb, so, 0, 1,
+                                             _abi.stream_handle())
+        else:
+            st = lib.lrp_add_forward(a.data_ptr(), b.data_ptr(), out.data_ptr(), rows, n, sa, sb, so, _abi.stream_handle())
+        _abi.check(st, fn_name + "_forward")
+    return out
+
+
+def quantize_offset(x: torch.Tensor, mu: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ste_round(x - mu) + mu, fused; mu has x's shape or is per-channel (1, C, 1, 1).  `out` (inference only, mu of x's
+    shape): write into this tensor -- it may be a channel slice of a larger one, or x itself."""
+    if out is not None:
+        return _into("quantize_offset", x, mu, out)
     return _QuantizeOffset.apply(x, mu)
 
 
-def lrp_add(y_hat: torch.Tensor, lrp: torch.Tensor) -> torch.Tensor:
-    """y_hat + 0.5 * tanh(lrp)."""
+def lrp_add(y_hat: torch.Tensor, lrp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """y_hat + 0.5 * tanh(lrp).  `out` (inference only): destination, may be a channel slice or y_hat itself."""
+    if out is not None:
+        return _into("lrp_add", y_hat, lrp, out)
     return _LrpAdd.apply(y_hat, lrp)
 
 

@@ -231,6 +231,28 @@ MWA_API int alpha_pyramid_forward(const float* alpha, float* recon, float* level
  * One launch, no host synchronisation (the reference's boolean-mask assignments synchronise twice). */
 MWA_API int mask_constraint_forward(const float* mask, float* out, int B, int H, int W, int quant_levels, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions of the transforms (the callers of the hot path)   replaces the torch.nn.Conv2d /
+ *   ConvTranspose2d calls of layers/TransformRGB.py:16-100, layers/Masked_Attention.py:150-181 and
+ *   models/AutoEncoderRGB_Journal.py:139-203 (F.conv2d / F.conv_transpose2d, fp32) in inference.
+ *
+ * kind 0: convolution, k in {1, 3, 5}, stride 1 or 2 (H, W even), padding k / 2, dilation 1, groups 1
+ * kind 1: transposed convolution, k = 5, stride 2, padding 2, output padding 1 (output 2H x 2W)
+ * conv_prepare : weight (Cout, Cin, k, k) [kind 0] / (Cin, Cout, k, k) [kind 1] -> bf16 hi / lo UMMA operand image
+ * conv_forward : out = act(conv(x) + bias (+ residual));  x fp32 NCHW with batch stride `x_batch_stride` floats (a
+ *                channel slice of a larger tensor is fine), out fp32 NCHW with batch stride `out_batch_stride`,
+ *                residual dense (B, Cout, Ho, Wo) or NULL, act: 0 none, 1 GELU (erf), 2 ReLU.
+ *                split_hi / split_lo: scratch of conv_split_bytes(B, Cin, H, W) bytes each.
+ *                Implicit GEMM on tcgen05, bf16 hi + lo operands in three passes, fp32 accumulation: ~1e-5 relative.
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int64_t conv_image_bytes(int kind, int Cin, int Cout, int k, int stride);
+MWA_API int64_t conv_split_bytes(int B, int Cin, int H, int W);
+MWA_API int conv_prepare(const float* w, int kind, int Cin, int Cout, int k, int stride, void* image, int64_t image_bytes,
+                         void* stream);
+MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bias, const float* residual, float* out,
+                         int64_t out_batch_stride, const void* image, void* split_hi, void* split_lo, int kind, int B,
+                         int Cin, int Cout, int H, int W, int k, int stride, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ win_attention = importlib.import_module(PACKAGE_NAME + ".layers.win_attention")
 Masked_Attention = importlib.import_module(PACKAGE_NAME + ".layers.Masked_Attention")
 SupplyMask = importlib.import_module(PACKAGE_NAME + ".layers.SupplyMask")
 data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
+conv = importlib.import_module(PACKAGE_NAME + ".layers.conv")
 codec = importlib.import_module(PACKAGE_NAME + ".codec")
 _params = importlib.import_module(PACKAGE_NAME + ".layers._params")
 

@@ -1,0 +1,93 @@
+"""The transforms' convolutions on the B200 (csrc/conv_tc.cu: implicit GEMM on tcgen05, bf16 hi + lo operands, fp32
+accumulation) against the reference's own operator, torch.nn.functional.conv2d / conv_transpose2d in fp32 on the CPU
+(layers/TransformRGB.py:16-100, layers/Masked_Attention.py:150-181, models/AutoEncoderRGB_Journal.py:139-203 call
+exactly these).  Tolerance: BASELINE.json's 1e-3 relative / 1e-4 absolute, on every element."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# kind, Cin, Cout, k, stride, B, H, W, act, residual, bias
+CASES = [
+    ("conv", 192, 96, 1, 1, 2, 16, 32, 1, False, True),       # residual unit: conv1x1 + GELU
+    ("conv", 96, 96, 3, 1, 2, 16, 32, 1, False, True),        # residual unit: conv3x3 + GELU
+    ("conv", 96, 192, 1, 1, 2, 16, 32, 1, True, True),        # residual unit: conv1x1 + identity + GELU
+    ("conv", 40, 40, 3, 1, 1, 8, 12, 1, False, True),         # C = 80 wrapper, grid smaller than one tile
+    ("conv", 120, 224, 3, 1, 2, 24, 40, 1, False, True),      # slice loop, K not a multiple of 64, ragged tiles
+    ("conv", 224, 128, 3, 1, 1, 16, 16, 1, False, True),
+    ("conv", 128, 8, 3, 1, 2, 16, 16, 0, False, True),        # slice loop head: 8 output channels
+    ("conv", 288, 320, 3, 1, 1, 16, 16, 0, False, True),      # hyper synthesis: two N blocks (sub-pixel conv 288 -> 4 x 80)
+    ("conv", 80, 320, 3, 2, 1, 32, 32, 1, False, True),       # h_a: stride 2
+    ("conv", 3, 192, 5, 2, 2, 32, 48, 0, False, True),        # analysis x1: 3 input channels, 5x5 stride 2
+    ("conv", 192, 192, 5, 2, 1, 32, 32, 0, False, True),      # analysis x2 / x3
+    ("conv", 32, 32, 3, 1, 1, 40, 48, 2, False, True),        # DSE: ReLU
+    ("conv", 32, 3, 1, 1, 1, 40, 48, 0, True, True),          # DSE output conv + identity
+    ("conv", 64, 64, 3, 1, 1, 8, 16, 0, False, False),        # no bias
+    ("deconv", 192, 192, 5, 2, 1, 16, 24, 0, False, True),    # synthesis x2 / x3
+    ("deconv", 192, 3, 5, 2, 2, 12, 20, 0, False, True),      # synthesis x4: 3 output channels, ragged tiles
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}_{c[1]}to{c[2]}_k{c[3]}s{c[4]}_{c[6]}x{c[7]}")
+def test_convolution_matches_torch_cpu_fp32(pkg, cuda_dev, case):
+    kind, cin, cout, k, s, B, H, W, act, use_res, use_bias = case
+    conv_mod = pkg.conv
+    g = torch.Generator().manual_seed(cin * 7 + cout + k)
+    x = torch.randn(B, cin, H, W, generator=g) * 1.5
+    if kind == "conv":
+        m = conv_mod.Conv2d(cin, cout, k, stride=s, padding=k // 2, bias=use_bias)
+    else:
+        m = conv_mod.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1, bias=use_bias)
+    with torch.no_grad():
+        m.weight.normal_(0, (1.0 / (cin * k * k)) ** 0.5, generator=g)
+        if use_bias:
+            m.bias.normal_(0, 0.2, generator=g)
+        ref = F.conv2d(x, m.weight, m.bias, stride=s, padding=k // 2) if kind == "conv" else \
+            F.conv_transpose2d(x, m.weight, m.bias, stride=s, padding=k // 2, output_padding=1)
+        res = torch.randn(ref.shape, generator=g) if use_res else None
+        if use_res:
+            ref = ref + res
+        ref = F.gelu(ref) if act == 1 else F.relu(ref) if act == 2 else ref
+        m = m.to(cuda_dev)
+        y = m(x.to(cuda_dev), act=act, residual=None if res is None else res.to(cuda_dev))
+    assert y.shape == ref.shape
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+    assert float((y.cpu() - ref).abs().max()) < 5e-5 * max(1.0, float(ref.abs().max()))     # bf16 x 3 is ~2^-16 relative
+
+
+def test_convolution_on_a_channel_slice_and_weight_update(pkg, cuda_dev):
+    """the slice loop feeds channel-prefix views of its support buffer (batch stride > C H W); a weight update must reach
+    the cached operand image"""
+    m = pkg.conv.Conv2d(88, 224, 3, padding=1).to(cuda_dev)
+    big = torch.randn(2, 128, 16, 24, device=cuda_dev)
+    with torch.no_grad():
+        y = m(big[:, :88])
+        ref = F.conv2d(big[:, :88].cpu(), m.weight.cpu(), m.bias.cpu(), padding=1)
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+        m.weight.mul_(0.5)
+        y2 = m(big[:, :88])
+        ref2 = F.conv2d(big[:, :88].cpu(), m.weight.cpu(), m.bias.cpu(), padding=1)
+        torch.testing.assert_close(y2.cpu(), ref2, rtol=1e-3, atol=1e-4)
+
+
+def test_convolution_with_autograd_history_takes_the_library_path(pkg, cuda_dev):
+    m = pkg.conv.Conv2d(16, 16, 3, padding=1).to(cuda_dev)
+    x = torch.randn(1, 16, 8, 8, device=cuda_dev, requires_grad=True)
+    y = m(x, act=1)
+    y.sum().backward()
+    assert x.grad is not None and m.weight.grad is not None
+
+
+def test_conv_stack_fuses_activations(pkg, cuda_dev):
+    conv = pkg.conv
+    torch.manual_seed(0)
+    stack = conv.ConvStack(conv.Conv2d(24, 32, 3, padding=1), torch.nn.GELU(),
+                           torch.nn.Sequential(conv.Conv2d(32, 64, 3, padding=1), torch.nn.PixelShuffle(2)), torch.nn.GELU(),
+                           conv.Conv2d(16, 8, 3, padding=1))
+    plain = torch.nn.Sequential(*[m for m in stack])
+    x = torch.randn(2, 24, 16, 16)
+    with torch.no_grad():
+        ref = plain(x)
+        y = stack.to(cuda_dev)(x.to(cuda_dev))
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)

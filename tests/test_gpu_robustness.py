@@ -95,3 +95,71 @@ def test_channels_last_gives_the_same_result(pkg, cuda_dev, C, heads, ws, shift)
     with torch.no_grad():
         torch.testing.assert_close(gm(x.contiguous(memory_format=torch.channels_last)).contiguous(), gm(x), rtol=1e-5,
                                    atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ parameter-block cache
+def test_param_block_follows_weight_updates(pkg, cuda_dev):
+    """the cached kernel-ready parameter block must never serve stale weights: in-place updates through the parameter
+    (optimizer step, load_state_dict) are seen through `_version`; writes through `.data` are not visible to any key and
+    need `invalidate_param_blocks`; a captured CUDA graph re-derives the block at replay time"""
+    import copy
+    torch.manual_seed(0)
+    g = pkg.GDN(192).to(cuda_dev)
+    x = torch.randn(2, 192, 16, 24, device=cuda_dev)
+    with torch.no_grad():
+        y0 = g(x)
+        g.beta.mul_(1.5)                                     # bumps _version
+        y1 = g(x)
+        assert not torch.equal(y0, y1)
+        ref = copy.deepcopy(g)
+        g.beta.data.mul_(2.0)                                # invisible to the cache key
+        ref.beta.data.mul_(2.0)
+        assert pkg.invalidate_param_blocks(g) == 1
+        torch.testing.assert_close(g(x), ref(x), rtol=0, atol=0)
+        sd = {k: v.clone() for k, v in g.state_dict().items()}
+        sd["beta"] = sd["beta"] * 0.5
+        g.load_state_dict(sd)
+        ref.load_state_dict(sd)
+        torch.testing.assert_close(g(x), ref(x), rtol=0, atol=0)
+        # CUDA graph: capture, then change the weights, replay -> the replay uses the new weights
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = g(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        before = out.clone()
+        g.beta.mul_(1.25)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert not torch.equal(before, out)
+        torch.testing.assert_close(out, g(x), rtol=0, atol=0)
+
+
+def test_param_block_is_rebuilt_every_call_in_training(pkg, cuda_dev):
+    m = pkg.MaskedWinBasedAttention(80, 8, 4, 2).to(cuda_dev)
+    x = torch.randn(1, 80, 8, 8, device=cuda_dev)
+    a = torch.ones(1, 1, 8, 8, device=cuda_dev)
+    y0 = m(x, a)                                             # grad enabled: prepare runs on every call
+    m.attn.proj.weight.data.mul_(0.5)                        # a write no key can see
+    y1 = m(x, a)
+    assert not torch.equal(y0, y1)
+    with torch.no_grad():
+        m.attn.proj.weight.mul_(2.0)
+        torch.testing.assert_close(m(x, a), y0.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_param_block_cross_stream_hit_waits_for_the_fill(pkg, cuda_dev):
+    g = pkg.GDN(192).to(cuda_dev)
+    x = torch.randn(4, 192, 64, 96, device=cuda_dev)
+    with torch.no_grad():
+        ref = g(x).clone()
+        g.invalidate_param_block()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            y1 = g(x)                                        # fills the block on s1
+        with torch.cuda.stream(s2):
+            y2 = g(x)                                        # cache hit on another stream: must wait for the fill
+        torch.cuda.synchronize()
+    assert torch.equal(y1, ref) and torch.equal(y2, ref)

@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""profiling target: the six GDN / IGDN launches of one forward at BASELINE config-2 shapes (batch 16), once each"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mwa_b200 as pkg
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+with torch.no_grad():
+    for warm in (True, False):
+        for d, inv in ((2, False), (4, False), (8, False), (8, True), (4, True), (2, True)):
+            m = pkg.GDN(192, inverse=inv)
+            m.gamma.add_(torch.rand(192, 192) * 0.02)
+            m = m.to(dev)
+            x = torch.randn(16, 192, 512 // d, 768 // d, device=dev)
+            y = m(x)
+            if warm:
+                break
+torch.cuda.synchronize()
+print("done")
