@@ -67,6 +67,35 @@ def patch_model_rounding(model_module) -> None:
     model_module.ste_round = ste_round
 
 
+def accelerate_convs(model) -> int:
+    """Switch the convolutions of an ALREADY BUILT model (the reference's AutoEncoder, built from its own files) to this
+    package's drop-in classes, in place: every plain `torch.nn.Conv2d` / `ConvTranspose2d` becomes `layers.conv.Conv2d` /
+    `ConvTranspose2d` and every plain `nn.Sequential` that holds convolutions becomes a `ConvStack` (activations folded
+    into the convolutions' epilogues).  Parameters, buffers, hooks and state-dict keys are untouched -- only the class
+    of the module objects changes.  In inference on CUDA the covered geometries then run csrc/conv_tc.cu, everything else
+    (and every call that records autograd history) keeps going through torch.nn.functional.  Returns the number of
+    convolutions switched."""
+    import torch.nn as nn
+    from .layers import conv as C
+    n = 0
+    for m in model.modules():
+        if type(m) is nn.Conv2d:
+            m.__class__ = C.Conv2d
+            m._img = C._WeightImage()
+            n += 1
+        elif type(m) is nn.ConvTranspose2d:
+            m.__class__ = C.ConvTranspose2d
+            m._img = C._WeightImage()
+            n += 1
+    for m in model.modules():
+        if type(m) is nn.Sequential and any(isinstance(c, (C.Conv2d, C.ConvTranspose2d)) or
+                                            (type(c) is nn.Sequential and len(c) == 2 and isinstance(c[0], C.Conv2d))
+                                            for c in m):
+            if not (len(m) == 2 and isinstance(m[1], nn.PixelShuffle)):      # sub-pixel pairs stay plain: their parent fuses them
+                m.__class__ = C.ConvStack
+    return n
+
+
 def uninstall() -> None:
     for name in ("layers",) + tuple(f"layers.{n}" for n in _DROPINS + ("Masked_Attention", "SupplyMask")):
         sys.modules.pop(name, None)

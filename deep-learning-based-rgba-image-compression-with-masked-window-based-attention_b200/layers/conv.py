@@ -7,7 +7,7 @@
                                  activations folded into the convolutions' epilogues
 
 Inference (no autograd history) on CUDA fp32 NCHW tensors runs `conv_forward` of csrc/conv_tc.cu: implicit GEMM on
-tcgen05 with bf16 hi + lo operands in three passes and fp32 accumulation -- fp32-faithful (~1e-5 relative), where the
+tcgen05 with fp16 hi + lo operands in three passes and fp32 accumulation -- fp32-faithful (~1e-6 relative), where the
 reference's torch.nn.Conv2d in fp32 is cuDNN's SIMT path on a GPU.  Covered: k in {1, 3, 5}, stride 1 or 2, padding k / 2,
 groups 1, dilation 1; transposed k = 5, stride 2, padding 2, output padding 1 -- every convolution of the Journal
 models.  Anything else, and every call that records autograd history (training: the backward is torch's), goes to

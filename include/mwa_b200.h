@@ -238,12 +238,14 @@ MWA_API int mask_constraint_forward(const float* mask, float* out, int B, int H,
  *
  * kind 0: convolution, k in {1, 3, 5}, stride 1 or 2 (H, W even), padding k / 2, dilation 1, groups 1
  * kind 1: transposed convolution, k = 5, stride 2, padding 2, output padding 1 (output 2H x 2W)
- * conv_prepare : weight (Cout, Cin, k, k) [kind 0] / (Cin, Cout, k, k) [kind 1] -> bf16 hi / lo UMMA operand image
+ * conv_prepare : weight (Cout, Cin, k, k) [kind 0] / (Cin, Cout, k, k) [kind 1] -> fp16 hi / lo UMMA operand image
+ *                (per output channel scaled by a power of two into fp16's normal range; the inverse scales ride along)
  * conv_forward : out = act(conv(x) + bias (+ residual));  x fp32 NCHW with batch stride `x_batch_stride` floats (a
  *                channel slice of a larger tensor is fine), out fp32 NCHW with batch stride `out_batch_stride`,
  *                residual dense (B, Cout, Ho, Wo) or NULL, act: 0 none, 1 GELU (erf), 2 ReLU.
  *                split_hi / split_lo: scratch of conv_split_bytes(B, Cin, H, W) bytes each.
- *                Implicit GEMM on tcgen05, bf16 hi + lo operands in three passes, fp32 accumulation: ~1e-5 relative.
+ *                Implicit GEMM on tcgen05, fp16 hi + lo operands in three passes, fp32 accumulation: ~1e-6 relative;
+ *                activations beyond +-1.3e5 saturate (fp16 hi + lo range).
  * ------------------------------------------------------------------------------------------------ */
 MWA_API int64_t conv_image_bytes(int kind, int Cin, int Cout, int k, int stride);
 MWA_API int64_t conv_split_bytes(int B, int Cin, int H, int W);

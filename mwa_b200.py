@@ -42,6 +42,7 @@ lrp_add = quant.lrp_add
 quantize_levels = quant.quantize_levels
 install = _install.install
 patch_model_rounding = _install.patch_model_rounding
+accelerate_convs = _install.accelerate_convs
 uninstall = _install.uninstall
 build = build_mod.build
 GradientAllReduce = data_parallel.GradientAllReduce

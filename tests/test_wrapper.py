@@ -78,3 +78,22 @@ def test_gate_residual_forward_backward(pkg, cuda_dev, shape, channels_last):
     torch.testing.assert_close(out.detach().double().cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
     for d, r in zip(dev, ref_in):
         torch.testing.assert_close(d.grad.double().cpu(), r.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_accelerate_convs_switches_classes_and_keeps_values_and_keys(pkg):
+    """post-construction switch of a model's convolutions to the drop-in classes: same state dict, same CPU results
+    (without a CUDA tensor the drop-ins run torch.nn.functional, exactly like the classes they replace)"""
+    import torch
+    import torch.nn as nn
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(3, 8, 5, stride=2, padding=2), nn.GELU(),
+                        nn.Sequential(nn.Conv2d(8, 32, 3, padding=1), nn.PixelShuffle(2)), nn.GELU(),
+                        nn.ConvTranspose2d(8, 4, 5, stride=2, padding=2, output_padding=1), nn.ReLU(), nn.Conv2d(4, 2, 1))
+    x = torch.randn(2, 3, 16, 24)
+    ref = net(x)
+    keys = list(net.state_dict().keys())
+    assert pkg.accelerate_convs(net) == 4
+    assert isinstance(net, pkg.conv.ConvStack) and isinstance(net[0], pkg.conv.Conv2d)
+    assert isinstance(net[4], pkg.conv.ConvTranspose2d) and type(net[2]) is nn.Sequential
+    assert list(net.state_dict().keys()) == keys
+    torch.testing.assert_close(net(x), ref, rtol=1e-6, atol=1e-6)
