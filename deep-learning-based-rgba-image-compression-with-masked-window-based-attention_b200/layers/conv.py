@@ -93,6 +93,8 @@ def _run(x, weight, bias, image, kind, k, stride, act, residual, cout, ho, wo):
 
 
 class Conv2d(nn.Conv2d):
+    min_channels = 8          # narrower ends go to the library (see _covered); tests set 1 to exercise the kernel there
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self._img = _WeightImage()
@@ -102,7 +104,11 @@ class Conv2d(nn.Conv2d):
         return (self.kernel_size[0] == self.kernel_size[1] and k in (1, 3, 5) and self.stride[0] == self.stride[1]
                 and s in (1, 2) and tuple(self.padding) == (k // 2, k // 2) and tuple(self.dilation) == (1, 1)
                 and self.groups == 1 and self.padding_mode == "zeros" and x.shape[1] == self.in_channels
-                and (s == 1 or (x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0)))
+                and (s == 1 or (x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0))
+                # 3-channel ends of the transforms (x1, the DSE 1x1s): pure memory streams with K or N = 3, where the
+                # 64-channel K blocks and 16-column N blocks of the GEMM kernel are mostly padding -- measured slower than
+                # the library's fp32 kernels there, so they stay with it
+                and self.in_channels >= self.min_channels and self.out_channels >= self.min_channels)
 
     def forward(self, x, act=ACT_NONE, residual=None):
         if _fast_ok(x, self.weight, self.bias, residual) and self._covered(x):

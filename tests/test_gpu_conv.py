@@ -37,6 +37,7 @@ def test_convolution_matches_torch_cpu_fp32(pkg, cuda_dev, case):
     x = torch.randn(B, cin, H, W, generator=g) * 1.5
     if kind == "conv":
         m = conv_mod.Conv2d(cin, cout, k, stride=s, padding=k // 2, bias=use_bias)
+        m.min_channels = 1                 # exercise the kernel on the 3-channel ends too (the module routes them to the library)
     else:
         m = conv_mod.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1, bias=use_bias)
     with torch.no_grad():
