@@ -7,9 +7,10 @@ is absent (the GPU box of the test / bench harness): identical attribute names a
 (`Encoder.x1.weight` ... `lrp_transforms.9.4.bias`, `entropy_bottleneck.quantiles`), identical forward signature and
 return values, so a reference checkpoint loads with `load_state_dict(..., strict=False)`.
 
-What runs where: masked window attention, GDN / IGDN, the gate of the attention wrapper, the alpha pyramid and every
-rounding step are this package's sm_100a kernels; the convolutions are torch (cuDNN) -- SURVEY.md section 8f ranks them
-"next".  The entropy models are restated from CompressAI's published definitions (factorised prior of Balle et al. 2018,
+What runs where: masked window attention, GDN / IGDN, the alpha pyramid, every rounding step and (in inference) the
+convolutions -- tcgen05 implicit GEMMs chained through fp16 hi / lo planes, with GELU / ReLU, residual adds, the wrapper's
+gate, the slice loop's quantisation and lrp update as epilogues (csrc/conv_tc.cu) -- are this package's sm_100a kernels;
+the 3-channel ends (x1, x4, the DSE 1x1s) and everything that records autograd history are torch (cuDNN).  The entropy models are restated from CompressAI's published definitions (factorised prior of Balle et al. 2018,
 Gaussian conditional with scale lower bound 0.11 and likelihood lower bound 1e-9) only to produce the bpp terms of the
 forward; they are not part of the parity contract ("parity unpinned").
 """
@@ -24,7 +25,7 @@ import torch.nn.functional as F
 from . import quant
 from .layers.GDN import GDN
 from .layers.Masked_Attention import Win_noShift_Attention, conv3x3
-from .layers.conv import ACT_RELU, Conv2d, ConvStack, ConvTranspose2d
+from .layers.conv import ACT_LRP, ACT_QUANT, ACT_RELU, Conv2d, ConvStack, ConvTranspose2d, SplitAct
 from .layers.SupplyMask import SupplyMaskToTransform, alpha_pyramid
 
 
@@ -49,8 +50,12 @@ class EnhancementBlock(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.conv2 = Conv2d(n, n, 3, padding=1)
 
-    def forward(self, x):
-        return self.conv2(self.conv1(x, act=ACT_RELU), residual=x)
+    def forward(self, x, **kw):
+        if self.conv1.input_ps(x) is None:
+            return self.conv2(self.conv1(x, act=ACT_RELU), residual=x)
+        # conv1's output exists only as the planes conv2 reads; x may be a SplitAct carrying its dense tensor
+        return self.conv2(self.conv1(x, act=ACT_RELU, emit_ps=1, want_dense=False),
+                          residual=x.dense if isinstance(x, SplitAct) else x, **kw)
 
 
 class DSE(nn.Module):
@@ -64,7 +69,10 @@ class DSE(nn.Module):
 
     def forward(self, x):
         first = self.input_conv(x)
-        t = self.enh3(self.enh2(self.enh1(first)))
+        if self.enh1.conv1.input_ps(first) is None:
+            t = self.enh3(self.enh2(self.enh1(first)))
+        else:
+            t = self.enh3(self.enh2(self.enh1(first, emit_ps=1), emit_ps=1))
         return self.output_conv(t + first, residual=x)
 
 
@@ -227,6 +235,8 @@ class AutoEncoder(nn.Module):
         B, M, H, W = y.shape
         sl, ms = M // self.num_slices, self.max_support_slices
         in_place = not (torch.is_grad_enabled() and (y.requires_grad or latent_means.requires_grad))
+        if in_place and self.cc_mean_transforms[0][0].input_ps(latent_means) is not None:
+            return self._slice_loop_fused(y, latent_means, latent_scales, want_scales)
         if in_place:
             return self._slice_loop_in_place(y, latent_means, latent_scales, want_scales)
         y_hat_slices, mus, scales = [], [], []
@@ -241,6 +251,38 @@ class AutoEncoder(nn.Module):
             y_hat_slices.append(y_hat)
             mus.append(mu)
         return (torch.cat(y_hat_slices, 1), torch.cat(mus, 1), torch.cat(scales, 1) if want_scales else None)
+
+    def _slice_loop_fused(self, y, latent_means, latent_scales, want_scales):
+        """inference on the B200 convolution kernel: no elementwise launch and no concatenation in the loop.
+        * the supports live as fp16 hi / lo planes [latent means | y_hat_0 .. y_hat_4 | scratch slice] (and the same with
+          the latent scales in front); a convolution reads a channel PREFIX of them -- one of the reference's torch.cats;
+        * the last convolution of cc_mean_transforms[i] quantises in its epilogue: mu goes to its slice of `means`,
+          ste_round(y_i - mu) + mu (:257) as fp32 for the lrp step and as planes into the slot behind the supports;
+        * the last convolution of lrp_transforms[i] adds 0.5 tanh(lrp) (:262-264) in its epilogue, writes y_hat_i into its
+          slice of the result and, for i < 5, its planes into the support slot."""
+        from .layers.conv import split_into
+        B, M, H, W = y.shape
+        sl, ms = M // self.num_slices, self.max_support_slices
+        dev = y.device
+        mean_sup = split_into(latent_means, SplitAct.empty(B, M, H, W, 1, dev, channels=M + (ms + 1) * sl))
+        scale_sup = split_into(latent_scales, SplitAct.empty(B, M, H, W, 1, dev, channels=M + ms * sl)) if want_scales else None
+        y_hat_all, means = torch.empty_like(y), torch.empty_like(y)
+        scales = torch.empty_like(y) if want_scales else None
+        yq = torch.empty(B, sl, H, W, device=dev, dtype=y.dtype)
+        for i in range(self.num_slices):
+            k = min(i, ms)
+            lo, hi = i * sl, (i + 1) * sl
+            slot = M + k * sl
+            self.cc_mean_transforms[i](mean_sup.prefix(slot), final_act=ACT_QUANT, aux=y[:, lo:hi], out=yq,
+                                       out2=means[:, lo:hi], emit_into=(mean_sup, slot))
+            if want_scales:
+                self.cc_scale_transforms[i](scale_sup.prefix(slot), out=scales[:, lo:hi])
+            self.lrp_transforms[i](mean_sup.prefix(slot + sl), final_act=ACT_LRP, aux=yq, out=y_hat_all[:, lo:hi],
+                                   emit_into=(mean_sup, slot) if i < ms else None)
+            if i < ms and want_scales:                   # the same planes for the scale branch's supports
+                scale_sup.hi[..., slot:slot + sl] = mean_sup.hi[..., slot:slot + sl]
+                scale_sup.lo[..., slot:slot + sl] = mean_sup.lo[..., slot:slot + sl]
+        return y_hat_all, means, scales
 
     def _slice_loop_in_place(self, y, latent_means, latent_scales, want_scales):
         B, M, H, W = y.shape

@@ -4,10 +4,12 @@
         a = conv_a(x) ; b = conv_b(attn(x, mask)) ; out = a * sigmoid(b) + x          (reference :143-189)
 
 Same constructor, children and state-dict keys as the reference (`conv_a.{0,1,2}.conv.{0,2,4}.*`, `attn.attn.*`,
-`conv_b.{0,1,2}.conv.{0,2,4}.*`, `conv_b.3.*`).  The two residual-unit stacks are ordinary convolutions and stay with
-cuDNN (they are callers of the hot path, not part of it); `attn` is the fused sm_100a masked window attention, and the
-gate + residual `a * sigmoid(b) + x` -- three elementwise kernels and eight tensor passes in the reference -- is ONE
-hand-written kernel (`gate_residual`, csrc/gate.cu), forward and backward.
+`conv_b.{0,1,2}.conv.{0,2,4}.*`, `conv_b.3.*`).  `attn` is the fused sm_100a masked window attention.  In inference the
+residual units run on the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu) as one chain: between two convolutions the
+activation exists only as the fp16 hi / lo planes the consumer's TMA reads, written by the producer's epilogue; GELU, the
+identity add and -- in conv_b's last 1x1 -- the gate + residual `a * sigmoid(b) + x` are epilogues too.  With autograd
+recording the convolutions are torch's and the gate is ONE hand-written kernel (`gate_residual`, csrc/gate.cu), forward
+and backward, instead of the reference's three elementwise kernels.
 Only the names the Journal models use are provided (`conv1x1`, `Win_noShift_Attention`); the reference file's legacy
 blocks (`ResBlockMask`, `AttentionMask`: they reference an undefined `CustomConv2DPyMV3`) are not reproduced.
 """
@@ -18,7 +20,7 @@ from torch.autograd import Function
 from .. import _abi
 from .masked_win_attention import *  # noqa: F401,F403  (the reference file star-imports it too, :6)
 from .masked_win_attention import WinBasedAttention
-from .conv import ACT_GELU, Conv2d, ConvStack
+from .conv import ACT_GATE, ACT_GELU, Conv2d, ConvStack, SplitAct
 
 
 def conv1x1(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
@@ -89,9 +91,10 @@ class Win_noShift_Attention(nn.Module):
                 )
                 self.relu = nn.GELU()
 
-            def forward(self, x):
-                # conv -> + identity -> GELU: the add and the activation ride in the last convolution's epilogue
-                return self.conv(x, residual=x, final_act=ACT_GELU)
+            def forward(self, x, **kw):
+                # conv -> + identity -> GELU: the add and the activation ride in the last convolution's epilogue.
+                # x may be a SplitAct (planes for the first 1x1, dense tensor for the identity); kw: emit_ps / want_dense
+                return self.conv(x, residual=x.dense if isinstance(x, SplitAct) else x, final_act=ACT_GELU, **kw)
 
         self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
 
@@ -105,7 +108,15 @@ class Win_noShift_Attention(nn.Module):
         )
 
     def forward(self, x, mask):
-        a = self.conv_a(x)
+        if self.conv_a[0].conv[0].input_ps(x) is None:            # training / uncovered: module by module
+            a = self.conv_a(x)
+            b = self.attn(x, mask)
+            b = self.conv_b(b)
+            return gate_residual(a, b, x)
+        a = x
+        for j in range(3):                                        # dense (identity of the next unit) + planes (its 1x1)
+            a = self.conv_a[j](a, emit_ps=1 if j < 2 else 0)
         b = self.attn(x, mask)
-        b = self.conv_b(b)
-        return gate_residual(a, b, x)
+        for j in range(3):                                        # the last unit feeds only the closing 1x1: planes alone
+            b = self.conv_b[j](b, emit_ps=1, want_dense=j < 2)
+        return self.conv_b[3](b, act=ACT_GATE, aux=a, residual=x)

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from .. import _abi
 
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUANT, ACT_LRP, ACT_GATE = 0, 1, 2, 3, 4, 5
 
 
 def _act_of(m):
@@ -34,6 +34,54 @@ def _act_of(m):
 
 def _apply_act(y, act):
     return F.gelu(y) if act == ACT_GELU else F.relu(y) if act == ACT_RELU else y
+
+
+class SplitAct:
+    """An activation as the fp16 hi / lo planes a convolution's TMA reads: int16 tensors [B][ps*ps][H/ps][W/ps][cstride]
+    (channels last, ps = 2: the four pixel-parity planes a stride-2 convolution wants).  Written by the epilogue of the
+    convolution that produced the activation (conv_forward_ex, out_hi / out_lo), so that between two convolutions the
+    tensor crosses HBM once, as 4 bytes per element, instead of fp32 out + fp32 in + split out.  `C` channels starting at
+    channel 0 are valid; `dense` optionally carries the fp32 NCHW tensor as well (residual connections need it)."""
+
+    __slots__ = ("hi", "lo", "B", "C", "H", "W", "ps", "dense")
+
+    def __init__(self, hi, lo, C, H, W, ps, dense=None):
+        self.hi, self.lo, self.B, self.C, self.H, self.W, self.ps, self.dense = hi, lo, hi.shape[0], C, H, W, ps, dense
+
+    @staticmethod
+    def empty(B, C, H, W, ps, device, channels=None):
+        cs = (max(C, channels or 0) + 7) // 8 * 8
+        shape = (B, ps * ps, H // ps, W // ps, cs)
+        return SplitAct(torch.empty(shape, dtype=torch.int16, device=device), torch.empty(shape, dtype=torch.int16, device=device),
+                        C, H, W, ps)
+
+    @property
+    def cstride(self):
+        return self.hi.shape[-1]
+
+    @property
+    def shape(self):
+        return (self.B, self.C, self.H, self.W)
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def prefix(self, C):
+        """the first C channels (same buffers): a torch.cat support of the slice loop"""
+        return SplitAct(self.hi, self.lo, C, self.H, self.W, self.ps, None)
+
+
+def split_into(x, dst: SplitAct, coff=0):
+    """write the fp16 hi / lo planes of the fp32 NCHW tensor x into channels [coff, coff + C) of dst (conv_act_split)"""
+    lib = _abi.load()
+    B, C, H, W = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and _dense_nchw(x)) or (B, H, W) != (dst.B, dst.H, dst.W):
+        raise RuntimeError(f"split_into: bad source {tuple(x.shape)} / {x.stride()} for planes of {dst.shape}")
+    with torch.cuda.device(x.device):
+        _abi.check(lib.conv_act_split(x.data_ptr(), x.stride(0), B, C, H, W, dst.ps, dst.hi.data_ptr(), dst.lo.data_ptr(),
+                                      dst.cstride, coff, _abi.stream_handle()), "conv_act_split")
+    return dst
 
 
 class _WeightImage:
@@ -66,38 +114,167 @@ class _WeightImage:
 
 
 def _fast_ok(x, *tensors):
+    if isinstance(x, SplitAct):
+        return True
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0):
         return False
     if torch.is_grad_enabled() and (x.requires_grad or any(t is not None and t.requires_grad for t in tensors)):
         return False
-    C, H, W = x.shape[1:]
-    return x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W and x.stride(0) >= C * H * W
+    return _dense_nchw(x)
 
 
-def _run(x, weight, bias, image, kind, k, stride, act, residual, cout, ho, wo):
+def _run(x, bias, image, kind, k, stride, act, residual, cout, ho, wo, emit_ps=0, want_dense=True, aux=None, out=None,
+         out2=None, emit_into=None):
+    """one conv_forward_ex call.  x: fp32 NCHW tensor or SplitAct.  Returns the dense result, or -- with emit_ps / emit_into
+    -- a SplitAct (carrying the dense result too when want_dense)."""
     lib = _abi.load()
     B, cin, H, W = x.shape
-    out = torch.empty(B, cout, ho, wo, device=x.device, dtype=x.dtype)
-    nsplit = int(lib.conv_split_bytes(B, cin, H, W))
-    split = torch.empty(2, nsplit, dtype=torch.uint8, device=x.device)
+    dev = x.device
+    if isinstance(x, SplitAct):
+        need_ps = 2 if (kind == 0 and stride == 2) else 1
+        if x.ps != need_ps:
+            raise RuntimeError(f"conv: split input has ps {x.ps}, this convolution needs {need_ps}")
+        xp, xbs, in_hi, in_lo, in_cs = None, 0, x.hi, x.lo, x.cstride
+    else:
+        nsplit = int(lib.conv_split_bytes(B, cin, H, W))
+        scratch = torch.empty(2, nsplit, dtype=torch.uint8, device=dev)
+        xp, xbs, in_hi, in_lo, in_cs = x.data_ptr(), x.stride(0), scratch[0], scratch[1], 0
+    if out is None and want_dense:
+        out = torch.empty(B, cout, ho, wo, device=dev, dtype=torch.float32)
+    if out is not None and (tuple(out.shape) != (B, cout, ho, wo) or not _dense_nchw(out)):
+        raise RuntimeError(f"conv: bad output tensor {tuple(out.shape)} / {out.stride()}")
     if residual is not None:
-        if residual.shape != out.shape:
-            raise RuntimeError(f"conv: residual shape {tuple(residual.shape)} != output shape {tuple(out.shape)}")
+        if tuple(residual.shape) != (B, cout, ho, wo):
+            raise RuntimeError(f"conv: residual shape {tuple(residual.shape)} != output shape {(B, cout, ho, wo)}")
         residual = residual.contiguous()
+    for name, t in (("aux", aux), ("out2", out2)):
+        if t is not None and (tuple(t.shape) != (B, cout, ho, wo) or not _dense_nchw(t)):
+            raise RuntimeError(f"conv: bad {name} tensor {tuple(t.shape)} / {t.stride()}")
+    sp, coff = None, 0
+    if emit_into is not None:
+        sp, coff = emit_into
+    elif emit_ps:
+        sp = SplitAct.empty(B, cout, ho, wo, emit_ps, dev)
     b = None if bias is None else bias.detach().contiguous()
-    with torch.cuda.device(x.device):
-        _abi.check(lib.conv_forward(x.data_ptr(), x.stride(0), _abi.ptr(b), _abi.ptr(residual), out.data_ptr(),
-                                    cout * ho * wo, image.data_ptr(), split[0].data_ptr(), split[1].data_ptr(), kind, B, cin,
-                                    cout, H, W, k, stride, act, _abi.stream_handle()), "conv_forward")
+    with torch.cuda.device(dev):
+        _abi.check(lib.conv_forward_ex(
+            xp, xbs, in_hi.data_ptr(), in_lo.data_ptr(), in_cs, _abi.ptr(b), _abi.ptr(residual), _abi.ptr(out),
+            0 if out is None else out.stride(0), _abi.ptr(aux), 0 if aux is None else aux.stride(0), _abi.ptr(out2),
+            0 if out2 is None else out2.stride(0), None if sp is None else sp.hi.data_ptr(),
+            None if sp is None else sp.lo.data_ptr(), 0 if sp is None else sp.ps, 0 if sp is None else sp.cstride, coff,
+            image.data_ptr(), kind, B, cin, cout, H, W, k, stride, act, _abi.stream_handle()), "conv_forward_ex")
+    if sp is None:
+        return out
+    if emit_into is None:
+        sp.dense = out
+        return sp
     return out
 
 
-class Conv2d(nn.Conv2d):
+def _dense_nchw(t):
+    C, H, W = t.shape[1:]
+    return t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W and t.stride(0) >= C * H * W
+
+
+class _ShapeOnly:
+    """stands in for a tensor that does not exist yet when a consumer is asked whether it will take the fast path"""
+
+    is_cuda, dtype, requires_grad = True, torch.float32, False
+
+    def __init__(self, shape, device):
+        self.shape, self.device = tuple(shape), device
+
+    def dim(self):
+        return len(self.shape)
+
+    def numel(self):
+        n = 1
+        for v in self.shape:
+            n *= v
+        return n
+
+    def stride(self, i):
+        st = [1] * len(self.shape)
+        for j in range(len(self.shape) - 2, -1, -1):
+            st[j] = st[j + 1] * self.shape[j + 1]
+        return st[i]
+
+
+def _fallback(x):
+    if isinstance(x, SplitAct):
+        if x.dense is None:
+            raise RuntimeError("conv: a split activation without its dense tensor reached a convolution outside the fast path")
+        return x.dense
+    return x
+
+
+class _FastConv:
+    """what Conv2d and ConvTranspose2d share: the cached weight image, its invalidation, and the fast-path call"""
+
+    def _init_fast(self):
+        self._img = _WeightImage()
+
+    def input_ps(self, x):
+        """parity planes this layer wants its input split into (1 or 2) if it will take the fast path on x, else None"""
+        if not (_fast_ok(x, self.weight, self.bias) and self._covered(x)):
+            return None
+        return 2 if (self._kind == 0 and self.stride[0] == 2) else 1
+
+    def _fast(self, x, act, residual, **kw):
+        k, s = self.kernel_size[0], self.stride[0]
+        img = self._img.get(self.weight, self._kind, k, s)
+        if self._kind == 0:
+            ho, wo = x.shape[2] // s, x.shape[3] // s
+        else:
+            ho, wo = 2 * x.shape[2], 2 * x.shape[3]
+        return _run(x, self.bias, img, self._kind, k, s, act, residual, self.out_channels, ho, wo, **kw)
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        if "_img" in self.__dict__:
+            self._img.invalidate()
+        return out
+
+    def _load_from_state_dict(self, *a, **kw):
+        super()._load_from_state_dict(*a, **kw)
+        if "_img" in self.__dict__:
+            self._img.invalidate()
+
+
+_EPI_KW = ("emit_ps", "want_dense", "aux", "out", "out2", "emit_into")
+
+
+def _plain_epilogue(y, act, residual, kw):
+    """the library path's version of the fused epilogues (training, uncovered geometries)"""
+    aux = kw.get("aux")
+    if act == ACT_QUANT:
+        from .. import quant
+        if kw.get("out2") is not None:
+            kw["out2"].copy_(y)
+        y = quant.quantize_offset(aux, y)
+    elif act == ACT_LRP:
+        y = aux + 0.5 * torch.tanh(y)
+    elif act == ACT_GATE:
+        y = aux * torch.sigmoid(y) + residual
+    else:
+        if residual is not None:
+            y = y + residual
+        y = _apply_act(y, act)
+    if kw.get("out") is not None:
+        kw["out"].copy_(y)
+        y = kw["out"]
+    if kw.get("emit_ps") or kw.get("emit_into") is not None:
+        raise RuntimeError("conv: split emission was requested from a convolution outside the fast path")
+    return y
+
+
+class Conv2d(_FastConv, nn.Conv2d):
     min_channels = 8          # narrower ends go to the library (see _covered); tests set 1 to exercise the kernel there
+    _kind = 0
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self._img = _WeightImage()
+        self._init_fast()
 
     def _covered(self, x):
         k, s = self.kernel_size[0], self.stride[0]
@@ -110,91 +287,69 @@ class Conv2d(nn.Conv2d):
                 # the library's fp32 kernels there, so they stay with it
                 and self.in_channels >= self.min_channels and self.out_channels >= self.min_channels)
 
-    def forward(self, x, act=ACT_NONE, residual=None):
-        if _fast_ok(x, self.weight, self.bias, residual) and self._covered(x):
-            k, s = self.kernel_size[0], self.stride[0]
-            img = self._img.get(self.weight, 0, k, s)
-            return _run(x, self.weight, self.bias, img, 0, k, s, act, residual, self.out_channels, x.shape[2] // s,
-                        x.shape[3] // s)
-        y = super().forward(x)
-        if residual is not None:
-            y = y + residual
-        return _apply_act(y, act)
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
-        return out
-
-    def _load_from_state_dict(self, *a, **kw):
-        super()._load_from_state_dict(*a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
+    def forward(self, x, act=ACT_NONE, residual=None, **kw):
+        if _fast_ok(x, self.weight, self.bias, residual, kw.get("aux")) and self._covered(x):
+            return self._fast(x, act, residual, **kw)
+        return _plain_epilogue(super().forward(_fallback(x)), act, residual, kw)
 
 
-class ConvTranspose2d(nn.ConvTranspose2d):
+class ConvTranspose2d(_FastConv, nn.ConvTranspose2d):
+    min_channels = 8
+    _kind = 1
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self._img = _WeightImage()
+        self._init_fast()
 
     def _covered(self, x):
         return (tuple(self.kernel_size) == (5, 5) and tuple(self.stride) == (2, 2) and tuple(self.padding) == (2, 2)
                 and tuple(self.output_padding) == (1, 1) and tuple(self.dilation) == (1, 1) and self.groups == 1
-                and x.shape[1] == self.in_channels)
+                and x.shape[1] == self.in_channels and self.in_channels >= self.min_channels
+                and self.out_channels >= self.min_channels)
 
-    def forward(self, x, output_size=None, act=ACT_NONE, residual=None):
-        if output_size is None and _fast_ok(x, self.weight, self.bias, residual) and self._covered(x):
-            img = self._img.get(self.weight, 1, 5, 2)
-            return _run(x, self.weight, self.bias, img, 1, 5, 2, act, residual, self.out_channels, 2 * x.shape[2],
-                        2 * x.shape[3])
-        y = super().forward(x, output_size)
-        if residual is not None:
-            y = y + residual
-        return _apply_act(y, act)
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
-        return out
-
-    def _load_from_state_dict(self, *a, **kw):
-        super()._load_from_state_dict(*a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
+    def forward(self, x, output_size=None, act=ACT_NONE, residual=None, **kw):
+        if output_size is None and _fast_ok(x, self.weight, self.bias, residual, kw.get("aux")) and self._covered(x):
+            return self._fast(x, act, residual, **kw)
+        return _plain_epilogue(super().forward(_fallback(x), output_size), act, residual, kw)
 
 
 class ConvStack(nn.Sequential):
     """nn.Sequential whose forward folds the GELU / ReLU that follows a convolution -- directly, or after the PixelShuffle
-    of a sub-pixel convolution (an elementwise function commutes with the shuffle) -- into that convolution's epilogue.
-    Children and state-dict keys are those of the plain Sequential."""
+    of a sub-pixel convolution (an elementwise function commutes with the shuffle) -- into that convolution's epilogue, and
+    hands the activation between two adjacent convolutions over as fp16 hi / lo planes written by the producer's epilogue
+    (SplitAct) instead of an fp32 tensor.  Children and state-dict keys are those of the plain Sequential.
 
-    def forward(self, x, residual=None, final_act=ACT_NONE):
+    forward(x, residual=None, final_act=ACT_NONE, **epilogue options of the LAST convolution: emit_ps, want_dense, aux, out,
+    out2, emit_into); x may be a SplitAct."""
+
+    def forward(self, x, residual=None, final_act=ACT_NONE, **kw):
         mods = list(self)
         i = 0
         while i < len(mods):
             m = mods[i]
-            last = i == len(mods) - 1
             nxt = _act_of(mods[i + 1]) if i + 1 < len(mods) else None
+            step = 2 if nxt is not None else 1
+            last = i + step >= len(mods)
             if isinstance(m, (Conv2d, ConvTranspose2d)):
-                if nxt is not None:
-                    x = m(x, act=nxt)
-                    i += 2
-                elif last:
-                    x = m(x, act=final_act, residual=residual)
-                    i += 1
+                if last:
+                    x = m(x, act=nxt if nxt is not None else final_act, residual=residual, **kw)
                 else:
-                    x = m(x)
-                    i += 1
+                    # the consumer is the next module: if it is a convolution on the fast path, feed it split planes only
+                    consumer, ps = mods[i + step], None
+                    if isinstance(consumer, (Conv2d, ConvTranspose2d)) and m.input_ps(x) is not None:
+                        s = m.stride[0]
+                        oshape = (x.shape[0], m.out_channels) + ((x.shape[2] // s, x.shape[3] // s) if m._kind == 0
+                                                                 else (2 * x.shape[2], 2 * x.shape[3]))
+                        ps = consumer.input_ps(_ShapeOnly(oshape, x.device))
+                    if ps is not None:
+                        x = m(x, act=nxt or ACT_NONE, emit_ps=ps, want_dense=False)
+                    else:
+                        x = m(x, act=nxt or ACT_NONE)
+                i += step
             elif isinstance(m, nn.Sequential) and len(m) == 2 and isinstance(m[0], Conv2d) and isinstance(m[1], nn.PixelShuffle):
-                if nxt is not None:
-                    x = m[1](m[0](x, act=nxt))
-                    i += 2
-                else:
-                    x = m[1](m[0](x))
-                    i += 1
+                x = m[1](m[0](x, act=nxt or ACT_NONE))
+                i += step
             else:
-                x = m(x)
+                x = m(_fallback(x))
                 i += 1
         return x

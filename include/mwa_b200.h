@@ -255,6 +255,34 @@ MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bi
                          int64_t out_batch_stride, const void* image, void* split_hi, void* split_lo, int kind, int B,
                          int Cin, int Cout, int H, int W, int k, int stride, int act, void* stream);
 
+/* conv_forward_ex : the same kernel with the chaining and epilogue options the transforms use so that an activation
+ *   crosses HBM once between two convolutions and the elementwise steps around the slice loop cost no launch:
+ *   input   x != NULL: fp32 NCHW as above (in_hi / in_lo are scratch of conv_split_bytes each);
+ *           x == NULL: in_hi / in_lo already hold the fp16 hi / lo planes [B][ps*ps][H/ps][W/ps][in_cstride] (ps = 2 for a
+ *           stride-2 convolution, else 1) written by a previous call's out_hi / out_lo; the first Cin channels are read
+ *           (a channel PREFIX of a wider buffer is a valid input: the reference's torch.cat supports,
+ *           models/AutoEncoderRGB_Journal.py:243-259, are prefixes of one buffer);
+ *   output  out (fp32 NCHW, may be NULL) and / or out_hi / out_lo: the result as hi / lo planes for the NEXT convolution
+ *           (out_ps = that convolution's ps) at channel offset out_coff of a buffer with channel pitch out_cstride
+ *           (multiples of 8; channels [Cout, round_up(Cout, 8)) are written as zeros);
+ *   act     0 none, 1 GELU, 2 ReLU (after bias + residual), and with v = conv(x) + bias:
+ *           3 quantise : out = ste_round(aux - v) + v, out2 (optional) = v      (models/AutoEncoderRGB_Journal.py:257:
+ *                        v = mu of the slice, aux = y_slice; bit-identical to quantize_offset_forward on the same v)
+ *           4 lrp      : out = aux + 0.5 * tanh(v)                               (:262-264; aux may alias out)
+ *           5 gate     : out = aux * sigmoid(v) + residual                       (layers/Masked_Attention.py:186-188:
+ *                        v = conv_b's last 1x1, aux = a, residual = x)
+ *           aux: fp32 NCHW (B, Cout, Ho, Wo) with batch stride aux_batch_stride; out2 likewise. */
+/* conv_act_split : fp32 NCHW (B, C, H, W; batch stride x_batch_stride) -> the fp16 hi / lo planes of conv_forward_ex's
+ *   x == NULL input, at channel offset out_coff of buffers with channel pitch out_cstride (how an activation that was NOT
+ *   produced by one of these convolutions -- GDN, attention, a PixelShuffle -- enters a chain or a support buffer). */
+MWA_API int conv_act_split(const float* x, int64_t x_batch_stride, int B, int C, int H, int W, int ps, void* out_hi,
+                           void* out_lo, int out_cstride, int out_coff, void* stream);
+MWA_API int conv_forward_ex(const float* x, int64_t x_batch_stride, void* in_hi, void* in_lo, int in_cstride,
+                            const float* bias, const float* residual, float* out, int64_t out_batch_stride,
+                            const float* aux, int64_t aux_batch_stride, float* out2, int64_t out2_batch_stride,
+                            void* out_hi, void* out_lo, int out_ps, int out_cstride, int out_coff, const void* image,
+                            int kind, int B, int Cin, int Cout, int H, int W, int k, int stride, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

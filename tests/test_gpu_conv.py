@@ -92,3 +92,122 @@ def test_conv_stack_fuses_activations(pkg, cuda_dev):
         ref = plain(x)
         y = stack.to(cuda_dev)(x.to(cuda_dev))
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+
+
+def _cpu_stack(stack):
+    return torch.nn.Sequential(*[m for m in stack])
+
+
+def test_chained_stack_hands_planes_between_convolutions(pkg, cuda_dev):
+    """stride 2 -> 1 -> 2 chain (h_a of the model): every intermediate exists only as fp16 hi / lo planes written by the
+    producer's epilogue (ps = 1 and ps = 2 layouts); result against torch CPU fp32"""
+    conv = pkg.conv
+    torch.manual_seed(1)
+    g = torch.nn.GELU
+    stack = conv.ConvStack(conv.Conv2d(80, 96, 3, stride=2, padding=1), g(), conv.Conv2d(96, 72, 3, padding=1), g(),
+                           conv.Conv2d(72, 64, 3, stride=2, padding=1), g(), conv.Conv2d(64, 40, 1))
+    x = torch.randn(2, 80, 32, 48)
+    with torch.no_grad():
+        ref = _cpu_stack(stack)(x)
+        stack = stack.to(cuda_dev)
+        calls = []
+        orig = conv._run
+
+        def spy(xin, *a, **kw):
+            calls.append((type(xin).__name__, kw.get("emit_ps", 0), kw.get("want_dense", True)))
+            return orig(xin, *a, **kw)
+
+        conv._run = spy
+        try:
+            y = stack(x.to(cuda_dev))
+        finally:
+            conv._run = orig
+    assert calls == [("Tensor", 1, False), ("SplitAct", 2, False), ("SplitAct", 1, False), ("SplitAct", 0, True)]
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+
+
+def test_planes_from_the_epilogue_equal_planes_from_the_split_kernel(pkg, cuda_dev):
+    """a convolution fed by its producer's planes gives bit-identical results to one fed the producer's fp32 output"""
+    conv = pkg.conv
+    torch.manual_seed(2)
+    a, b = conv.Conv2d(48, 56, 3, padding=1).to(cuda_dev), conv.Conv2d(56, 24, 3, padding=1).to(cuda_dev)
+    x = torch.randn(2, 48, 20, 28, device=cuda_dev)
+    with torch.no_grad():
+        mid = a(x, act=1)
+        y_dense = b(mid)
+        sp = a(x, act=1, emit_ps=1, want_dense=True)
+        assert torch.equal(sp.dense, mid)
+        y_planes = b(sp)
+    assert torch.equal(y_dense, y_planes)
+
+
+def test_quantise_and_lrp_epilogues_are_bit_identical_to_the_rounding_kernels(pkg, cuda_dev):
+    """models/AutoEncoderRGB_Journal.py:257, :262-264 as epilogues of the slice loop's last convolutions"""
+    conv, quant = pkg.conv, pkg.quant
+    torch.manual_seed(3)
+    m = conv.Conv2d(128, 8, 3, padding=1).to(cuda_dev)
+    x = torch.randn(2, 128, 16, 24, device=cuda_dev)
+    ybig = torch.randn(2, 80, 16, 24, device=cuda_dev) * 4
+    y_slice = ybig[:, 16:24]
+    with torch.no_grad():
+        mu = m(x)
+        want = quant.quantize_offset(y_slice, mu)
+        got, mu2 = torch.empty_like(mu), torch.empty_like(mu)
+        sup = conv.SplitAct.empty(2, 96, 16, 24, 1, cuda_dev)
+        sup.hi.zero_(); sup.lo.zero_()
+        m(x, act=conv.ACT_QUANT, aux=y_slice, out=got, out2=mu2, emit_into=(sup, 88))
+        assert torch.equal(mu2, mu)
+        assert torch.equal(got, want)
+        # the planes written behind the supports are the hi / lo halves of the same values
+        hi = sup.hi[:, 0, :, :, 88:96].view(torch.float16).float().permute(0, 3, 1, 2)
+        lo = sup.lo[:, 0, :, :, 88:96].view(torch.float16).float().permute(0, 3, 1, 2)
+        torch.testing.assert_close(hi + lo, want, rtol=2e-6, atol=1e-7)     # fp16 hi + lo: ~2^-22 relative
+        assert int(sup.hi[..., :88].abs().max()) == 0
+        want_lrp = quant.lrp_add(want, mu)
+        got_lrp = torch.empty_like(mu)
+        m(x, act=conv.ACT_LRP, aux=want, out=got_lrp)
+        assert torch.equal(got_lrp, want_lrp)
+        inplace = want.clone()
+        m(x, act=conv.ACT_LRP, aux=inplace, out=inplace)
+        assert torch.equal(inplace, want_lrp)
+
+
+def test_gate_epilogue_matches_the_gate_kernel(pkg, cuda_dev):
+    """layers/Masked_Attention.py:186-188 as the epilogue of conv_b's last 1x1"""
+    conv = pkg.conv
+    torch.manual_seed(4)
+    m = conv.Conv2d(80, 80, 1).to(cuda_dev)
+    x, a, ident = (torch.randn(2, 80, 16, 24, device=cuda_dev) for _ in range(3))
+    with torch.no_grad():
+        want = pkg.Masked_Attention.gate_residual(a, m(x), ident)
+        got = m(x, act=conv.ACT_GATE, aux=a, residual=ident)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_wrapper_chain_equals_module_by_module(pkg, cuda_dev):
+    """Win_noShift_Attention in inference (planes between the residual units' convolutions, gate as an epilogue) against
+    the same module run convolution by convolution"""
+    torch.manual_seed(5)
+    w = pkg.Masked_Attention.Win_noShift_Attention(80, 8, 4, 2).to(cuda_dev)
+    x = torch.randn(2, 80, 16, 24, device=cuda_dev)
+    alpha = (torch.rand(2, 1, 16, 24, device=cuda_dev) > 0.3).float()
+    with torch.no_grad():
+        y = w(x, alpha)
+        a = w.conv_a(x)
+        b = w.conv_b(w.attn(x, alpha))
+        ref = pkg.Masked_Attention.gate_residual(a, b, x)
+    torch.testing.assert_close(y, ref, rtol=1e-6, atol=1e-6)
+
+
+def test_fused_slice_loop_equals_the_loop_with_separate_rounding_launches(pkg, cuda_dev):
+    """models/AutoEncoderRGB_Journal.py:240-266: planes as supports + quantise / lrp epilogues against the same
+    convolutions with torch-style supports and the rounding kernels: identical bits"""
+    torch.manual_seed(6)
+    model = pkg.codec.AutoEncoder().to(cuda_dev).eval()
+    y = torch.randn(2, 80, 16, 24, device=cuda_dev) * 3
+    lm, ls = torch.randn_like(y), torch.rand_like(y) + 0.2
+    with torch.no_grad():
+        got = model._slice_loop_fused(y, lm, ls, True)
+        want = model._slice_loop_in_place(y, lm, ls, True)
+    for g, w, name in zip(got, want, ("y_hat", "means", "scales")):
+        assert torch.equal(g, w), name

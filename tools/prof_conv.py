@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Launch one convolution of the codec a few times (profiling target for ncu):
+   python tools/prof_conv.py ru1x1b|ru3x3|ru1x1a|dse3x3|cc0|cc2|cc4|x2|dx3|dx4"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mwa_b200 as pkg  # noqa: E402
+
+B, H, W = 16, 512, 768
+# kind, cin, cout, k, stride, h, w, act, residual
+CASES = {
+    "ru1x1a": ("conv", 192, 96, 1, 1, H // 4, W // 4, 1, False),
+    "ru3x3": ("conv", 96, 96, 3, 1, H // 4, W // 4, 1, False),
+    "ru1x1b": ("conv", 96, 192, 1, 1, H // 4, W // 4, 1, True),
+    "dse3x3": ("conv", 32, 32, 3, 1, H, W, 2, False),
+    "cc0": ("conv", 120, 224, 3, 1, H // 8, W // 8, 1, False),
+    "cc2": ("conv", 224, 128, 3, 1, H // 8, W // 8, 1, False),
+    "cc4": ("conv", 128, 8, 3, 1, H // 8, W // 8, 0, False),
+    "x2": ("conv", 192, 192, 5, 2, H // 2, W // 2, 0, False),
+    "dx3": ("deconv", 192, 192, 5, 2, H // 4, W // 4, 0, False),
+    "dx4": ("deconv", 192, 3, 5, 2, H // 2, W // 2, 0, False),
+}
+what = sys.argv[1]
+kind, cin, cout, k, s, h, w, act, res = CASES[what]
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+with torch.no_grad():
+    x = torch.randn(B, cin, h, w, device=dev)
+    if kind == "conv":
+        m = pkg.conv.Conv2d(cin, cout, k, stride=s, padding=k // 2).to(dev)
+    else:
+        m = pkg.conv.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1).to(dev)
+    y = m(x, act=act)
+    r = torch.randn_like(y) if res else None
+    for _ in range(4):
+        y = m(x, act=act, residual=r)
+torch.cuda.synchronize()
+print("done", float(y.abs().mean()))
