@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import quant
 from .layers.GDN import GDN
 from .layers.Masked_Attention import Win_noShift_Attention, conv3x3
-from .layers.conv import ACT_LRP, ACT_QUANT, ACT_RELU, Conv2d, ConvStack, ConvTranspose2d, SplitAct
+from .layers.conv import ACT_ADD2, ACT_LRP, ACT_QUANT, ACT_RELU, Conv2d, ConvStack, ConvTranspose2d, SplitAct
 from .layers.SupplyMask import SupplyMaskToTransform, alpha_pyramid
 
 
@@ -68,12 +68,17 @@ class DSE(nn.Module):
         self.output_conv = Conv2d(n, 3, 1)
 
     def forward(self, x):
-        first = self.input_conv(x)
-        if self.enh1.conv1.input_ps(first) is None:
+        if self.input_conv.input_ps(x) is None:
+            first = self.input_conv(x)
             t = self.enh3(self.enh2(self.enh1(first)))
-        else:
-            t = self.enh3(self.enh2(self.enh1(first, emit_ps=1), emit_ps=1))
-        return self.output_conv(t + first, residual=x)
+            return self.output_conv(t + first, residual=x)
+        # one chain: every intermediate that only feeds a convolution exists as planes alone; the last enhancement block's
+        # second convolution adds its identity AND the skip `first`, and hands planes to the output convolution
+        first = self.input_conv(x, emit_ps=1)
+        t = self.enh2(self.enh1(first, emit_ps=1), emit_ps=1)
+        h = self.enh3.conv1(t, act=ACT_RELU, emit_ps=1, want_dense=False)
+        s = self.enh3.conv2(h, act=ACT_ADD2, residual=t.dense, aux=first.dense, emit_ps=1, want_dense=False)
+        return self.output_conv(s, residual=x)
 
 
 class Analysis_transform(nn.Module):

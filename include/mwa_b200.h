@@ -271,6 +271,8 @@ MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bi
  *           4 lrp      : out = aux + 0.5 * tanh(v)                               (:262-264; aux may alias out)
  *           5 gate     : out = aux * sigmoid(v) + residual                       (layers/Masked_Attention.py:186-188:
  *                        v = conv_b's last 1x1, aux = a, residual = x)
+ *           6 add2     : out = (v + residual) + aux                              (layers/TransformRGB.py:27, :47: the last
+ *                        enhancement block's identity and the DSE skip in one epilogue)
  *           aux: fp32 NCHW (B, Cout, Ho, Wo) with batch stride aux_batch_stride; out2 likewise. */
 /* conv_act_split : fp32 NCHW (B, C, H, W; batch stride x_batch_stride) -> the fp16 hi / lo planes of conv_forward_ex's
  *   x == NULL input, at channel offset out_coff of buffers with channel pitch out_cstride (how an activation that was NOT
