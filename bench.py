@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload "C2-forward" (BASELINE.json configs[1], per GPU): the full AutoEncoderRGB_Journal encode + decode forward
-(<package>/codec.py: the reference's module tree on the B200 modules, convolutions through cuDNN in fp32) on a batch of
+(<package>/codec.py: the reference's module tree on the B200 modules, convolutions on the tcgen05 kernel) on a batch of
 16 synthetic 768x512 RGBA images, random-init weights.  A "step" is one forward of the batch incl. the alpha pyramids.
 value = images/s = 16 * N / step time (device time, max over ranks); e2e = the same with the RGBA batch coming from
 pinned host memory and x_hat going back, copies inside the timed region.  Images are independent -> ranks shard by image
@@ -292,9 +292,10 @@ class OpTimer:
         return {n: statistics.mean(a.elapsed_time(b) for a, b in ev) for n, ev in self.events.items() if ev}
 
 
-# our kernels per forward: 2 alpha pyramids (2 + 1 launches), 4 attention calls x (scan, compact, dropped-window copy,
-# main), 6 GDN, 4 gates, z rounding + 10 x (quantise, lrp add)
-LAUNCHES_PER_FORWARD = 3 + 4 * 4 + 6 + 4 + 1 + 20
+# hot-path kernels per forward: 2 alpha pyramids (2 + 1 launches), 4 attention calls x (scan, compact, dropped-window copy,
+# main), 6 GDN, z rounding; the gate, the slice quantisation and the lrp update are convolution epilogues.  The
+# convolution launches (kernel + plane-split launches) are counted live by the binding (_abi.launch_count).
+LAUNCHES_PER_FORWARD = 3 + 4 * 4 + 6 + 1
 # round 1's hot-path-only step: 4 attention calls x 4 + 6 GDN + 22 rounding launches
 LAUNCHES_PER_HOTPATH_STEP = 4 * 4 + 6 + (2 + 20)
 
@@ -309,7 +310,8 @@ def traffic_table():
         return json.load(f)
 
 
-def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None, want_e2e=True, sampler=None):
+def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None, want_e2e=True, sampler=None, library_convs=False):
+    pkg.conv.USE_KERNEL = not library_convs
     torch.backends.cudnn.allow_tf32 = bool(tf32_convs)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(234)
@@ -333,6 +335,9 @@ def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None
             while not sampler.rows and time.time() < t_dead and sampler.proc is not None:
                 step()
                 torch.cuda.synchronize()
+        n0 = pkg._abi.launch_count
+        step()
+        conv_launches = pkg._abi.launch_count - n0               # convolution kernels + plane splits of one forward
         timer.on = True
         ms_per_step, t0, t1 = timed_steps(step, steps, 0, D)
         timer.on = False
@@ -403,7 +408,7 @@ def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None
     del net
     torch.cuda.empty_cache()
     return dict(value=value, ms_per_step=ms_per_step, per_op_ms=per_op, rooflines=roofs, e2e=e2e, clocks=clocks,
-                hot_path_ms_per_step=hot_ms, hot_path_share=hot_ms / ms_per_step, steps=steps)
+                hot_path_ms_per_step=hot_ms, hot_path_share=hot_ms / ms_per_step, steps=steps, conv_launches=conv_launches)
 
 
 # ------------------------------------------------------------------------------------------------ hot path only
@@ -627,10 +632,14 @@ def main():
     fwd = leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, want_e2e=not args.no_e2e, sampler=sampler)
     extra = {}
     if "tf32" in legs:
-        t = leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=True, steps=max(3, min(args.steps, 10)), want_e2e=False)
-        extra["forward_tf32_convs"] = {"value": t["value"], "unit": UNIT, "ms_per_step": t["ms_per_step"], "steps": t["steps"],
-                                       "note": "same forward with torch.backends.cudnn.allow_tf32 = True (torch's default, i.e. what "
-                                               "the unmodified reference runs on a GPU); our kernels unchanged"}
+        for key, tf32 in (("forward_library_convs_fp32", False), ("forward_library_convs_tf32", True)):
+            t = leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=tf32, steps=max(3, min(args.steps, 5)), want_e2e=False,
+                            library_convs=True)
+            extra[key] = {"value": t["value"], "unit": UNIT, "ms_per_step": t["ms_per_step"], "steps": t["steps"],
+                          "note": "same forward with every convolution through torch.nn.functional (cuDNN, "
+                                  + ("allow_tf32 = True: torch's default, what the unmodified reference runs on a GPU"
+                                     if tf32 else "fp32, TF32 off: the reference's arithmetic") + "); the hot-path kernels unchanged"}
+        pkg.conv.USE_KERNEL = True
     if "hotpath" in legs:
         extra["hotpath"] = leg_hotpath(pkg, dev, rank, world, D, args, pk, steps=max(5, min(args.steps, 50)))
     if "config5" in legs:
@@ -664,13 +673,15 @@ def main():
             roofline["peak_source"] = (pk["source"] + " (MEASURED_PEAKS.json burst figures)") if pk["source"] == "measured" \
                 else "fallback (B200_PROFILING.md)"
         gdn_r = next((r for r in roofs if r["kernel"].startswith("GDN")), None)
-        hot_launches = LAUNCHES_PER_FORWARD * fwd["steps"]
+        per_forward = LAUNCHES_PER_FORWARD + fwd["conv_launches"]
+        hot_launches = per_forward * fwd["steps"]
         line = {
             "metric": METRIC, "value": fwd["value"], "unit": UNIT, "n_gpus": world, "steps": fwd["steps"],
             "warmup": args.warmup, "ms_per_step": fwd["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "f32 (attention: fp16 hi+lo split operands, 3 tcgen05 passes, f32 accumulate = f32-faithful; 4x4 attention "
-                     "plain f32; GDN contraction bf16x3 split + f32 accumulate; convolutions cuDNN f32, TF32 off)",
+                     "plain f32; GDN contraction bf16x3 split + f32 accumulate; convolutions fp16 hi+lo split operands, 3 tcgen05 passes, "
+                     "chunked f32 accumulation outside the tensor core = f32-faithful)",
             "data": "synthetic",
             "config": {"workload": "C2-forward: AutoEncoderRGB_Journal encode + decode forward (alpha pyramids, analysis, "
                                    "hyperprior, 10-slice loop, synthesis, bpp), batch 16 x 768x512 RGBA per GPU, random-init "
@@ -679,8 +690,10 @@ def main():
                        "l2": "activations of one step >> 126 MB L2 (1.2 GB per 1/2-scale tensor): inputs larger than L2, no flush",
                        "hot_path_share_of_step": fwd["hot_path_share"]},
             "roofline": roofline, "roofline_gdn": gdn_r, "rooflines": roofs, "cpu_baseline": cpu, "e2e": fwd["e2e"],
-            "gpu_launches": hot_launches, "gpu_launches_note": f"{LAUNCHES_PER_FORWARD} launches of this repo's kernels per forward "
-                                                                "(the convolutions are cuDNN launches and are not counted)",
+            "gpu_launches": hot_launches,
+            "gpu_launches_note": f"{per_forward} launches of this repo's kernels per forward: {LAUNCHES_PER_FORWARD} hot-path launches "
+                                 f"(alpha pyramids, attention, GDN, z rounding) + {fwd['conv_launches']} convolution / plane-split "
+                                 "launches counted by the binding; the entropy-model bpp terms are torch elementwise kernels",
             "clocks": fwd["clocks"], "per_op_ms": fwd["per_op_ms"], "hot_path_ms_per_step": fwd["hot_path_ms_per_step"],
         }
         line.update(extra)

@@ -76,6 +76,14 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
 
+# kernel launches issued through this binding (bench.py's `gpu_launches`): the wrappers add what each call launches
+launch_count = 0
+
+
+def count_launches(n: int) -> None:
+    global launch_count
+    launch_count += n
+
 
 class MwaB200Error(RuntimeError):
     pass

@@ -81,6 +81,7 @@ def split_into(x, dst: SplitAct, coff=0):
     with torch.cuda.device(x.device):
         _abi.check(lib.conv_act_split(x.data_ptr(), x.stride(0), B, C, H, W, dst.ps, dst.hi.data_ptr(), dst.lo.data_ptr(),
                                       dst.cstride, coff, _abi.stream_handle()), "conv_act_split")
+    _abi.count_launches(1)
     return dst
 
 
@@ -113,7 +114,12 @@ class _WeightImage:
         return self.img
 
 
+USE_KERNEL = True          # False: every convolution through torch.nn.functional (bench.py's library-convolution leg)
+
+
 def _fast_ok(x, *tensors):
+    if not USE_KERNEL:
+        return False
     if isinstance(x, SplitAct):
         return True
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0):
@@ -163,6 +169,7 @@ def _run(x, bias, image, kind, k, stride, act, residual, cout, ho, wo, emit_ps=0
             0 if out2 is None else out2.stride(0), None if sp is None else sp.hi.data_ptr(),
             None if sp is None else sp.lo.data_ptr(), 0 if sp is None else sp.ps, 0 if sp is None else sp.cstride, coff,
             image.data_ptr(), kind, B, cin, cout, H, W, k, stride, act, _abi.stream_handle()), "conv_forward_ex")
+    _abi.count_launches(1 if xp is None else 2)
     if sp is None:
         return out
     if emit_into is None:
