@@ -285,6 +285,21 @@ MWA_API int conv_forward_ex(const float* x, int64_t x_batch_stride, void* in_hi,
                             void* out_hi, void* out_lo, int out_ps, int out_cstride, int out_coff, const void* image,
                             int kind, int B, int Cin, int Cout, int H, int W, int k, int stride, int act, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Masked MS-SSIM (evaluation on the device)   replaces  metrics/masked_ms_ssim_torch.py:58-121 (_ssim)
+ *   and the per-level body of :181-265 (ms_ssim with a mask).
+ * ms_ssim_level_forward : X, Y (B, C, H, W) fp32 dense, mask (B, H, W): the mask is binarised (> 0) and multiplied into both
+ *     images, the five moments are blurred with the 11-tap Gaussian (sigma 1.5, valid mode, along H then W), and
+ *     sums[(b * C + c) * 2 + {0, 1}] receive the SSIM / CS map sums over the positions of the (H-10) x (W-10) valid region
+ *     whose nearest-resized mask is non-zero, counts[b] the number of such positions (both overwritten).  H, W >= 11.
+ * ms_ssim_pool_forward  : the level's images times the binarised mask, and the binarised mask, through
+ *     F.avg_pool2d(2, padding = size % 2): Xo, Yo (B, C, Hp, Wp), Mo (B, Hp, Wp) with Hp = (H + 2 (H % 2) - 2) / 2 + 1.
+ * The five-level product (weights 0.0448 ... 0.1333, relu, mean over images and channels) is a handful of scalars. */
+MWA_API int ms_ssim_level_forward(const float* X, const float* Y, const float* mask, int B, int C, int H, int W,
+                                  float data_range, float* sums, float* counts, void* stream);
+MWA_API int ms_ssim_pool_forward(const float* X, const float* Y, const float* mask, int B, int C, int H, int W, float* Xo,
+                                 float* Yo, float* Mo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
