@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -157,6 +158,49 @@ class EntropyBottleneck(nn.Module):
                 v = v + torch.tanh(getattr(self, f"_factor{i:d}")) * torch.tanh(v)
         return v
 
+    @torch.no_grad()
+    def update(self):
+        """quantised CDF of every channel's learned density over [median - minima, median + maxima] (CompressAI's
+        EntropyBottleneck.update); the tables live on the host, where the coder runs"""
+        from . import entropy
+        q = self.quantiles.detach().float()
+        medians = q[:, 0, 1]
+        minima = torch.ceil(medians - q[:, 0, 0]).clamp(min=0).int()
+        maxima = torch.ceil(q[:, 0, 2] - medians).clamp(min=0).int()
+        length = (maxima + minima + 1).tolist()
+        samples = (medians - minima)[:, None, None] + torch.arange(max(length), device=q.device)[None, None, :]
+        lo, up = self._logits_cumulative(samples - 0.5), self._logits_cumulative(samples + 0.5)
+        sign = -torch.sign(lo + up)
+        pmf = torch.abs(torch.sigmoid(sign * up) - torch.sigmoid(sign * lo))[:, 0, :].double().cpu().numpy()
+        lens = torch.tensor(length)
+        tail = (torch.sigmoid(lo[:, 0, 0]) + torch.sigmoid(-up[:, 0, :].gather(1, (lens - 1).to(q.device)[:, None])[:, 0]))
+        self._table = entropy.CdfTable(pmf, tail.double().cpu().numpy(), length, (-minima).tolist())
+        return True
+
+    def _symbols(self, z):
+        return torch.round(z - self._get_medians()).to(torch.int32)
+
+    @torch.no_grad()
+    def compress(self, z):
+        """one string per image: the channel is the table index (models/AutoEncoderRGB_Journal.py:319)"""
+        if getattr(self, "_table", None) is None:
+            self.update()
+        B, C, H, W = z.shape
+        sym = self._symbols(z).cpu().numpy()
+        idx = torch.arange(C, dtype=torch.int32).view(C, 1, 1).expand(C, H, W).contiguous().numpy()
+        return [self._table.encode(sym[b], idx) for b in range(B)]
+
+    @torch.no_grad()
+    def decompress(self, strings, size):
+        """(:320, :372): symbols + medians"""
+        if getattr(self, "_table", None) is None:
+            self.update()
+        C, (H, W) = self.channels, size
+        idx = torch.arange(C, dtype=torch.int32).view(C, 1, 1).expand(C, H, W).contiguous().numpy()
+        sym = [torch.from_numpy(self._table.decoder(st).decode(idx)).view(1, C, H, W) for st in strings]
+        dev = self.quantiles.device
+        return torch.cat(sym, 0).to(dev).float() + self._get_medians()
+
     def likelihood(self, z_hat):
         B, C = z_hat.shape[:2]
         v = z_hat.transpose(0, 1).reshape(C, 1, -1)
@@ -171,6 +215,20 @@ class GaussianConditional(nn.Module):
 
     def __init__(self, scale_table=None):
         super().__init__()
+        self.scale_table, self._table = None, None
+
+    def update_scale_table(self, scale_table, force=False):
+        """one quantised Gaussian CDF per scale level (CompressAI's GaussianConditional.update_scale_table + update)"""
+        from . import entropy
+        if self._table is not None and not force:
+            return False
+        self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32).clone()
+        self._table = entropy.gaussian_table(self.scale_table)
+        return True
+
+    def build_indexes(self, scales):
+        from . import entropy
+        return entropy.build_indexes(scales, self.scale_table)
 
     @staticmethod
     def likelihood(y, scales, means):
@@ -317,6 +375,80 @@ class AutoEncoder(nn.Module):
                     scale_sup[:, M + i * sl:M + (i + 1) * sl] = y_hat
             mus.append(mu)
         return y_hat_all, torch.cat(mus, 1), torch.cat(scales, 1) if want_scales else None
+
+    # ------------------------------------------------------------------------------------------------ bitstream
+    def update(self, scale_table=None, force=False):
+        """models/AutoEncoderRGB_Journal.py:306-311"""
+        from . import entropy
+        updated = self.gaussian_conditional.update_scale_table(entropy.get_scale_table() if scale_table is None else scale_table,
+                                                               force=force)
+        if force or getattr(self.entropy_bottleneck, "_table", None) is None:
+            updated |= self.entropy_bottleneck.update()
+        return updated
+
+    @torch.no_grad()
+    def compress(self, input, mask):
+        """models/AutoEncoderRGB_Journal.py:312-368.  The device side is the forward's own pieces (analysis, hyperprior,
+        fused slice loop: one pass gives every slice's mu, scale and y_hat); symbols and table indexes of all slices go to
+        the host in ONE copy and the rANS coder runs there (csrc/rans.cu), one string per image (for a batch of one this is
+        the reference's structure; the reference puts a whole batch into one string and can only decompress batch 1)."""
+        self.update()
+        _, me = alpha_pyramid(mask, 3)
+        y = self.Encoder(input, mask, None, me[1], me[2], None)
+        z = self.h_a(y)
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.shape[-2:])
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        _, means, scales = self.slice_loop(y, latent_means, latent_scales)
+        symbols = torch.round(y - means).to(torch.int32).cpu().numpy()          # quantize(y, "symbols", mu)   (:347)
+        indexes = self.gaussian_conditional.build_indexes(scales).cpu().numpy()
+        table = self.gaussian_conditional._table
+        y_strings = [table.encode(symbols[b], indexes[b]) for b in range(y.shape[0])]
+        return {"strings": [y_strings, z_strings], "shape": z.shape[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape, mask):
+        """models/AutoEncoderRGB_Journal.py:370-415: slice by slice -- mu and scale of slice i need the decoded slices < i --
+        with the same kernels as the encoder, so the tables' indexes and the reconstruction are bit-identical to its."""
+        from .layers.conv import split_into
+        self.update()
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        latent_scales, latent_means = self.h_scale_s(z_hat), self.h_mean_s(z_hat)
+        B, M, H, W = latent_means.shape
+        sl, ms, dev = M // self.num_slices, self.max_support_slices, latent_means.device
+        table = self.gaussian_conditional._table
+        decoders = [table.decoder(st) for st in strings[0]]
+        fused = self.cc_mean_transforms[0][0].input_ps(latent_means) is not None
+        if fused:
+            mean_sup = split_into(latent_means, SplitAct.empty(B, M, H, W, 1, dev, channels=M + (ms + 1) * sl))
+            scale_sup = split_into(latent_scales, SplitAct.empty(B, M, H, W, 1, dev, channels=M + ms * sl))
+        y_hat_slices = []
+        for i in range(self.num_slices):
+            k = min(i, ms)
+            slot = M + k * sl
+            if fused:
+                mu = self.cc_mean_transforms[i](mean_sup.prefix(slot))
+                scale = self.cc_scale_transforms[i](scale_sup.prefix(slot))
+            else:
+                support = y_hat_slices[:ms]
+                mu = self.cc_mean_transforms[i](torch.cat([latent_means] + support, 1))
+                scale = self.cc_scale_transforms[i](torch.cat([latent_scales] + support, 1))
+            idx = self.gaussian_conditional.build_indexes(scale).cpu().numpy()
+            sym = torch.from_numpy(np.stack([decoders[b].decode(idx[b]) for b in range(B)])).view(B, sl, H, W)
+            y_hat = sym.to(dev).float() + mu                                   # dequantize(rv, mu)   (:395)
+            if fused:
+                split_into(y_hat, mean_sup, slot)
+                lrp = self.lrp_transforms[i](mean_sup.prefix(slot + sl), final_act=ACT_LRP, aux=y_hat, out=y_hat,
+                                             emit_into=(mean_sup, slot) if i < ms else None)
+                if i < ms:
+                    scale_sup.hi[..., slot:slot + sl] = mean_sup.hi[..., slot:slot + sl]
+                    scale_sup.lo[..., slot:slot + sl] = mean_sup.lo[..., slot:slot + sl]
+            else:
+                y_hat = quant.lrp_add(y_hat, self.lrp_transforms[i](torch.cat([latent_means] + y_hat_slices[:ms] + [y_hat], 1)))
+            y_hat_slices.append(y_hat)
+        _, md = alpha_pyramid(mask, 3)
+        x_hat = self.Decoder(torch.cat(y_hat_slices, 1), mask, None, md[1], md[2], None).clamp_(0, 1)
+        return {"x_hat": x_hat}
 
     def detail(self, input, mask, reconmask, me2=None, me3=None):
         """every tensor of the forward the parity tests look at"""

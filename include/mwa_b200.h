@@ -300,6 +300,22 @@ MWA_API int ms_ssim_level_forward(const float* X, const float* Y, const float* m
 MWA_API int ms_ssim_pool_forward(const float* X, const float* Y, const float* mask, int B, int C, int H, int W, float* Xo,
                                  float* Yo, float* Mo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Range-ANS coder of the bitstream (HOST functions: every pointer is host memory)   replaces the
+ *   compressai.ans calls of models/AutoEncoderRGB_Journal.py:330-368 (BufferedRansEncoder.encode_with_indexes + flush) and
+ *   :374-403 (RansDecoder.set_stream + decode_stream): 64-bit rANS state, 32-bit words, 16-bit CDFs chosen per symbol by
+ *   `indexes`, 4-bit bypass digits for values outside a CDF's support.  Byte parity with CompressAI is unpinned (absent).
+ * cdfs      : (ncdf, cdf_stride) int32; row i has cdf_sizes[i] increasing entries from 0 to 65536; its last interval is the
+ *             escape symbol; symbol value = table position + offsets[i]
+ * encode    : returns the number of bytes written to `out` (multiple of 4) or a negative MWA_ERR_* (WORKSPACE: too small)
+ * decode    : `state` = 4 x int64, zeroed before the first call on a stream; later calls continue where the last stopped */
+MWA_API int64_t rans_encode_with_indexes(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                                         int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, int ncdf,
+                                         uint8_t* out, int64_t out_capacity);
+MWA_API int rans_decode_with_indexes(const uint8_t* stream, int64_t nbytes, int64_t* state, const int32_t* indexes, int64_t n,
+                                     const int32_t* cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                                     int ncdf, int32_t* symbols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,3 +98,32 @@ def test_full_forward_batch_and_baseline_size_against_oracle_samples(pkg, cuda_d
         me = R.alpha_pyramid(p["alpha"][:1])
         y0 = M.analysis(M._sub(w, "Encoder."), p["image"][:1], me[1], me[2])
     torch.testing.assert_close(r["y"][:1].cpu(), y0, rtol=RTOL, atol=ATOL)
+
+
+def test_compress_decompress_round_trip(pkg, cuda_dev, model_keys):
+    """models/AutoEncoderRGB_Journal.py:312-415: the decoder, working slice by slice from the strings alone, reproduces the
+    encoder-side reconstruction bit for bit, and the strings are as long as the forward's rate estimate says"""
+    cfg = next(iter(G.MODEL_CASES.values()))
+    p = G.model_inputs(cfg)
+    net = _codec(pkg, model_keys, cfg["seed"], cuda_dev)
+    image = torch.cat([p["image"], p["image"].flip(3)], 0).to(cuda_dev)
+    alpha = torch.cat([p["alpha"], p["alpha"].flip(3)], 0).to(cuda_dev)
+    with torch.no_grad():
+        out = net.compress(image, alpha)
+        assert len(out["strings"][0]) == 2 and len(out["strings"][1]) == 2 and tuple(out["shape"]) == (3, 4)
+        rec = net.decompress(out["strings"], out["shape"], alpha)["x_hat"]
+        me = net.EncMakeMask(alpha)
+        x_hat, _, bpp, _, _ = net(image, alpha, alpha, me[0], me[1], me[2], me[3])
+    assert torch.equal(rec, x_hat.clamp(0, 1))
+    nbits = 8 * sum(len(s) for group in out["strings"] for s in group)
+    est = float(bpp) * image.shape[0] * image.shape[2] * image.shape[3]
+    # the estimate is the continuous model's (likelihoods floored at 1e-9 = 30 bits a symbol); the coder works from the 64
+    # quantised tables and codes far-out symbols through the escape, which is cheaper than that floor on a random-init
+    # model: the stream must not be LONGER than the estimate, and not implausibly short (tests/test_entropy.py holds the
+    # coder itself to 2 % of its tables' entropy)
+    assert 0.5 * est < nbits < 1.05 * est + 4096, (nbits, est)
+    # a single image: the reference's own structure (one y string, one z string)
+    with torch.no_grad():
+        one = net.compress(image[:1], alpha[:1])
+        rec1 = net.decompress(one["strings"], one["shape"], alpha[:1])["x_hat"]
+    assert torch.equal(rec1, rec[:1])
