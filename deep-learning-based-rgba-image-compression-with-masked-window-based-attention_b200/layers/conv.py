@@ -10,8 +10,10 @@ Inference (no autograd history) on CUDA fp32 NCHW tensors runs `conv_forward` of
 tcgen05 with fp16 hi + lo operands in three passes and fp32 accumulation -- fp32-faithful (~1e-6 relative), where the
 reference's torch.nn.Conv2d in fp32 is cuDNN's SIMT path on a GPU.  Covered: k in {1, 3, 5}, stride 1 or 2, padding k / 2,
 groups 1, dilation 1; transposed k = 5, stride 2, padding 2, output padding 1 -- every convolution of the Journal
-models.  Anything else, and every call that records autograd history (training: the backward is torch's), goes to
-torch.nn.functional (cuDNN) unchanged.
+models.  With autograd history (training) the forward and the input gradient run on the same kernel
+(the input gradient of a convolution is a convolution with the flipped / transposed weights: stride 1 -> stride 1, the 5x5
+stride-2 convolution -> the transposed kernel, the transposed convolution -> the stride-2 kernel); the weight / bias
+gradients (a contraction over all pixels) are the library's.  Anything else goes to torch.nn.functional (cuDNN) unchanged.
 """
 from __future__ import annotations
 
@@ -98,10 +100,12 @@ class _WeightImage:
     def __deepcopy__(self, memo):
         return _WeightImage()
 
-    def get(self, w, kind, k, stride):
+    def get(self, w, kind, k, stride, transform=None):
         key = (w.data_ptr(), w._version, str(w.device))
         if self.img is None or key != self.key:
             lib = _abi.load()
+            if transform is not None:
+                w = transform(w.detach())
             cin, cout = (w.shape[1], w.shape[0]) if kind == 0 else (w.shape[0], w.shape[1])
             nbytes = int(lib.conv_image_bytes(kind, cin, cout, k, stride))
             if nbytes <= 0:
@@ -130,7 +134,7 @@ def _fast_ok(x, *tensors):
 
 
 def _run(x, bias, image, kind, k, stride, act, residual, cout, ho, wo, emit_ps=0, want_dense=True, aux=None, out=None,
-         out2=None, emit_into=None):
+         out2=None, emit_into=None, in_scale=None):
     """one conv_forward_ex call.  x: fp32 NCHW tensor or SplitAct.  Returns the dense result, or -- with emit_ps / emit_into
     -- a SplitAct (carrying the dense result too when want_dense)."""
     lib = _abi.load()
@@ -168,7 +172,8 @@ def _run(x, bias, image, kind, k, stride, act, residual, cout, ho, wo, emit_ps=0
             0 if out is None else out.stride(0), _abi.ptr(aux), 0 if aux is None else aux.stride(0), _abi.ptr(out2),
             0 if out2 is None else out2.stride(0), None if sp is None else sp.hi.data_ptr(),
             None if sp is None else sp.lo.data_ptr(), 0 if sp is None else sp.ps, 0 if sp is None else sp.cstride, coff,
-            image.data_ptr(), kind, B, cin, cout, H, W, k, stride, act, _abi.stream_handle()), "conv_forward_ex")
+            image.data_ptr(), kind, B, cin, cout, H, W, k, stride, act, _abi.ptr(in_scale), _abi.stream_handle()),
+            "conv_forward_ex")
     _abi.count_launches(1 if xp is None else 2)
     if sp is None:
         return out
@@ -215,11 +220,72 @@ def _fallback(x):
     return x
 
 
+def gradient_scale(g):
+    """device scalar 2^k that brings max |g| to ~2^10: gradients sit far below fp16's normal range (6e-5), where the
+    hi + lo split of the kernel's operands has no precision left; a power of two changes nothing else.  No host sync."""
+    amax = g.detach().abs().amax().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(1024.0 / amax))).reshape(1).float()
+
+
+def conv1x1_nchw(x, w2d, out=None, scale_input=False):
+    """out[b, :, p] = w2d @ x[b, :, p] on the convolution kernel (the per-pixel C x C contractions of the GDN backward)"""
+    lib = _abi.load()
+    cout, cin = w2d.shape
+    nbytes = int(lib.conv_image_bytes(0, cin, cout, 1, 1))
+    img = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _abi.check(lib.conv_prepare(w2d.detach().contiguous().data_ptr(), 0, cin, cout, 1, 1, img.data_ptr(), nbytes,
+                                    _abi.stream_handle()), "conv_prepare")
+    return _run(x, None, img, 0, 1, 1, ACT_NONE, None, cout, x.shape[2], x.shape[3], out=out,
+                in_scale=gradient_scale(x) if scale_input else None)
+
+
+class _ConvTrainFn(torch.autograd.Function):
+    """forward and input gradient on conv_forward_ex; weight / bias gradients through aten.convolution_backward"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        ctx.mod = mod
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        with torch.no_grad():
+            return mod._fast(x, ACT_NONE, None)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        mod = ctx.mod
+        g = g.contiguous()
+        gx = gw = gb = None
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        with torch.no_grad():
+            if need_x and mod._dgrad_ok(x):
+                gx = mod._dgrad(g, x)
+                need_x = False
+            if need_x or need_w or need_b:
+                transposed = mod._kind == 1
+                r = torch.ops.aten.convolution_backward(
+                    g, x, weight, [mod.out_channels] if ctx.has_bias else None, list(mod.stride), list(mod.padding),
+                    list(mod.dilation), transposed, list(mod.output_padding) if transposed else [0, 0], mod.groups,
+                    [bool(need_x), bool(need_w), bool(need_b)])
+                gx = r[0] if need_x else gx
+                gw = r[1] if need_w else None
+                gb = r[2] if need_b else None
+        return gx, gw, gb, None
+
+
+def _train_ok(x, mod):
+    """a call that records autograd history and that the kernel covers: dense fp32 NCHW on CUDA"""
+    return (USE_KERNEL and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0
+            and _dense_nchw(x) and x.stride(0) == x.shape[1] * x.shape[2] * x.shape[3] and mod._covered(x))
+
+
 class _FastConv:
     """what Conv2d and ConvTranspose2d share: the cached weight image, its invalidation, and the fast-path call"""
 
     def _init_fast(self):
         self._img = _WeightImage()
+        self._dimg = _WeightImage()          # operand image of the input-gradient convolution
 
     def input_ps(self, x):
         """parity planes this layer wants its input split into (1 or 2) if it will take the fast path on x, else None"""
@@ -238,14 +304,21 @@ class _FastConv:
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
+        for name in ("_img", "_dimg"):
+            if name in self.__dict__:
+                self.__dict__[name].invalidate()
         return out
 
     def _load_from_state_dict(self, *a, **kw):
         super()._load_from_state_dict(*a, **kw)
-        if "_img" in self.__dict__:
-            self._img.invalidate()
+        for name in ("_img", "_dimg"):
+            if name in self.__dict__:
+                self.__dict__[name].invalidate()
+
+    def _train_forward(self, x, act, residual, kw):
+        """training: kernel forward + kernel input gradient; the epilogue steps as ordinary differentiable torch ops"""
+        y = _ConvTrainFn.apply(x, self.weight, self.bias, self)
+        return _plain_epilogue(y, act, residual, kw)
 
 
 _EPI_KW = ("emit_ps", "want_dense", "aux", "out", "out2", "emit_into")
@@ -296,9 +369,27 @@ class Conv2d(_FastConv, nn.Conv2d):
                 # the library's fp32 kernels there, so they stay with it
                 and self.in_channels >= self.min_channels and self.out_channels >= self.min_channels)
 
+    def _dgrad_ok(self, x):
+        k, s = self.kernel_size[0], self.stride[0]
+        return self.out_channels >= 8 and (s == 1 or k == 5)
+
+    def _dgrad(self, g, x):
+        """d loss / d x: stride 1 -> the same convolution with the taps flipped and the channel roles swapped; 5x5 stride 2 ->
+        the transposed-convolution plan with the weight as it is ((Cout, Cin, k, k) reads as (in, out, k, k))"""
+        k, s = self.kernel_size[0], self.stride[0]
+        B, cin, H, W = x.shape
+        if s == 1:
+            key_w = self.weight
+            img = self._dimg.get(key_w, 0, k, 1, transform=lambda w: w.flip(2, 3).transpose(0, 1).contiguous())
+            return _run(g, None, img, 0, k, 1, ACT_NONE, None, cin, H, W, in_scale=gradient_scale(g))
+        img = self._dimg.get(self.weight, 1, k, 2)
+        return _run(g, None, img, 1, k, 2, ACT_NONE, None, cin, H, W, in_scale=gradient_scale(g))
+
     def forward(self, x, act=ACT_NONE, residual=None, **kw):
         if _fast_ok(x, self.weight, self.bias, residual, kw.get("aux")) and self._covered(x):
             return self._fast(x, act, residual, **kw)
+        if torch.is_grad_enabled() and _train_ok(x, self):
+            return self._train_forward(x, act, residual, kw)
         return _plain_epilogue(super().forward(_fallback(x)), act, residual, kw)
 
 
@@ -315,9 +406,21 @@ class ConvTranspose2d(_FastConv, nn.ConvTranspose2d):
                 and tuple(self.output_padding) == (1, 1) and tuple(self.dilation) == (1, 1) and self.groups == 1
                 and x.shape[1] == self.in_channels and self.in_channels >= self.min_channels)
 
+    def _dgrad_ok(self, x):
+        return self.out_channels >= 8
+
+    def _dgrad(self, g, x):
+        """d loss / d x of the transposed convolution = the 5x5 stride-2 convolution of the output gradient with the same
+        weight ((Cin, Cout, k, k) reads as (out, in, k, k))"""
+        B, cin, H, W = x.shape
+        img = self._dimg.get(self.weight, 0, 5, 2)
+        return _run(g, None, img, 0, 5, 2, ACT_NONE, None, cin, H, W, in_scale=gradient_scale(g))
+
     def forward(self, x, output_size=None, act=ACT_NONE, residual=None, **kw):
         if output_size is None and _fast_ok(x, self.weight, self.bias, residual, kw.get("aux")) and self._covered(x):
             return self._fast(x, act, residual, **kw)
+        if output_size is None and torch.is_grad_enabled() and _train_ok(x, self):
+            return self._train_forward(x, act, residual, kw)
         return _plain_epilogue(super().forward(_fallback(x), output_size), act, residual, kw)
 
 

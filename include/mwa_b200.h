@@ -273,7 +273,9 @@ MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bi
  *                        v = conv_b's last 1x1, aux = a, residual = x)
  *           6 add2     : out = (v + residual) + aux                              (layers/TransformRGB.py:27, :47: the last
  *                        enhancement block's identity and the DSE skip in one epilogue)
- *           aux: fp32 NCHW (B, Cout, Ho, Wo) with batch stride aux_batch_stride; out2 likewise. */
+ *           aux: fp32 NCHW (B, Cout, Ho, Wo) with batch stride aux_batch_stride; out2 likewise.
+ *   in_scale  NULL, or a DEVICE scalar s (a power of two): the fp32 input is multiplied by s before it is split and the
+ *           result divided by s -- for inputs far below fp16's normal range (the gradients of the backward pass). */
 /* conv_act_split : fp32 NCHW (B, C, H, W; batch stride x_batch_stride) -> the fp16 hi / lo planes of conv_forward_ex's
  *   x == NULL input, at channel offset out_coff of buffers with channel pitch out_cstride (how an activation that was NOT
  *   produced by one of these convolutions -- GDN, attention, a PixelShuffle -- enters a chain or a support buffer). */
@@ -283,7 +285,8 @@ MWA_API int conv_forward_ex(const float* x, int64_t x_batch_stride, void* in_hi,
                             const float* bias, const float* residual, float* out, int64_t out_batch_stride,
                             const float* aux, int64_t aux_batch_stride, float* out2, int64_t out2_batch_stride,
                             void* out_hi, void* out_lo, int out_ps, int out_cstride, int out_coff, const void* image,
-                            int kind, int B, int Cin, int Cout, int H, int W, int k, int stride, int act, void* stream);
+                            int kind, int B, int Cin, int Cout, int H, int W, int k, int stride, int act,
+                            const float* in_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked MS-SSIM (evaluation on the device)   replaces  metrics/masked_ms_ssim_torch.py:58-121 (_ssim)

@@ -72,12 +72,53 @@ def test_convolution_on_a_channel_slice_and_weight_update(pkg, cuda_dev):
         torch.testing.assert_close(y2.cpu(), ref2, rtol=1e-3, atol=1e-4)
 
 
-def test_convolution_with_autograd_history_takes_the_library_path(pkg, cuda_dev):
-    m = pkg.conv.Conv2d(16, 16, 3, padding=1).to(cuda_dev)
-    x = torch.randn(1, 16, 8, 8, device=cuda_dev, requires_grad=True)
-    y = m(x, act=1)
-    y.sum().backward()
-    assert x.grad is not None and m.weight.grad is not None
+GRAD_CASES = [
+    ("conv", 48, 96, 1, 1, 16, 24),        # residual-unit 1x1
+    ("conv", 40, 40, 3, 1, 16, 24),        # 3x3 stride 1: flipped taps
+    ("conv", 64, 72, 5, 2, 16, 32),        # 5x5 stride 2: input gradient on the transposed plan
+    ("conv", 80, 96, 3, 2, 16, 16),        # 3x3 stride 2 (h_a): input gradient through the library
+    ("deconv", 72, 64, 5, 2, 8, 12),       # transposed: input gradient on the stride-2 plan
+]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES, ids=lambda c: f"{c[0]}_{c[1]}to{c[2]}_k{c[3]}s{c[4]}")
+def test_training_forward_and_gradients_match_torch_cpu(pkg, cuda_dev, case):
+    """with autograd recording the forward and the input gradient run on the kernel (the weight / bias gradients are the
+    library's): everything against torch CPU fp32 autograd"""
+    kind, cin, cout, k, s, H, W = case
+    conv = pkg.conv
+    g = torch.Generator().manual_seed(cin + cout + k)
+    if kind == "conv":
+        m = conv.Conv2d(cin, cout, k, stride=s, padding=k // 2)
+    else:
+        m = conv.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1)
+    x = torch.randn(2, cin, H, W, generator=g)
+    ref_m = type(m).__mro__[2](*( (cin, cout, k) ), stride=s, padding=k // 2, **({"output_padding": 1} if kind == "deconv" else {}))
+    ref_m.load_state_dict(m.state_dict())
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.gelu(ref_m(xr))
+    go = torch.randn(yr.shape, generator=g)
+    yr.backward(go)
+    m = m.to(cuda_dev)
+    xd = x.to(cuda_dev).requires_grad_(True)
+    calls = []
+    orig = conv._run
+
+    def spy(xin, *a, **kw):
+        calls.append(a[2])                   # kind of every kernel launch
+        return orig(xin, *a, **kw)
+
+    conv._run = spy
+    try:
+        yd = m(xd, act=conv.ACT_GELU)
+        yd.backward(go.to(cuda_dev))
+    finally:
+        conv._run = orig
+    assert len(calls) == (1 if (kind == "conv" and k == 3 and s == 2) else 2), calls
+    torch.testing.assert_close(yd.detach().cpu(), yr.detach(), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(m.weight.grad.cpu(), ref_m.weight.grad, rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(m.bias.grad.cpu(), ref_m.bias.grad, rtol=1e-3, atol=2e-4)
 
 
 def test_conv_stack_fuses_activations(pkg, cuda_dev):
@@ -211,3 +252,17 @@ def test_fused_slice_loop_equals_the_loop_with_separate_rounding_launches(pkg, c
         want = model._slice_loop_in_place(y, lm, ls, True)
     for g, w, name in zip(got, want, ("y_hat", "means", "scales")):
         assert torch.equal(g, w), name
+
+
+def test_input_gradient_of_tiny_gradients_keeps_fp32_accuracy(pkg, cuda_dev):
+    """real loss gradients are ~1e-7: far below fp16's normal range.  The power-of-two input scale (conv_forward_ex
+    in_scale) keeps the hi + lo split exact enough: relative error of the input gradient as for O(1) gradients"""
+    conv = pkg.conv
+    torch.manual_seed(9)
+    m = conv.Conv2d(64, 64, 3, padding=1).to(cuda_dev)
+    x = torch.randn(2, 64, 16, 24, device=cuda_dev, requires_grad=True)
+    go = torch.randn(2, 64, 16, 24, device=cuda_dev) * 3e-8
+    m(x).backward(go)
+    ref = torch.nn.functional.conv_transpose2d(go.double().cpu(), m.weight.double().cpu(), padding=1).float()
+    err = (x.grad.detach().cpu() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 1e-5, float(err)
