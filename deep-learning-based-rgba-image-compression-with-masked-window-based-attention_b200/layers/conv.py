@@ -100,17 +100,19 @@ class _WeightImage:
     def __deepcopy__(self, memo):
         return _WeightImage()
 
-    def get(self, w, kind, k, stride, transform=None):
+    def get(self, w, kind, k, stride):
+        """kind 0 / 1: convolution / transposed convolution weight; 2: the input gradient of a stride-1 convolution whose
+        weight w is.  The buffer is kept across weight updates (training re-prepares every step)."""
         key = (w.data_ptr(), w._version, str(w.device))
         if self.img is None or key != self.key:
             lib = _abi.load()
-            if transform is not None:
-                w = transform(w.detach())
             cin, cout = (w.shape[1], w.shape[0]) if kind == 0 else (w.shape[0], w.shape[1])
-            nbytes = int(lib.conv_image_bytes(kind, cin, cout, k, stride))
+            nbytes = int(lib.conv_image_bytes(0 if kind == 2 else kind, cin, cout, k, stride))
             if nbytes <= 0:
                 raise _abi.MwaB200Error("conv: unsupported geometry")
-            img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+            img = self.img
+            if img is None or img.numel() != nbytes or img.device != w.device:
+                img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
             wc = w.detach().contiguous()
             _abi.check(lib.conv_prepare(wc.data_ptr(), kind, cin, cout, k, stride, img.data_ptr(), nbytes,
                                         _abi.stream_handle()), "conv_prepare")
@@ -379,8 +381,7 @@ class Conv2d(_FastConv, nn.Conv2d):
         k, s = self.kernel_size[0], self.stride[0]
         B, cin, H, W = x.shape
         if s == 1:
-            key_w = self.weight
-            img = self._dimg.get(key_w, 0, k, 1, transform=lambda w: w.flip(2, 3).transpose(0, 1).contiguous())
+            img = self._dimg.get(self.weight, 2, k, 1)
             return _run(g, None, img, 0, k, 1, ACT_NONE, None, cin, H, W, in_scale=gradient_scale(g))
         img = self._dimg.get(self.weight, 1, k, 2)
         return _run(g, None, img, 1, k, 2, ACT_NONE, None, cin, H, W, in_scale=gradient_scale(g))

@@ -238,7 +238,9 @@ MWA_API int mask_constraint_forward(const float* mask, float* out, int B, int H,
  *
  * kind 0: convolution, k in {1, 3, 5}, stride 1 or 2 (H, W even), padding k / 2, dilation 1, groups 1
  * kind 1: transposed convolution, k = 5, stride 2, padding 2, output padding 1 (output 2H x 2W)
- * conv_prepare : weight (Cout, Cin, k, k) [kind 0] / (Cin, Cout, k, k) [kind 1] -> fp16 hi / lo UMMA operand image
+ * kind 2 (conv_prepare only): the INPUT-GRADIENT convolution of a stride-1 convolution, prepared straight from that
+ *         convolution's weight (Cin, Cout, k, k) = (its Cout, its Cin): flipped taps, swapped channel roles; run with kind 0
+ * conv_prepare : weight (Cout, Cin, k, k) [kind 0] / (Cin, Cout, k, k) [kind 1, 2] -> fp16 hi / lo UMMA operand image
  *                (per output channel scaled by a power of two into fp16's normal range; the inverse scales ride along)
  * conv_forward : out = act(conv(x) + bias (+ residual));  x fp32 NCHW with batch stride `x_batch_stride` floats (a
  *                channel slice of a larger tensor is fine), out fp32 NCHW with batch stride `out_batch_stride`,
