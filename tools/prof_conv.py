@@ -35,7 +35,11 @@ with torch.no_grad():
         m = pkg.conv.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1).to(dev)
     y = m(x, act=act)
     r = torch.randn_like(y) if res else None
+    planes = "planes" in sys.argv          # as inside a chain: planes in, dense + planes out
+    if planes:
+        xs = pkg.conv.split_into(x, pkg.conv.SplitAct.empty(B, cin, h, w, 2 if (kind == "conv" and s == 2) else 1, dev))
     for _ in range(4):
-        y = m(x, act=act, residual=r)
+        y = m(xs, act=act, residual=r, emit_ps=1) if planes else m(x, act=act, residual=r)
 torch.cuda.synchronize()
+y = y.dense if hasattr(y, "dense") else y
 print("done", float(y.abs().mean()))
