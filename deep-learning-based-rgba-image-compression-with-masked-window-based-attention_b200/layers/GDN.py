@@ -16,7 +16,6 @@ from torch.autograd import Function
 
 from .. import _abi
 from ._params import ParamBlock, ParamBlockOwner
-from .conv import conv1x1_nchw
 
 
 class LowerBound(Function):
@@ -61,8 +60,6 @@ def _composed_backward(lib, x, grad_y, beta, gamma, blk, mod, channels_last, gx,
     nb = torch.empty_like(x)
     if channels_last:
         torch.matmul(tok(x2), gT_eff, out=tok(nb))       # n_i = sum_j x2_j gamma[i][j]
-    elif x.dim() == 4 and C % 8 == 0:
-        conv1x1_nchw(x2, g_eff, out=nb, scale_input=True)   # the convolution kernel as the GEMM engine (fp32-faithful tcgen05)
     else:
         torch.matmul(g_eff, tok(x2), out=tok(nb))
     dn = torch.empty_like(x)
@@ -71,8 +68,6 @@ def _composed_backward(lib, x, grad_y, beta, gamma, blk, mod, channels_last, gx,
     t = torch.empty_like(x)
     if channels_last:
         torch.matmul(tok(dn), g_eff, out=tok(t))         # t_j = sum_i dn_i gamma[i][j]
-    elif x.dim() == 4 and C % 8 == 0:
-        conv1x1_nchw(dn, gT_eff, out=t, scale_input=True)
     else:
         torch.matmul(gT_eff, tok(dn), out=tok(t))
     _abi.check(lib.gdn_bwd_dx(nb.data_ptr(), x.data_ptr(), t.data_ptr(), gx.data_ptr(), x.numel(), st), "gdn_bwd_dx")

@@ -17,6 +17,7 @@ from torch.autograd import Function
 
 from .. import _abi
 from ._params import ParamBlock, ParamBlockOwner
+from .conv import gemm_tokens
 
 
 def _window_partition(x, window_size):
@@ -109,12 +110,13 @@ class WindowAttentionFunction(Function):
                 _abi.check(lib.mwa_bwd_gather(x.data_ptr(), _abi.ptr(alpha), grad_out.data_ptr(), xw.data_ptr(),
                                               dy.data_ptr(), flags.data_ptr(), B, C, H, W, ws, shift,
                                               int(channels_last), st), "mwa_bwd_gather")
-                qkv = torch.addmm(qkv_b, xw, qw.t()) if qkv_b is not None else xw @ qw.t()
-                dao = dy @ pw
+                # the token GEMMs on the convolution kernel (fp32-faithful tcgen05; gradients pre-scaled by a power of two)
+                qkv = gemm_tokens(xw, qw, qkv_b)
+                dao = gemm_tokens(dy, pw, weight_is_in_out=True, scale_input=True)
                 _abi.check(lib.mwa_bwd_core(qkv.data_ptr(), dao.data_ptr(), blk.data_ptr(), None, flags.data_ptr(),
                                             ao.data_ptr(), dqkv.data_ptr(), gtab.data_ptr(), nwin, C, H, W,
                                             attn_mod.num_heads, ws, shift, 0, st), "mwa_bwd_core")
-                dxw = dqkv @ qw
+                dxw = gemm_tokens(dqkv, qw, weight_is_in_out=True, scale_input=True)
                 _abi.check(lib.mwa_bwd_scatter(grad_out.data_ptr(), dxw.data_ptr(), gx.data_ptr(), B, C, H, W, ws,
                                                shift, int(channels_last), st), "mwa_bwd_scatter")
             need = ctx.needs_input_grad
@@ -183,12 +185,12 @@ class TokenAttentionFunction(Function):
                                                          m.num_heads, ws, nw, _abi.stream_handle()),
                            "window_attention_backward")
             else:
-                qkv = torch.addmm(qkv_b, xf, qw.t()) if qkv_b is not None else xf @ qw.t()
-                dao = dyf @ pw
+                qkv = gemm_tokens(xf.contiguous(), qw, qkv_b)
+                dao = gemm_tokens(dyf.contiguous(), pw, weight_is_in_out=True, scale_input=True)
                 _abi.check(lib.mwa_bwd_core(qkv.data_ptr(), dao.data_ptr(), blk.data_ptr(), _abi.ptr(mask), None,
                                             ao.data_ptr(), dqkv.data_ptr(), gtab.data_ptr(), K, C, 0, 0, m.num_heads,
                                             ws, 0, nw, _abi.stream_handle()), "mwa_bwd_core")
-                torch.matmul(dqkv, qw, out=gx.view(K * N, C))
+                gx = gemm_tokens(dqkv, qw, weight_is_in_out=True, scale_input=True).view(K, N, C)
             need = ctx.needs_input_grad
             with _abi.tf32_reduction(K * N):
                 gw1 = dqkv.t() @ xf if need[2] else None

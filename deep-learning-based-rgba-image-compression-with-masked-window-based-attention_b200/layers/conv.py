@@ -120,6 +120,7 @@ class _WeightImage:
         return self.img
 
 
+GEMM_TOKENS_MIN_FLOP = 2e9
 USE_KERNEL = True          # False: every convolution through torch.nn.functional (bench.py's library-convolution leg)
 
 
@@ -229,17 +230,33 @@ def gradient_scale(g):
     return torch.exp2(torch.floor(torch.log2(1024.0 / amax))).reshape(1).float()
 
 
-def conv1x1_nchw(x, w2d, out=None, scale_input=False):
-    """out[b, :, p] = w2d @ x[b, :, p] on the convolution kernel (the per-pixel C x C contractions of the GDN backward)"""
+def gemm_tokens(x2d, w, bias=None, weight_is_in_out=False, scale_input=False):
+    """out (T, Cout) = x2d (T, Cin) @ W^T (+ bias) on the convolution kernel (gemm_tokens_forward): the token GEMMs of the
+    attention backward.  W is (Cout, Cin), or -- weight_is_in_out -- given as (Cin, Cout) and used as it lies (out = x2d @ w).
+    Shapes the kernel does not take (T % 8, Cout % 8) and small problems (< 2 GFLOP: the split + prepare launches cost more
+    than the library's fp32 GEMM there, measured on the 4x4-window layer and on 256x256 crops) go to the library GEMM."""
+    T, cin = x2d.shape
+    cout = w.shape[1] if weight_is_in_out else w.shape[0]
+    if not (USE_KERNEL and x2d.is_cuda and x2d.dtype == torch.float32 and T > 0 and T % 8 == 0 and cout % 8 == 0
+            and x2d.is_contiguous() and 2.0 * T * cin * cout >= GEMM_TOKENS_MIN_FLOP):
+        out = x2d @ (w if weight_is_in_out else w.t())
+        return out if bias is None else out + bias
     lib = _abi.load()
-    cout, cin = w2d.shape
     nbytes = int(lib.conv_image_bytes(0, cin, cout, 1, 1))
-    img = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
-        _abi.check(lib.conv_prepare(w2d.detach().contiguous().data_ptr(), 0, cin, cout, 1, 1, img.data_ptr(), nbytes,
-                                    _abi.stream_handle()), "conv_prepare")
-    return _run(x, None, img, 0, 1, 1, ACT_NONE, None, cout, x.shape[2], x.shape[3], out=out,
-                in_scale=gradient_scale(x) if scale_input else None)
+    img = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+    out = torch.empty(T, cout, device=x2d.device, dtype=torch.float32)
+    cpad = (cin + 7) // 8 * 8
+    split = torch.empty(2, T * cpad, dtype=torch.int16, device=x2d.device)
+    sc = gradient_scale(x2d) if scale_input else None
+    b = None if bias is None else bias.detach().contiguous()
+    with torch.cuda.device(x2d.device):
+        _abi.check(lib.conv_prepare(w.detach().contiguous().data_ptr(), 2 if weight_is_in_out else 0, cin, cout, 1, 1,
+                                    img.data_ptr(), nbytes, _abi.stream_handle()), "conv_prepare")
+        _abi.check(lib.gemm_tokens_forward(x2d.data_ptr(), T, cin, _abi.ptr(b), out.data_ptr(), cout, img.data_ptr(),
+                                           split[0].data_ptr(), split[1].data_ptr(), _abi.ptr(sc), _abi.stream_handle()),
+                   "gemm_tokens_forward")
+    _abi.count_launches(3)
+    return out
 
 
 class _ConvTrainFn(torch.autograd.Function):

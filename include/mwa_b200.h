@@ -278,6 +278,13 @@ MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bi
  *           aux: fp32 NCHW (B, Cout, Ho, Wo) with batch stride aux_batch_stride; out2 likewise.
  *   in_scale  NULL, or a DEVICE scalar s (a power of two): the fp32 input is multiplied by s before it is split and the
  *           result divided by s -- for inputs far below fp16's normal range (the gradients of the backward pass). */
+/* gemm_tokens_forward : out[t, :] = W x[t, :] + bias for T token rows (token-major, the layout of the attention backward's
+ *   scratch tensors) on the convolution kernel: x (T, Cin), out (T, Cout) fp32 row-major, T % 8 == 0, Cout % 8 == 0; `image`
+ *   from conv_prepare(k = 1: kind 0 with W (Cout, Cin), or kind 2 with W given as (Cin, Cout)); split_hi / split_lo scratch of
+ *   T * round_up(Cin, 8) * 2 bytes each; in_scale as for conv_forward_ex.  Replaces the library GEMMs
+ *   qkv = xw Wqkv^T + b, dao = dy Wproj, dxw = dqkv Wqkv of the attention backward. */
+MWA_API int gemm_tokens_forward(const float* x, int64_t T, int Cin, const float* bias, float* out, int Cout, const void* image,
+                                void* split_hi, void* split_lo, const float* in_scale, void* stream);
 /* conv_act_split : fp32 NCHW (B, C, H, W; batch stride x_batch_stride) -> the fp16 hi / lo planes of conv_forward_ex's
  *   x == NULL input, at channel offset out_coff of buffers with channel pitch out_cstride (how an activation that was NOT
  *   produced by one of these convolutions -- GDN, attention, a PixelShuffle -- enters a chain or a support buffer). */
