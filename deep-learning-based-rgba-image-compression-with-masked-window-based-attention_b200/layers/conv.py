@@ -233,11 +233,11 @@ def gradient_scale(g):
 def gemm_tokens(x2d, w, bias=None, weight_is_in_out=False, scale_input=False):
     """out (T, Cout) = x2d (T, Cin) @ W^T (+ bias) on the convolution kernel (gemm_tokens_forward): the token GEMMs of the
     attention backward.  W is (Cout, Cin), or -- weight_is_in_out -- given as (Cin, Cout) and used as it lies (out = x2d @ w).
-    Shapes the kernel does not take (T % 8, Cout % 8) and small problems (< 2 GFLOP: the split + prepare launches cost more
+    Shapes the kernel does not take (T % 32, Cout % 8) and small problems (< 2 GFLOP: the split + prepare launches cost more
     than the library's fp32 GEMM there, measured on the 4x4-window layer and on 256x256 crops) go to the library GEMM."""
     T, cin = x2d.shape
     cout = w.shape[1] if weight_is_in_out else w.shape[0]
-    if not (USE_KERNEL and x2d.is_cuda and x2d.dtype == torch.float32 and T > 0 and T % 8 == 0 and cout % 8 == 0
+    if not (USE_KERNEL and x2d.is_cuda and x2d.dtype == torch.float32 and T > 0 and T % 32 == 0 and cout % 8 == 0
             and x2d.is_contiguous() and 2.0 * T * cin * cout >= GEMM_TOKENS_MIN_FLOP):
         out = x2d @ (w if weight_is_in_out else w.t())
         return out if bias is None else out + bias

@@ -279,7 +279,7 @@ MWA_API int conv_forward(const float* x, int64_t x_batch_stride, const float* bi
  *   in_scale  NULL, or a DEVICE scalar s (a power of two): the fp32 input is multiplied by s before it is split and the
  *           result divided by s -- for inputs far below fp16's normal range (the gradients of the backward pass). */
 /* gemm_tokens_forward : out[t, :] = W x[t, :] + bias for T token rows (token-major, the layout of the attention backward's
- *   scratch tensors) on the convolution kernel: x (T, Cin), out (T, Cout) fp32 row-major, T % 8 == 0, Cout % 8 == 0; `image`
+ *   scratch tensors) on the convolution kernel: x (T, Cin), out (T, Cout) fp32 row-major, T % 32 == 0, Cout % 8 == 0; `image`
  *   from conv_prepare(k = 1: kind 0 with W (Cout, Cin), or kind 2 with W given as (Cin, Cout)); split_hi / split_lo scratch of
  *   T * round_up(Cin, 8) * 2 bytes each; in_scale as for conv_forward_ex.  Replaces the library GEMMs
  *   qkv = xw Wqkv^T + b, dao = dy Wproj, dxw = dqkv Wqkv of the attention backward. */
