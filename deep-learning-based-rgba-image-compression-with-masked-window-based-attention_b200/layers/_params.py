@@ -92,4 +92,9 @@ def invalidate_param_blocks(model: torch.nn.Module) -> int:
         if isinstance(m, ParamBlockOwner):
             m.invalidate_param_block()
             n += 1
+        for name in ("_img", "_dimg"):                 # prepared weight images of the convolutions (layers/conv.py)
+            img = m.__dict__.get(name)
+            if img is not None and hasattr(img, "invalidate"):
+                img.invalidate()
+                n += 1
     return n

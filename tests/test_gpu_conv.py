@@ -266,3 +266,18 @@ def test_input_gradient_of_tiny_gradients_keeps_fp32_accuracy(pkg, cuda_dev):
     ref = torch.nn.functional.conv_transpose2d(go.double().cpu(), m.weight.double().cpu(), padding=1).float()
     err = (x.grad.detach().cpu() - ref).abs().max() / ref.abs().max()
     assert float(err) < 1e-5, float(err)
+
+
+def test_weight_image_follows_data_writes_after_invalidate(pkg, cuda_dev):
+    """a write through .data changes neither the pointer nor the version counter: invalidate_param_blocks() is the
+    documented way to make the cached operand images follow it"""
+    m = pkg.conv.Conv2d(16, 16, 3, padding=1).to(cuda_dev)
+    x = torch.randn(1, 16, 8, 16, device=cuda_dev)
+    with torch.no_grad():
+        y0 = m(x)
+        m.weight.data.mul_(2.0)
+        assert pkg.invalidate_param_blocks(m) >= 1
+        y1 = m(x)
+        ref = F.conv2d(x.cpu(), m.weight.cpu(), m.bias.cpu(), padding=1)
+    torch.testing.assert_close(y1.cpu(), ref, rtol=1e-3, atol=1e-4)
+    assert not torch.allclose(y0, y1)
