@@ -25,6 +25,7 @@ data_parallel = importlib.import_module(PACKAGE_NAME + ".data_parallel")
 conv = importlib.import_module(PACKAGE_NAME + ".layers.conv")
 codec = importlib.import_module(PACKAGE_NAME + ".codec")
 metrics = importlib.import_module(PACKAGE_NAME + ".metrics")
+pipeline = importlib.import_module(PACKAGE_NAME + ".pipeline")
 _params = importlib.import_module(PACKAGE_NAME + ".layers._params")
 
 GDN = GDN_mod.GDN
@@ -50,6 +51,7 @@ GradientAllReduce = data_parallel.GradientAllReduce
 RGBACodec = codec.AutoEncoder
 masked_ms_ssim = metrics.masked_ms_ssim
 masked_psnr = metrics.masked_psnr
+HostPipeline = pipeline.HostPipeline
 invalidate_param_blocks = _params.invalidate_param_blocks
 MwaB200Error = _abi.MwaB200Error
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_V1 = (_abi.ALGO_AUTO, _abi.ALGO_SIMT, _abi.ALGO_TCGEN05,

@@ -127,3 +127,24 @@ def test_compress_decompress_round_trip(pkg, cuda_dev, model_keys):
         one = net.compress(image[:1], alpha[:1])
         rec1 = net.decompress(one["strings"], one["shape"], alpha[:1])["x_hat"]
     assert torch.equal(rec1, rec[:1])
+
+
+def test_host_pipeline_equals_direct_forward(pkg, cuda_dev, model_keys):
+    """HostPipeline: copies on side streams around the forward; every batch's reconstruction lands in its pinned host
+    buffer and equals the forward called directly"""
+    cfg = next(iter(G.MODEL_CASES.values()))
+    p = G.model_inputs(cfg)
+    net = _codec(pkg, model_keys, cfg["seed"], cuda_dev)
+    rgba = torch.cat([p["image"], p["alpha"]], 1)
+    batches = [rgba.pin_memory(), rgba.flip(3).contiguous().pin_memory(), rgba.flip(2).contiguous().pin_memory()]
+    outs = [torch.zeros(1, 3, cfg["H"], cfg["W"]).pin_memory() for _ in batches]
+    pipe = pkg.HostPipeline(net)
+    res = pipe.run(batches, outs)
+    torch.cuda.synchronize()
+    assert len(res) == 3
+    with torch.no_grad():
+        for hb, out in zip(batches, outs):
+            d = hb.to(cuda_dev)
+            me = net.EncMakeMask(d[:, 3:4])
+            want = net(d[:, :3], d[:, 3:4], d[:, 3:4], me[0], me[1], me[2], me[3])[0]
+            assert torch.equal(out, want.cpu())
