@@ -9,6 +9,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mwa_b200 as pkg  # noqa: E402
 
+if os.environ.get("MWA_LIB"):              # A/B against a variant library
+    pkg._abi.LIB_PATH = os.path.abspath(os.environ["MWA_LIB"])
+
 B, H, W = 16, 512, 768
 # kind, cin, cout, k, stride, h, w, act, residual
 CASES = {
@@ -40,6 +43,19 @@ with torch.no_grad():
         xs = pkg.conv.split_into(x, pkg.conv.SplitAct.empty(B, cin, h, w, 2 if (kind == "conv" and s == 2) else 1, dev))
     for _ in range(4):
         y = m(xs, act=act, residual=r, emit_ps=1) if planes else m(x, act=act, residual=r)
+    if "time" in sys.argv:                 # CUDA-event time per launch (not under ncu)
+        big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for _ in range(10):
+            big.zero_()                    # flush L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = m(xs, act=act, residual=r, emit_ps=1) if planes else m(x, act=act, residual=r)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        print(f"{what:8s} {'planes' if planes else 'dense '} median {ts[len(ts) // 2] * 1e3:8.1f} us   min {ts[0] * 1e3:8.1f} us")
 torch.cuda.synchronize()
 y = y.dense if hasattr(y, "dense") else y
 print("done", float(y.abs().mean()))
