@@ -27,6 +27,8 @@ _SIGNATURES = {
     "gdn_param_bytes": (c_int64, [c_int]),
     "gdn_prepare": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int64, c_void_p]),
     "gdn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "gdn_forward_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
     "gdn_backward_workspace_bytes": (c_int64, [c_int64, c_int, c_int64]),
     "gdn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p]),

@@ -82,6 +82,13 @@ class DSE(nn.Module):
         return self.output_conv(s, residual=x)
 
 
+def _gdn_into(gdn, x, consumer):
+    """gdn(x) for the convolution `consumer`: as the fp16 hi / lo planes it reads when both take their B200 paths
+    (gdn_forward_planes: no fp32 result, no split launch), else the dense tensor"""
+    ps = consumer.input_ps(x) if torch.is_tensor(x) and x.dim() == 4 and x.shape[1] == consumer.in_channels else None
+    return gdn.request_planes(ps)(x) if ps else gdn(x)
+
+
 class Analysis_transform(nn.Module):
     """layers/TransformRGB.py:52-75"""
 
@@ -98,10 +105,11 @@ class Analysis_transform(nn.Module):
         self.attention2 = Win_noShift_Attention(dim=M, num_heads=8, window_size=4, shift_size=2)
 
     def forward(self, input, mask, me1, me2, me3, me4):
-        y = self.gdn1(self.x1(input))
+        # a GDN whose only consumer is a convolution on the kernel writes that convolution's input planes directly
+        y = _gdn_into(self.gdn1, self.x1(input), self.x2)
         y = self.gdn2(self.x2(y))
         y = self.attention1(y, me2)
-        y = self.gdn3(self.x3(y))
+        y = _gdn_into(self.gdn3, self.x3(y), self.x4)
         return self.attention2(self.x4(y), me3)
 
 
@@ -123,10 +131,10 @@ class Synthesis_transform(nn.Module):
 
     def forward(self, input, reconmask, md1, md2, md3, md4):
         y = self.attention1(input, md3)
-        y = self.igdn1(self.x1(y))
+        y = _gdn_into(self.igdn1, self.x1(y), self.x2)
         y = self.igdn2(self.x2(y))
         y = self.attention2(y, md2)
-        y = self.igdn3(self.x3(y))
+        y = _gdn_into(self.igdn3, self.x3(y), self.x4)
         return self.dse(self.x4(y))
 
 

@@ -7,6 +7,8 @@
 
 namespace b200 {
 
+int gdn_forward_planes_tc(const float* x, void* out_hi, void* out_lo, int ps, int cstride, const void* params, int64_t n_img,
+                          int C, int H, int W, int inverse, cudaStream_t st);
 int gdn_forward_tc(const float* x, float* y, const void* params, int64_t n_img, int C, int64_t hw, int inverse,
                    int channels_last, cudaStream_t st);   // gdn_tc.cu
 bool gdn_tc_supported(int C, int64_t hw, int channels_last);
@@ -466,6 +468,16 @@ int gdn_forward(const float* x, float* y, const void* params, int64_t n_img, int
     if (C <= 256) return launch_gdn_simt<64>(x, y, params, n_img, C, hw, inverse, channels_last, st);
     if (C <= 512) return launch_gdn_simt<128>(x, y, params, n_img, C, hw, inverse, channels_last, st);
     return MWA_ERR_UNSUPPORTED;
+}
+
+int gdn_forward_planes(const float* x, void* out_hi, void* out_lo, int ps, int out_cstride, const void* params, int64_t n_img,
+                       int C, int H, int W, int inverse, void* stream) {
+    if (n_img < 0 || H < 0 || W < 0 || C <= 0) return MWA_ERR_INVALID;
+    if (n_img == 0 || H == 0 || W == 0) return MWA_OK;
+    if (!x || !out_hi || !out_lo || !params) return MWA_ERR_INVALID;
+    if (!aligned16(x) || !aligned16(out_hi) || !aligned16(out_lo)) return MWA_ERR_ALIGNMENT;
+    return gdn_forward_planes_tc(x, out_hi, out_lo, ps, out_cstride, params, n_img, C, H, W, inverse,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int64_t gdn_backward_workspace_bytes(int64_t n_img, int C, int64_t hw) {

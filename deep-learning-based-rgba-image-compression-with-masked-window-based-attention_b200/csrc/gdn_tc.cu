@@ -66,6 +66,11 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                  : "l"(p));
     return v;
 }
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -76,10 +81,18 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool kInverse, bool kNHWC>
+// Where the result goes when the consumer is a convolution of csrc/conv_tc.cu (gdn_forward_planes): the fp16 hi / lo planes its
+// TMA reads, [n_img][ps * ps][H / ps][W / ps][cstride] channels last -- the same values conv_act_split would produce from y.
+struct GdnPlanes {
+    uint16_t* hi;
+    uint16_t* lo;
+    int W, hp, wp, sh, cstride;          // sh = ps - 1 (ps is 1 or 2), hp = H / ps, wp = W / ps
+};
+
+template <bool kInverse, bool kNHWC, bool kPlanes = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ blk, int64_t hw,
-              int64_t tiles_per_img, int64_t num_tiles) {
+              int64_t tiles_per_img, int64_t num_tiles, const GdnPlanes sp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
@@ -309,6 +322,14 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                 __syncthreads();       // staging lives in the A ring: the next tile's operand stores must wait
             } else {
             float* yc = y + (img * kC + cg * 16) * hw + p0 + p;
+            int64_t spo = 0;
+            if constexpr (kPlanes) {
+                // this pixel's row of the planes: 32 contiguous bytes of hi and of lo per 16-channel group
+                const int64_t pp = valid ? p0 + p : 0;
+                const int oy = int(pp / sp.W), ox = int(pp - int64_t(oy) * sp.W);
+                const int plane = ((oy & sp.sh) << sp.sh) + (ox & sp.sh);
+                spo = ((((img << (2 * sp.sh)) + plane) * sp.hp + (oy >> sp.sh)) * sp.wp + (ox >> sp.sh)) * sp.cstride + cg * 16;
+            }
 #pragma unroll
             for (int kc = 0; kc < kChunks; ++kc) {
                 uint32_t acc[16], xv[16];
@@ -322,6 +343,30 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                                      : "=f"(bt[4 * j]), "=f"(bt[4 * j + 1]), "=f"(bt[4 * j + 2]), "=f"(bt[4 * j + 3])
                                      : "r"(s_beta + 4 * (ch0 + 4 * j)));
                 tmem_wait_ld();
+                if constexpr (kPlanes) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float n = __uint_as_float(acc[2 * j + i]) + bt[2 * j + i];
+                            float r;
+                            if (kInverse) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
+                            else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
+                            v[i] = __uint_as_float(xv[2 * j + i]) * r;
+                        }
+                        hi[j] = pack_f16x2(v[0], v[1]);
+                        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+                        lo[j] = pack_f16x2(v[0] - hf.x, v[1] - hf.y);
+                    }
+                    if (valid) {
+                        uint16_t* ph = sp.hi + spo + kc * kChunkK;
+                        uint16_t* pl = sp.lo + spo + kc * kChunkK;
+                        st_global_v8(ph, hi);         // one full 32-byte sector per lane and instruction (STG.256)
+                        st_global_v8(pl, lo);
+                    }
+                } else {
                 float* yj = yc;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -333,6 +378,7 @@ gdn_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t*
                     yj += hw;
                 }
                 yc += chunk_stride;
+                }
             }
             }
         }
@@ -350,12 +396,12 @@ bool gdn_tc_supported(int C, int64_t hw, int channels_last) {
     return C == kC && hw >= 1;
 }
 
-template <bool kInverse, bool kNHWC>
+template <bool kInverse, bool kNHWC, bool kPlanes = false>
 static int launch_gdn_tc(const float* x, float* y, const uint8_t* blk, int64_t hw, int64_t tiles_per_img,
-                         int64_t num_tiles, int grid, int smem, cudaStream_t st) {
-    MWA_TRY_CUDA(cudaFuncSetAttribute(gdn_tc_kernel<kInverse, kNHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                         int64_t num_tiles, int grid, int smem, cudaStream_t st, const GdnPlanes& sp = GdnPlanes{}) {
+    MWA_TRY_CUDA(cudaFuncSetAttribute(gdn_tc_kernel<kInverse, kNHWC, kPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                  "gdn_forward(tc attr)");
-    gdn_tc_kernel<kInverse, kNHWC><<<grid, kThreads, smem, st>>>(x, y, blk, hw, tiles_per_img, num_tiles);
+    gdn_tc_kernel<kInverse, kNHWC, kPlanes><<<grid, kThreads, smem, st>>>(x, y, blk, hw, tiles_per_img, num_tiles, sp);
     return check_launch("gdn_forward(tcgen05)");
 }
 
@@ -372,6 +418,26 @@ int gdn_forward_tc(const float* x, float* y, const void* params, int64_t n_img, 
                              : launch_gdn_tc<true, false>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st);
     return channels_last ? launch_gdn_tc<false, true>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st)
                          : launch_gdn_tc<false, false>(x, y, blk, hw, tiles_per_img, num_tiles, grid, smem, st);
+}
+
+// GDN whose consumer is a convolution: the result as that convolution's fp16 hi / lo input planes (no fp32 tensor, no
+// conv_act_split launch in between).  NCHW fp32 input, C == 192.
+int gdn_forward_planes_tc(const float* x, void* out_hi, void* out_lo, int ps, int cstride, const void* params, int64_t n_img,
+                          int C, int H, int W, int inverse, cudaStream_t st) {
+    const int64_t hw = int64_t(H) * W;
+    if (!gdn_tc_supported(C, hw, 0)) return MWA_ERR_UNSUPPORTED;
+    if ((ps != 1 && ps != 2) || H % ps != 0 || W % ps != 0 || cstride < C || cstride % 16 != 0) return MWA_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 31) return MWA_ERR_ALIGNMENT;
+    const int64_t tiles_per_img = (hw + kTileM - 1) / kTileM;
+    const int64_t num_tiles = n_img * tiles_per_img;
+    const int grid = static_cast<int>(num_tiles < kNumSMs ? num_tiles : kNumSMs);
+    const int smem = Smem::total + 1024;
+    GdnPlanes sp;
+    sp.hi = static_cast<uint16_t*>(out_hi); sp.lo = static_cast<uint16_t*>(out_lo);
+    sp.W = W; sp.sh = ps - 1; sp.hp = H / ps; sp.wp = W / ps; sp.cstride = cstride;
+    const uint8_t* blk = static_cast<const uint8_t*>(params);
+    if (inverse) return launch_gdn_tc<true, false, true>(x, nullptr, blk, hw, tiles_per_img, num_tiles, grid, smem, st, sp);
+    return launch_gdn_tc<false, false, true>(x, nullptr, blk, hw, tiles_per_img, num_tiles, grid, smem, st, sp);
 }
 
 }  // namespace b200

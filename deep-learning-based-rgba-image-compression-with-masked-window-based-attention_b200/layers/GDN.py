@@ -162,6 +162,7 @@ class GDN(ParamBlockOwner, nn.Module):
         self.reparam_offset = reparam_offset
         self.algo = _abi.ALGO_AUTO
         self._blk = ParamBlock()
+        self._emit_ps = 0
         self.build(ch)
 
     def build(self, ch):
@@ -183,7 +184,39 @@ class GDN(ParamBlockOwner, nn.Module):
 
         return self._blk.get((beta, gamma), nbytes, fill)
 
+    def _planes_ok(self, x):
+        """the call can hand its result to a convolution of this package as fp16 hi / lo planes (gdn_forward_planes): inference
+        (no autograd history) on a dense fp32 NCHW CUDA tensor with the 192 channels of the tcgen05 kernel"""
+        if torch.is_grad_enabled() and (x.requires_grad or self.beta.requires_grad or self.gamma.requires_grad):
+            return False
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 192 and x.numel() > 0
+                and x.is_contiguous() and self.algo in (_abi.ALGO_AUTO, _abi.ALGO_TCGEN05))
+
+    def forward_planes(self, inputs, ps):
+        """GDN for a convolution consumer (layers/TransformRGB.py:55-61, :81-88: gdn -> x2 / x4): returns the SplitAct that
+        convolution reads (ps = 2 for a stride-2 consumer) -- the fp32 result is never written and no split launch runs."""
+        from .conv import SplitAct
+        lib = _abi.load()
+        B, C, H, W = inputs.shape
+        self._refresh_if_training()
+        with torch.cuda.device(inputs.device):
+            blk = self._param_block(self.beta, self.gamma)
+            sp = SplitAct.empty(B, C, H, W, ps, inputs.device)
+            _abi.check(lib.gdn_forward_planes(inputs.data_ptr(), sp.hi.data_ptr(), sp.lo.data_ptr(), ps, sp.cstride,
+                                              blk.data_ptr(), B, C, H, W, int(self.inverse), _abi.stream_handle()),
+                       "gdn_forward_planes")
+        return sp
+
+    def request_planes(self, ps):
+        """one-shot request (the reference's forward signature stays as it is): the NEXT forward call returns the SplitAct
+        a convolution of this package reads (ps = 2 for a stride-2 consumer) if it can produce it, else the dense result"""
+        self._emit_ps = int(ps)
+        return self
+
     def forward(self, inputs):
+        emit_ps, self._emit_ps = self._emit_ps, 0
+        if emit_ps and inputs.dim() == 4 and self._planes_ok(inputs):
+            return self.forward_planes(inputs, emit_ps)
         unfold = False
         if inputs.dim() == 5:
             unfold = True

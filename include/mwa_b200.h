@@ -72,6 +72,13 @@ MWA_API int gdn_prepare(const float* beta_p, const float* gamma_p, int C, float 
                 float pedestal, void* params, int64_t params_bytes, void* stream);
 MWA_API int gdn_forward(const float* x, float* y, const void* params, int64_t n_img, int C, int64_t hw, int inverse,
                 int channels_last, int algo, void* stream);
+/* gdn_forward_planes : the same GDN / IGDN whose consumer is a convolution of this library (layers/TransformRGB.py:55-61,
+ *                 :81-88 -- gdn1 -> x2, gdn3 -> x4, igdn1 -> x2, igdn3 -> x4): y is written ONLY as the fp16 hi / lo planes
+ *                 that convolution's TMA reads ([n_img][ps*ps][H/ps][W/ps][out_cstride] channels last, ps = 2 for a stride-2
+ *                 consumer), bit-identical to conv_act_split of gdn_forward's y; no fp32 tensor and no split launch in
+ *                 between.  x fp32 NCHW, C == 192 (tcgen05 kernel only: MWA_ERR_UNSUPPORTED otherwise). */
+MWA_API int gdn_forward_planes(const float* x, void* out_hi, void* out_lo, int ps, int out_cstride, const void* params,
+                       int64_t n_img, int C, int H, int W, int inverse, void* stream);
 MWA_API int64_t gdn_backward_workspace_bytes(int64_t n_img, int C, int64_t hw);
 MWA_API int gdn_backward(const float* x, const float* grad_y, const float* beta_p, const float* gamma_p,
                  const void* params, float beta_bound, float gamma_bound, float* grad_x, float* grad_beta_p,

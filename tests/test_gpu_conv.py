@@ -281,3 +281,40 @@ def test_weight_image_follows_data_writes_after_invalidate(pkg, cuda_dev):
         ref = F.conv2d(x.cpu(), m.weight.cpu(), m.bias.cpu(), padding=1)
     torch.testing.assert_close(y1.cpu(), ref, rtol=1e-3, atol=1e-4)
     assert not torch.allclose(y0, y1)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("ps,B,H,W", [(1, 2, 6, 10), (2, 2, 8, 12), (1, 1, 16, 24), (2, 3, 32, 48)])
+def test_gdn_writes_the_planes_its_consumer_reads(pkg, cuda_dev, inverse, ps, B, H, W):
+    """gdn_forward_planes (GDN -> convolution sites of layers/TransformRGB.py:55-61, :81-88): the planes are bit-identical to
+    conv_act_split of gdn_forward's dense result, for ragged pixel counts (60 pixels < one 128-pixel tile) and both parities"""
+    conv_mod = pkg.conv
+    g = torch.Generator().manual_seed(17 + ps + H)
+    m = pkg.GDN(192, inverse=inverse)
+    with torch.no_grad():
+        m.beta.add_(torch.rand(192, generator=g) * 0.5)
+        m.gamma.add_(torch.rand(192, 192, generator=g) * 0.02)
+        m = m.to(cuda_dev)
+        x = (torch.randn(B, 192, H, W, generator=g) * 2.0).to(cuda_dev)
+        dense = m(x)
+        want = conv_mod.split_into(dense, conv_mod.SplitAct.empty(B, 192, H, W, ps, cuda_dev))
+        got = m.request_planes(ps)(x)
+    assert isinstance(got, conv_mod.SplitAct) and got.ps == ps and got.dense is None
+    assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+    with torch.enable_grad():                                   # with autograd history the call stays dense
+        xg = x.clone().requires_grad_(True)
+        assert torch.is_tensor(m.request_planes(ps)(xg))
+
+
+def test_transform_with_gdn_planes_matches_dense_gdn(pkg, cuda_dev, monkeypatch):
+    """the analysis transform's GDN -> convolution hand-over through planes gives the result of the dense path bit for bit"""
+    torch.manual_seed(5)
+    enc = pkg.codec.Analysis_transform(192, 80).eval().to(cuda_dev)
+    x = torch.rand(1, 3, 64, 96, device=cuda_dev)
+    a = torch.ones(1, 1, 64, 96, device=cuda_dev)
+    with torch.no_grad():
+        _, me = pkg.alpha_pyramid(a, 3)
+        y = enc(x, a, None, me[1], me[2], None)
+        monkeypatch.setattr(pkg.GDN, "_planes_ok", lambda self, t: False)     # force the dense GDN + conv_act_split path
+        y_dense = enc(x, a, None, me[1], me[2], None)
+    assert torch.equal(y, y_dense)
