@@ -89,6 +89,15 @@ def _gdn_into(gdn, x, consumer):
     return gdn.request_planes(ps)(x) if ps else gdn(x)
 
 
+def _attention_into(attention, x, mask, consumer):
+    """the attention wrapper for the convolution `consumer`: its gate epilogue writes the consumer's input planes when the
+    wrapper runs as the convolution chain and the consumer takes the kernel, else the dense tensor"""
+    ps = consumer.input_ps(x) if torch.is_tensor(x) and x.dim() == 4 and x.shape[1] == consumer.in_channels else None
+    if ps and attention.conv_a[0].conv[0].input_ps(x) is not None:
+        return attention.request_planes(ps)(x, mask)
+    return attention(x, mask)
+
+
 class Analysis_transform(nn.Module):
     """layers/TransformRGB.py:52-75"""
 
@@ -108,7 +117,7 @@ class Analysis_transform(nn.Module):
         # a GDN whose only consumer is a convolution on the kernel writes that convolution's input planes directly
         y = _gdn_into(self.gdn1, self.x1(input), self.x2)
         y = self.gdn2(self.x2(y))
-        y = self.attention1(y, me2)
+        y = _attention_into(self.attention1, y, me2, self.x3)
         y = _gdn_into(self.gdn3, self.x3(y), self.x4)
         return self.attention2(self.x4(y), me3)
 
@@ -130,10 +139,10 @@ class Synthesis_transform(nn.Module):
         self.dse = DSE(32)
 
     def forward(self, input, reconmask, md1, md2, md3, md4):
-        y = self.attention1(input, md3)
+        y = _attention_into(self.attention1, input, md3, self.x1)
         y = _gdn_into(self.igdn1, self.x1(y), self.x2)
         y = self.igdn2(self.x2(y))
-        y = self.attention2(y, md2)
+        y = _attention_into(self.attention2, y, md2, self.x3)
         y = _gdn_into(self.igdn3, self.x3(y), self.x4)
         return self.dse(self.x4(y))
 

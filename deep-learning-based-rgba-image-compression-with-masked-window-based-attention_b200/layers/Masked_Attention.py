@@ -107,7 +107,17 @@ class Win_noShift_Attention(nn.Module):
             conv1x1(N, N),
         )
 
+        self._emit_ps = 0
+
+    def request_planes(self, ps):
+        """one-shot request (the reference's forward signature stays as it is): if the NEXT forward call runs as the
+        convolution chain, its result comes back only as the fp16 hi / lo planes (SplitAct) that a convolution of this
+        package reads (ps = 2 for a stride-2 consumer) -- written by the gate epilogue, no fp32 tensor, no split launch"""
+        self._emit_ps = int(ps)
+        return self
+
     def forward(self, x, mask):
+        emit_ps, self._emit_ps = self._emit_ps, 0
         if self.conv_a[0].conv[0].input_ps(x) is None:            # training / uncovered: module by module
             a = self.conv_a(x)
             b = self.attn(x, mask)
@@ -119,4 +129,6 @@ class Win_noShift_Attention(nn.Module):
         b = self.attn(x, mask)
         for j in range(3):                                        # the last unit feeds only the closing 1x1: planes alone
             b = self.conv_b[j](b, emit_ps=1, want_dense=j < 2)
+        if emit_ps:
+            return self.conv_b[3](b, act=ACT_GATE, aux=a, residual=x, emit_ps=emit_ps, want_dense=False)
         return self.conv_b[3](b, act=ACT_GATE, aux=a, residual=x)

@@ -318,3 +318,23 @@ def test_transform_with_gdn_planes_matches_dense_gdn(pkg, cuda_dev, monkeypatch)
         monkeypatch.setattr(pkg.GDN, "_planes_ok", lambda self, t: False)     # force the dense GDN + conv_act_split path
         y_dense = enc(x, a, None, me[1], me[2], None)
     assert torch.equal(y, y_dense)
+
+
+@pytest.mark.parametrize("C,ws,ps", [(192, 8, 2), (192, 8, 1), (80, 4, 1)])
+def test_attention_wrapper_writes_the_planes_its_consumer_reads(pkg, cuda_dev, C, ws, ps):
+    """Win_noShift_Attention.request_planes (wrapper -> x3 / x1 sites of layers/TransformRGB.py:66-70, :91-97): the gate
+    epilogue's planes are bit-identical to conv_act_split of the dense result"""
+    conv_mod = pkg.conv
+    torch.manual_seed(3 + C + ps)
+    m = pkg.Win_noShift_Attention(C, num_heads=8, window_size=ws, shift_size=ws // 2).eval().to(cuda_dev)
+    B, H, W = 2, 4 * ws, 6 * ws
+    x = torch.randn(B, C, H, W, device=cuda_dev)
+    alpha = (torch.rand(B, 1, H, W, device=cuda_dev) > 0.3).float()
+    with torch.no_grad():
+        dense = m(x, alpha)
+        want = conv_mod.split_into(dense, conv_mod.SplitAct.empty(B, C, H, W, ps, cuda_dev))
+        got = m.request_planes(ps)(x, alpha)
+        again = m(x, alpha)                                       # the request is one-shot
+    assert isinstance(got, conv_mod.SplitAct) and got.ps == ps and got.dense is None
+    assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+    assert torch.is_tensor(again) and torch.equal(again, dense)
