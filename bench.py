@@ -337,7 +337,7 @@ def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None
                 torch.cuda.synchronize()
         n0 = pkg._abi.launch_count
         step()
-        conv_launches = pkg._abi.launch_count - n0               # convolution kernels + plane splits of one forward
+        conv_launches = pkg._abi.launch_count - n0               # convolution kernels + plane splits + rate terms of one forward
         timer.on = True
         ms_per_step, t0, t1 = timed_steps(step, steps, 0, D)
         timer.on = False
@@ -694,8 +694,9 @@ def main():
             "roofline": roofline, "roofline_gdn": gdn_r, "rooflines": roofs, "cpu_baseline": cpu, "e2e": fwd["e2e"],
             "gpu_launches": hot_launches,
             "gpu_launches_note": f"{per_forward} launches of this repo's kernels per forward: {LAUNCHES_PER_FORWARD} hot-path launches "
-                                 f"(alpha pyramids, attention, GDN, z rounding) + {fwd['conv_launches']} convolution / plane-split "
-                                 "launches counted by the binding; the entropy-model bpp terms are torch elementwise kernels",
+                                 f"(alpha pyramids, attention, GDN, z rounding) + {fwd['conv_launches']} convolution / plane-split / "
+                                 "rate-term launches counted by the binding (the masked squared error and the bpp terms are "
+                                 "rate_forward's four launches)",
             "clocks": fwd["clocks"], "per_op_ms": fwd["per_op_ms"], "hot_path_ms_per_step": fwd["hot_path_ms_per_step"],
         }
         line.update(extra)

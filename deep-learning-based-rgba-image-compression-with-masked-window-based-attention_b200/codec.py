@@ -479,8 +479,38 @@ class AutoEncoder(nn.Module):
         x_hat = self.Decoder(y_hat, reconmask, None, md[1], md[2], None)
         return dict(y=y, z=z, z_hat=z_hat, y_hat=y_hat, means=means, scales=scales, x_hat=x_hat)
 
+    def _rate_terms_fused(self, input, mask, r):
+        """mse, y bpp, z bpp, total bpp in four launches of csrc/rate.cu (rate_forward) -- inference on CUDA with the
+        factorised prior's standard filters; None when the call has to stay with the torch expressions below"""
+        eb = self.entropy_bottleneck
+        if torch.is_grad_enabled() or not input.is_cuda or eb.nlayers != 5 or tuple(eb._matrix1.shape[1:]) != (3, 3):
+            return None
+        from . import _abi
+        import ctypes
+        lib = _abi.load()
+        y, scales, means, z_hat, x_hat = (r[k].contiguous() for k in ("y", "scales", "means", "z_hat", "x_hat"))
+        inp, m = input.contiguous(), mask.contiguous()
+        if any(t.dtype != torch.float32 for t in (y, scales, means, z_hat, x_hat, inp, m)) or m.numel() != inp.numel() // inp.shape[1]:
+            return None
+        B, C, H, W = inp.shape
+        names = [f"_matrix{i}" for i in range(5)] + [f"_bias{i}" for i in range(5)] + [f"_factor{i}" for i in range(4)]
+        params = [getattr(eb, n).detach().contiguous() for n in names]
+        ptrs = (ctypes.c_void_p * 14)(*[p.data_ptr() for p in params])
+        ws = torch.empty(int(lib.rate_workspace_bytes(B)) // 8, dtype=torch.float64, device=inp.device)
+        out = torch.empty(4, dtype=torch.float32, device=inp.device)
+        with torch.cuda.device(inp.device):
+            _abi.check(lib.rate_forward(inp.data_ptr(), x_hat.data_ptr(), m.data_ptr(), B, C, H, W, y.data_ptr(),
+                                        scales.data_ptr(), means.data_ptr(), y.numel(), z_hat.data_ptr(), ptrs,
+                                        z_hat.shape[1], z_hat.shape[2] * z_hat.shape[3], ws.data_ptr(), ws.numel() * 8,
+                                        out.data_ptr(), _abi.stream_handle()), "rate_forward")
+        _abi.count_launches(4)
+        return out
+
     def forward(self, input, mask, reconmask, me1, me2, me3, me4):
         r = self.detail(input, mask, reconmask, me2, me3)
+        t = self._rate_terms_fused(input, mask, r)
+        if t is not None:
+            return r["x_hat"], t[0], t[3], t[1], t[2]
         y_bits = _bits(self.gaussian_conditional.likelihood(r["y"], r["scales"], r["means"]))
         z_bits = _bits(self.entropy_bottleneck.likelihood(r["z_hat"]))
         mse_loss = reconstruct_error(input, r["x_hat"], mask, reconmask)

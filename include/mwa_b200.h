@@ -335,6 +335,20 @@ MWA_API int rans_decode_with_indexes(const uint8_t* stream, int64_t nbytes, int6
                                      const int32_t* cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
                                      int ncdf, int32_t* symbols_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rate / distortion terms of the forward (csrc/rate.cu)   replaces  models/AutoEncoderRGB_Journal.py:36-64 (reconstruct_error)
+ * and :283-291 (bits of y under the Gaussian conditional, of z under the factorised prior, bpp), which the reference runs
+ * as ~90 elementwise / reduction / batched-GEMM launches: one pass per term + a finalize launch, inference only.
+ *   input, x_hat (B, C, H, W), mask (B, 1, H, W): squared error over the pixels with mask > 0, per image / (C * count), mean;
+ *   y, scales, means: n_y elements each;   z_hat (B, Cz, hw_z) with eb_params = HOST array of 14 device pointers
+ *   [_matrix0.._matrix4, _bias0.._bias4, _factor0.._factor3] of the factorised prior with filters (3, 3, 3, 3);
+ *   out4 (device) = [mse, y bpp, z bpp, y bpp + z bpp], bpp = bits / (B * H * W).  workspace: rate_workspace_bytes(B), 8-aligned.
+ * ------------------------------------------------------------------------------------------------ */
+MWA_API int64_t rate_workspace_bytes(int B);
+MWA_API int rate_forward(const float* input, const float* x_hat, const float* mask, int B, int C, int H, int W, const float* y,
+                 const float* scales, const float* means, int64_t n_y, const float* z_hat, const float* const* eb_params,
+                 int Cz, int64_t hw_z, void* workspace, int64_t workspace_bytes, float* out4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,28 @@ def test_host_pipeline_equals_direct_forward(pkg, cuda_dev, model_keys):
             me = net.EncMakeMask(d[:, 3:4])
             want = net(d[:, :3], d[:, 3:4], d[:, 3:4], me[0], me[1], me[2], me[3])[0]
             assert torch.equal(out, want.cpu())
+
+
+def test_fused_rate_terms_match_the_torch_expressions(pkg, cuda_dev, model_keys, monkeypatch):
+    """rate_forward (csrc/rate.cu) against the same forward with the rate / distortion tail as torch expressions
+    (models/AutoEncoderRGB_Journal.py:36-64, :283-291; CompressAI's likelihood formulas): mse, bpp, y bpp, z bpp"""
+    name = next(iter(G.MODEL_CASES))
+    cfg = G.MODEL_CASES[name]
+    p = G.model_inputs(cfg)
+    net = _codec(pkg, model_keys, cfg["seed"], cuda_dev)
+    with torch.no_grad():                       # a prior that is not at its initialisation: every parameter perturbed
+        gen = torch.Generator().manual_seed(11)
+        for n_, t in net.entropy_bottleneck.named_parameters():
+            if n_ != "quantiles":
+                t.add_((torch.randn(t.shape, generator=gen) * 0.3).to(cuda_dev))
+    image, alpha, recon = (p[k].to(cuda_dev) for k in ("image", "alpha", "reconmask"))
+    with torch.no_grad():
+        me = net.EncMakeMask(alpha)
+        fused = net(image, alpha, recon, me[0], me[1], me[2], me[3])
+        monkeypatch.setattr(type(net), "_rate_terms_fused", lambda self, *a: None)
+        plain = net(image, alpha, recon, me[0], me[1], me[2], me[3])
+    assert torch.equal(fused[0], plain[0])
+    for a, b, what in zip(fused[1:], plain[1:], ("mse", "bpp", "y bpp", "z bpp")):
+        assert a.shape == b.shape == torch.Size([]), what
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-9, msg=lambda m: f"{what}: {m}")
+    assert float(fused[3]) > 0 and float(fused[4]) > 0
