@@ -384,7 +384,10 @@ def leg_forward(pkg, dev, rank, world, D, args, pk, tf32_convs=False, steps=None
                       "achieved": px * 1536 / (msg * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                       "frac": px * 1536 / (msg * 1e-3) / 1e9 / pk["hbm"],
                       "traffic": tg["dram_bytes_per_step"] if tg else None, "traffic_source": tg["source"] if tg else None,
-                      "ms_per_step": msg})
+                      "ms_per_step": msg,
+                      "note": "1536 B per pixel (fp32 in, 4 B per element out); gdn1 / gdn3 / igdn1 / igdn3 write the fp16 hi / lo "
+                              "planes their consumer convolution reads (gdn_forward_planes: same bytes, no fp32 tensor and no "
+                              "split launch behind them), gdn2 / igdn2 the dense tensor the attention reads"})
     hot_ms = sum(per_op.values())
 
     # ---- e2e: RGBA batch from pinned host memory -> H2D -> forward -> x_hat D2H, all inside the timed region

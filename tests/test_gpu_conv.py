@@ -24,6 +24,9 @@ CASES = [
     ("conv", 32, 32, 3, 1, 1, 40, 48, 2, False, True),        # DSE: ReLU
     ("conv", 32, 3, 1, 1, 1, 40, 48, 0, True, True),          # DSE output conv + identity
     ("conv", 64, 64, 3, 1, 1, 8, 16, 0, False, False),        # no bias
+    ("conv", 96, 192, 1, 1, 1, 6, 128, 1, True, True),        # 1x1 tiles follow the width: 1 x 128 pixels
+    ("conv", 192, 96, 1, 1, 1, 5, 192, 1, False, True),       # 2 x 64 pixels, ragged last tile row
+    ("conv", 32, 3, 1, 1, 1, 3, 256, 0, True, True),          # 1 x 128 pixels, 3 output channels
     ("deconv", 192, 192, 5, 2, 1, 16, 24, 0, False, True),    # synthesis x2 / x3
     ("deconv", 192, 3, 5, 2, 2, 12, 20, 0, False, True),      # synthesis x4: 3 output channels, ragged tiles
 ]
