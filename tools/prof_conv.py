@@ -19,6 +19,8 @@ CASES = {
     "ru3x3": ("conv", 96, 96, 3, 1, H // 4, W // 4, 1, False),
     "ru1x1b": ("conv", 96, 192, 1, 1, H // 4, W // 4, 1, True),
     "dse3x3": ("conv", 32, 32, 3, 1, H, W, 2, False),
+    "dseout": ("conv", 32, 3, 1, 1, H, W, 0, True),
+    "x4": ("conv", 192, 80, 1, 1, H // 8, W // 8, 0, False),
     "cc0": ("conv", 120, 224, 3, 1, H // 8, W // 8, 1, False),
     "cc2": ("conv", 224, 128, 3, 1, H // 8, W // 8, 1, False),
     "cc4": ("conv", 128, 8, 3, 1, H // 8, W // 8, 0, False),
