@@ -214,7 +214,7 @@ class GDN(ParamBlockOwner, nn.Module):
         return self
 
     def forward(self, inputs):
-        emit_ps, self._emit_ps = self._emit_ps, 0
+        emit_ps, self._emit_ps = getattr(self, "_emit_ps", 0), 0
         if emit_ps and inputs.dim() == 4 and self._planes_ok(inputs):
             return self.forward_planes(inputs, emit_ps)
         unfold = False

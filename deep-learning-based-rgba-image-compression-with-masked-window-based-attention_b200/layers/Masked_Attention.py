@@ -117,7 +117,7 @@ class Win_noShift_Attention(nn.Module):
         return self
 
     def forward(self, x, mask):
-        emit_ps, self._emit_ps = self._emit_ps, 0
+        emit_ps, self._emit_ps = getattr(self, "_emit_ps", 0), 0
         if self.conv_a[0].conv[0].input_ps(x) is None:            # training / uncovered: module by module
             a = self.conv_a(x)
             b = self.attn(x, mask)
