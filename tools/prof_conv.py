@@ -39,12 +39,17 @@ with torch.no_grad():
     else:
         m = pkg.conv.ConvTranspose2d(cin, cout, k, stride=s, padding=k // 2, output_padding=1).to(dev)
     y = m(x, act=act)
-    r = torch.randn_like(y) if res else None
+    r = torch.randn_like(y) if (res and "nores" not in sys.argv) else None
+    kw = dict(emit_ps=1)
+    if "nodense" in sys.argv:              # attribution runs: planes only / dense only / no residual
+        kw["want_dense"] = False
+    if "noplanes" in sys.argv:
+        kw = {}
     planes = "planes" in sys.argv          # as inside a chain: planes in, dense + planes out
     if planes:
         xs = pkg.conv.split_into(x, pkg.conv.SplitAct.empty(B, cin, h, w, 2 if (kind == "conv" and s == 2) else 1, dev))
     for _ in range(4):
-        y = m(xs, act=act, residual=r, emit_ps=1) if planes else m(x, act=act, residual=r)
+        y = m(xs, act=act, residual=r, **kw) if planes else m(x, act=act, residual=r)
     if "time" in sys.argv:                 # CUDA-event time per launch (not under ncu)
         big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         ts = []
@@ -52,7 +57,7 @@ with torch.no_grad():
             big.zero_()                    # flush L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            y = m(xs, act=act, residual=r, emit_ps=1) if planes else m(x, act=act, residual=r)
+            y = m(xs, act=act, residual=r, **kw) if planes else m(x, act=act, residual=r)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -60,4 +65,4 @@ with torch.no_grad():
         print(f"{what:8s} {'planes' if planes else 'dense '} median {ts[len(ts) // 2] * 1e3:8.1f} us   min {ts[0] * 1e3:8.1f} us")
 torch.cuda.synchronize()
 y = y.dense if hasattr(y, "dense") else y
-print("done", float(y.abs().mean()))
+print("done", float(y.abs().mean()) if y is not None else "(planes only)")
